@@ -1,0 +1,163 @@
+"""Pin the CPU oracle against fixtures produced by the reference's own source
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import ssd_oracle as orc
+
+STD = (0.1, 0.1, 0.2, 0.2)
+
+
+def test_anchor_generation_matches_reference(golden):
+    g = golden("anchors")
+    a = orc.anchors_generate(**orc.STD_ANCHOR_CFG)
+    assert a.dtype == np.float32 and a.shape == (9600, 4)
+    assert np.array_equal(a, g["std_corners"])
+    # survey-time known answers
+    np.testing.assert_allclose(a[0], [-12.698076, -16.930172, 44.648075, 40.88017], rtol=1e-6)
+    np.testing.assert_allclose(a[-1], [385.28595, 241.38498, 764.914, 620.81506], rtol=1e-6)
+    tut = orc.anchors_generate(((30, 40), (15, 20), (8, 10), (4, 5)),
+                               centers_padding_from_borders_percentage=(0.025, 0.05, 0.075, 0.1),
+                               additional_square_box=True, image_shape=(480, 640))
+    assert np.array_equal(tut, g["tut_corners"])
+    odd = orc.anchors_generate(((3, 1), (2, 2)), ((1, 2), (1, 0.5, 3)), (0.3, 0.8), 0.1, False, (33, 65))
+    assert np.array_equal(odd, g["odd_once"])
+    stress = orc.anchors_generate(**orc.STRESS_ANCHOR_CFG)
+    assert tuple(g["stress_shape"]) == stress.shape == (100000, 4)
+    assert np.array_equal(stress[g["stress_rows"]], g["stress_sel"])
+    assert np.sum(stress, dtype=np.float64) == g["stress_sum"][0]
+
+
+def test_centroid_conversions(golden):
+    g = golden("anchors")
+    a = g["std_corners"]
+    c = np.stack(orc.corners_to_centroids(a[:, 0], a[:, 1], a[:, 2], a[:, 3]), 1)
+    assert np.array_equal(c, g["conv_centroids"]) and np.array_equal(c, g["std_centroids"])
+    k = np.stack(orc.centroids_to_corners(c[:, 0], c[:, 1], c[:, 2], c[:, 3]), 1)
+    assert np.array_equal(k, g["conv_corners"])
+
+
+CASES = ["cfg0", "cfg0_thr525_flip", "ties_int", "small", "label_oob"]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("literal", [True, False])
+def test_encode_matches_reference_source(golden, std_anchors, case, literal):
+    g = golden("encode_decode")
+    labels, boxes = g[case + "_gt_labels"], g[case + "_gt_boxes"]
+    thr, flip = float(g[case + "_thr"][0]), bool(g[case + "_flip"][0])
+    fn = orc.encode_image_literal if literal else orc.encode_image
+    for i in range(labels.shape[0]):
+        b = orc.flip_boxes_horizontal(boxes[i], 640) if flip else boxes[i]
+        L, O, m = fn(std_anchors, labels[i], b, 4, thr, STD)
+        assert np.array_equal(L, g[case + "_labels"][i])
+        assert np.array_equal(O, g[case + "_offsets"][i])  # same NumPy log => bit-equal here
+        assert (m >= 0).sum() == (np.abs(O).sum(1) > 0).sum() or case == "label_oob"
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_decode_matches_reference_source(golden, std_anchors, case):
+    g = golden("encode_decode")
+    anc = golden("anchors")["std_centroids"]
+    for i in range(g[case + "_offsets"].shape[0]):
+        o = g[case + "_offsets"][i]
+        assert np.array_equal(orc.decode_to_centroids(o, anc, STD), g[case + "_dec_centroids"][i])
+        assert np.array_equal(orc.decode_to_corners(o, anc, STD), g[case + "_dec_corners"][i])
+
+
+def test_encode_decode_round_trip_recovers_gt(golden, std_anchors):
+    g = golden("encode_decode")
+    anc = golden("anchors")["std_centroids"]
+    L, O, m = orc.encode_image(std_anchors, g["cfg0_gt_labels"][0], g["cfg0_gt_boxes"][0], 4, 0.5, STD)
+    dec = orc.decode_to_corners(O, anc, STD)
+    pos = np.nonzero(m >= 0)[0]
+    assert pos.size > 16
+    np.testing.assert_allclose(dec[pos], g["cfg0_gt_boxes"][0][m[pos]], atol=2e-3)
+    assert np.all(dec[m < 0] == 0)
+
+
+def test_centroid_ctor_variant(golden):
+    """datacoder.py:73-89: anchors given as centroids; corners are derived and
+    the encode re-derives centroids from those corners."""
+    g = golden("encode_decode")
+    a = golden("anchors")
+    c = a["std_centroids"]
+    corners = np.stack(orc.centroids_to_corners(c[:, 0], c[:, 1], c[:, 2], c[:, 3]), 1)
+    assert np.array_equal(corners, g["centroid_ctor_corners"])
+    L, O, _ = orc.encode_image(corners, g["cfg0_gt_labels"][0], g["cfg0_gt_boxes"][0], 4, 0.5, STD)
+    assert np.array_equal(L, g["centroid_ctor_labels"]) and np.array_equal(O, g["centroid_ctor_offsets"])
+
+
+def test_layers_decode_and_nms_wrapper(golden):
+    g = golden("layers")
+    anc = golden("anchors")["std_centroids"]
+    yxyx = orc.decode_batched_yxyx(g["offsets"], anc, STD)
+    assert np.array_equal(yxyx, g["decoded_yxyx"])
+    out, valid, aidx = orc.combined_nms(yxyx, g["scores"], 200, 200, 0.45, 0.01)
+    assert np.array_equal(out, g["det_200"])
+    out2, valid2, _ = orc.combined_nms(yxyx, g["scores"], 4, 10, 0.025, 0.2)
+    flat = out2.reshape(-1, 6)
+    assert np.array_equal(flat[flat[:, 0] > 0], g["det_bgdrop"])  # layers.py:165-166
+
+
+def test_nms_against_torchvision(golden):
+    tv = pytest.importorskip("torchvision")
+    import torch
+
+    g = golden("layers")
+    yxyx = g["decoded_yxyx"][0]
+    s = g["scores"][0, :, 1]
+    keep = orc.nms_per_class(yxyx, s, 10 ** 6, 0.45, 0.01)
+    cand = np.nonzero(s > np.float32(0.01))[0]
+    y0 = np.minimum(yxyx[:, 0], yxyx[:, 2]); y1 = np.maximum(yxyx[:, 0], yxyx[:, 2])
+    x0 = np.minimum(yxyx[:, 1], yxyx[:, 3]); x1 = np.maximum(yxyx[:, 1], yxyx[:, 3])
+    xyxy = torch.from_numpy(np.stack([x0, y0, x1, y1], 1)[cand])
+    tkeep = tv.ops.nms(xyxy, torch.from_numpy(s[cand]), 0.45).numpy()
+    assert cand[tkeep].tolist() == keep
+
+
+def test_eval_matches_reference(golden):
+    g = golden("eval")
+    N = g["pred_labels"].shape[0]
+    no_gt = int(g["no_gt_image"][0])
+    gl = [g["gt_labels"][i] if i != no_gt else np.zeros(0, np.int32) for i in range(N)]
+    gb = [g["gt_boxes"][i] if i != no_gt else np.zeros((0, 4), np.float32) for i in range(N)]
+    for i in range(N):
+        iou = orc.iou_pred_vs_true(g["pred_labels"][i], g["pred_boxes"][i], g["gt_labels"][i], g["gt_boxes"][i])
+        assert np.array_equal(iou, g["iou"][i])
+    assert np.array_equal(orc.iou_pred_vs_true(g["pred_labels"][0], g["pred_boxes"][0], [], np.zeros((0, 4))),
+                          g["iou_nogt"])
+    for thr, key in ((0.5, "ap50"), (0.6, "ap60"), (0.7, "ap70")):
+        ap = orc.average_precision(g["pred_labels"], g["pred_conf"], g["pred_boxes"], thr, gl, gb, [0, 1, 2, 3], 0)
+        np.testing.assert_allclose([ap[1], ap[2], ap[3]], g[key], rtol=0, atol=1e-12)
+        assert g[key].max() > 0
+    np.testing.assert_allclose(g["kat_iou"], [[0.935032, 0], [0, 0.74036145], [0, 0], [0, 0]], rtol=1e-6)
+
+
+def test_closed_form_equals_literal_on_tie_heavy_inputs(std_anchors):
+    """P3: closed form == concat -> unique -> sequential scatter, including
+    duplicated GT boxes and integer coordinates (many exact fp32 ties)."""
+    rng = np.random.default_rng(5)
+    n_dup = 0
+    for trial in range(12):
+        lab, box, _ = orc.synth_gt(rng, 1, 10, integer=True)
+        box[0, 4] = box[0, 2]
+        box[0, 7] = box[0, 2]
+        iou = orc.iou_matrix(std_anchors, box[0])
+        lit = orc.match_literal(iou, 0.5)
+        cf = orc.match_closed_form(iou, 0.5)
+        ref = np.full(std_anchors.shape[0], -1, np.int32)
+        for a, gidx in lit:
+            ref[a] = gidx
+        n_dup += len(lit) - len(set(lit[:, 0].tolist()))
+        assert np.array_equal(ref, cf)
+    assert n_dup > 0
+
+
+def test_csv_front_end():
+    l, b = orc.parse_gt_csv_text("1,10.5,20,30,40\r\n3,1,2,3,4\r\n")
+    assert l.tolist() == [1, 3] and b.dtype == np.float32 and b[0].tolist() == [10.5, 20, 30, 40]
+    l, b = orc.parse_gt_csv_text("", sep=None)
+    assert l.shape == (0,) and b.shape == (0, 4)
+    f = orc.flip_boxes_horizontal(np.array([[10, 5, 50, 60]], np.float32), 640)
+    assert f.tolist() == [[590, 5, 630, 60]]
