@@ -1,0 +1,129 @@
+/*
+ * ssdx.h - C ABI of libssdx.so: the B200 (sm_100a) SSD target/prediction path.
+ *
+ * The reference (matteo-stat/multi-task-learning-object-detection-semantic-
+ * segmentation, package `ssdseglib`) is pure Python and has no FFI of its own;
+ * its boundary for this path is the Python API of ssdseglib/boxes.py,
+ * datacoder.py, layers.py and evaluators.py.  Each entry point below replaces
+ * the arithmetic behind one of those Python entry points (cited as
+ * file:line); the Python mirror in
+ * multi-task-learning-object-detection-semantic-segmentation_b200/ssdseglib/
+ * binds them through ctypes (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; ssdx_last_error()
+ *     returns a thread-local message for the last failure on this thread;
+ *   - unless a parameter is documented "host", data pointers are DEVICE
+ *     pointers owned by the caller and living on the device the anchor handle
+ *     (or the `device` argument) names; all arrays are dense, row-major;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream).  Calls are asynchronous, stream-ordered, allocate nothing and
+ *     never synchronise; per-call scratch lives in the caller's workspace;
+ *   - all exports are re-entrant (the reference's encode is called from
+ *     concurrent tf.data workers, 03-...ipynb cell 8); the anchor handle is
+ *     immutable after creation and may be shared across threads and streams;
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with SSDX_ERR_CUDA.
+ */
+#ifndef SSDX_H_
+#define SSDX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSDX_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define SSDX_API __attribute__((visibility("default")))
+#else
+#define SSDX_API
+#endif
+
+#define SSDX_OK 0
+#define SSDX_ERR_INVALID (-1)   /* bad argument (mirrors the reference's ValueError sites) */
+#define SSDX_ERR_CUDA (-2)      /* CUDA runtime / launch failure */
+#define SSDX_ERR_WORKSPACE (-3) /* caller workspace too small */
+#define SSDX_ERR_NCCL (-4)      /* collective failure (host side, see ssdseglib/_dist.py) */
+
+typedef struct ssdx_anchors ssdx_anchors; /* opaque, device-resident anchor table */
+typedef void* ssdx_stream;                /* cudaStream_t */
+
+SSDX_API int ssdx_version(void);
+SSDX_API const char* ssdx_last_error(void);
+/* Number of CUDA devices visible; SSDX_ERR_CUDA if the driver is unusable. */
+SSDX_API int ssdx_device_count(int* count);
+
+/* ---- anchors: datacoder.py:6-117 (ctor), boxes.py:391-445 (conversions) ----
+ * corners_xyxy_host : host, (A,4) xmin,ymin,xmax,ymax - what the ctor stores or derives (:59-62, :84-89)
+ * centroids_host    : host, (A,4) cx,cy,w,h used by the DECODE side (:65-70, :78-81); NULL = derive from corners.
+ * The encode side always re-derives centroids from the corners (datacoder.py:251-256); the area is
+ * (ymax-ymin+1)*(xmax-xmin+1) (:111-114).  The table is uploaded once and stays in HBM/L2. */
+SSDX_API int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_host, int32_t num_anchors, int device,
+                        ssdx_anchors** out);
+SSDX_API int ssdx_anchors_destroy(ssdx_anchors* anchors);
+SSDX_API int ssdx_anchors_count(const ssdx_anchors* anchors, int32_t* num_anchors);
+SSDX_API int ssdx_anchors_device(const ssdx_anchors* anchors, int* device);
+
+/* ---- encode: datacoder.py:205-300 (_encode_ground_truth_labels_boxes, after the CSV read) ----
+ * gt_xyxy   (B,Gmax,4) f32, gt_label (B,Gmax) i32, gt_count (B) i32 (0 <= count <= Gmax; 0 => all background)
+ * std_host  : host, 4 floats (sigma cx, cy, w, h), datacoder.py:51
+ * out_labels (B,A,C) f32 one-hot (background row = [1,0,...]), out_offsets (B,A,4) f32 (tx,ty,tw,th)
+ * out_match  (B,A) i32 matched GT index or -1; may be NULL
+ * IoU, both arg-max reductions (ties -> lowest index) and the duplicate-resolution rule are bit-exact
+ * restatements of :205-244 and of the sequential scatter :286-298 (DESIGN.md "Parity contract"). */
+SSDX_API size_t ssdx_encode_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t gmax);
+SSDX_API int ssdx_encode(const ssdx_anchors* anchors, const float* gt_xyxy, const int32_t* gt_label, const int32_t* gt_count,
+                int32_t batch, int32_t gmax, int32_t num_classes, float iou_threshold, const float* std_host,
+                float* out_labels, float* out_offsets, int32_t* out_match, void* workspace, size_t workspace_bytes,
+                ssdx_stream stream);
+
+/* ---- decode: layers.py:45-81, datacoder.py:349-388, :390-432 ---- */
+#define SSDX_DECODE_YXYX 0             /* layers.DecodeBoxesCentroidsOffsets.call: (ymin,xmin,ymax,xmax), unmasked */
+#define SSDX_DECODE_CENTROIDS_MASKED 1 /* DataEncoderDecoder.decode_to_centroids: (cx,cy,w,h), background rows 0 */
+#define SSDX_DECODE_CORNERS_MASKED 2   /* DataEncoderDecoder.decode_to_corners: (xmin,ymin,xmax,ymax), masked twice */
+SSDX_API int ssdx_decode(const ssdx_anchors* anchors, const float* offsets /*(B,A,4)*/, int32_t batch, const float* std_host,
+                int mode, float* out /*(B,A,4)*/, ssdx_stream stream);
+
+/* ---- NMS: layers.py:127-168 -> tf.image.combined_non_max_suppression(q=1, clip_boxes=False) ----
+ * boxes_yxyx (B,A,4), scores (B,A,C) (background column included, as in the reference)
+ * out (B,K,6) = [label, prob, xmin, ymin, xmax, ymax] (layers.py:155-162), K = max_total; unused rows are 0
+ * out_valid (B) i32 = rows in use (TF's valid_detections, discarded by the layer); may be NULL
+ * out_anchor_idx (B,K) i32 = source anchor of each row, -1 padding (keep-set parity); may be NULL
+ * Equal scores are visited lower anchor index first, and merged lower class first (TF leaves both unspecified). */
+SSDX_API size_t ssdx_nms_workspace_bytes(int32_t batch, int32_t num_anchors, int32_t num_classes, int32_t max_per_class,
+                                int32_t max_total);
+SSDX_API int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t batch, int32_t num_anchors, int32_t num_classes,
+             int32_t max_per_class, int32_t max_total, float iou_threshold, float score_threshold, float* out,
+             int32_t* out_valid, int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
+             ssdx_stream stream);
+
+/* ---- detection eval: evaluators.py:6-63 (_iou_boxes_pred_vs_true) + :106-157 (TP flags, GT counts) ----
+ * pred_label (B,K) i32, pred_xyxy (B,K,4) f32; gt_* as in encode; labels are class indices in [0,C)
+ * out_tp (B,K) u8: 1 iff label != background and max_g IoU*[label match] >= iou_threshold (fp32 compare)
+ * counts (C,3) i64 ACCUMULATED (caller zeroes): [c][0] += TP, [c][1] += FP, [c][2] += GT boxes of class c */
+SSDX_API int ssdx_eval_tp(const int32_t* pred_label, const float* pred_xyxy, const float* gt_xyxy, const int32_t* gt_label,
+                 const int32_t* gt_count, int32_t batch, int32_t k, int32_t gmax, int32_t num_classes,
+                 int32_t background_label, float iou_threshold, uint8_t* out_tp, int64_t* counts, int device,
+                 ssdx_stream stream);
+
+/* evaluators.py:6-63 as a matrix: out (P,G) f32 = IoU (+1 convention, +1e-7f in the denominator) * [labels equal].
+ * G == 0 is the caller's business (the reference returns a (P,1) zero matrix, :27-28). */
+SSDX_API int ssdx_iou_pred_vs_true(const int32_t* pred_label, const float* pred_xyxy, const int32_t* gt_label,
+                                   const float* gt_xyxy, int32_t num_pred, int32_t num_gt, float* out, int device,
+                                   ssdx_stream stream);
+
+/* ---- GT ingest (host): datacoder.py:194-203, evaluators.py:111-121 ----
+ * Parses `label,xmin,ymin,xmax,ymax` records from `text` (host).  crlf_only != 0 reproduces datacoder.py:195
+ * (records split on "\r\n" only); 0 accepts "\n", "\r\n" (csv.reader).  flip_width > 0 applies the horizontal flip
+ * xmin' = W - xmax, xmax' = W - xmin in fp32 (:203).  Writes at most `capacity` rows to host arrays. */
+SSDX_API int ssdx_parse_gt_csv(const char* text, size_t text_len, int crlf_only, float flip_width, int32_t* labels_host,
+                      float* boxes_xyxy_host, int32_t capacity, int32_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDX_H_ */

@@ -1,0 +1,64 @@
+// Shared declarations for libssdx (sm_100a).  See include/ssdx.h for the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ssdx.h"
+
+// device-resident anchor table (immutable after ssdx_anchors_create)
+struct ssdx_anchors {
+  int device;
+  int32_t A;
+  float4* corners;   // (A) x0,y0,x1,y1                       datacoder.py:59-62 / :84-89
+  float* area;       // (A) (y1-y0+1)*(x1-x0+1)                datacoder.py:111-114
+  float4* enc_cent;  // (A) cx,cy,w,h re-derived from corners  datacoder.py:251-256
+  float4* dec_cent;  // (A) cx,cy,w,h as the ctor holds them   datacoder.py:65-70 / :78-81
+};
+
+void ssdx_set_error(const char* fmt, ...);
+
+#define SSDX_CHECK_ARG(cond, ...)     \
+  do {                                \
+    if (!(cond)) {                    \
+      ssdx_set_error(__VA_ARGS__);    \
+      return SSDX_ERR_INVALID;        \
+    }                                 \
+  } while (0)
+
+#define SSDX_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      ssdx_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return SSDX_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+#define SSDX_LAUNCH_CHECK(name)                                                     \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      ssdx_set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));     \
+      return SSDX_ERR_CUDA;                                                         \
+    }                                                                               \
+  } while (0)
+
+static inline size_t ssdx_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// number of SMs of a device (cached per device)
+int ssdx_sm_count(int device);
+
+// streaming (read-once / write-once) 128-bit accesses: keep the L1 for the anchor table
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}

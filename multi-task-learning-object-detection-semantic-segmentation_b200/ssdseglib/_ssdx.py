@@ -1,0 +1,291 @@
+"""ctypes binding of libssdx.so (include/ssdx.h) and the host/device plumbing around it.
+
+There is no CPU fallback here by design: if the shared library is missing the import fails, and if no
+CUDA device is present every compute call raises.  PyTorch is used only for device memory, pinned
+staging buffers, streams and DLPack exchange.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Any, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.environ.get("SSDX_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libssdx.so"))
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        f"libssdx.so not found at {_LIB_PATH}: build it with `python build.py` in "
+        f"{os.path.dirname(_HERE)} (or `python -c 'import __graft_entry__ as g; g.build()'` at the repo root). "
+        "This package has no CPU fallback.")
+
+lib = C.CDLL(_LIB_PATH)
+
+c_float_p = C.POINTER(C.c_float)
+c_i32_p = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol declared in include/ssdx.h (tests check this)
+SIGNATURES = {
+    "ssdx_version": (C.c_int, []),
+    "ssdx_last_error": (C.c_char_p, []),
+    "ssdx_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "ssdx_anchors_create": (C.c_int, [_vp, _vp, C.c_int32, C.c_int, C.POINTER(_vp)]),
+    "ssdx_anchors_destroy": (C.c_int, [_vp]),
+    "ssdx_anchors_count": (C.c_int, [_vp, c_i32_p]),
+    "ssdx_anchors_device": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "ssdx_encode_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "ssdx_encode": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, c_float_p, _vp, _vp,
+                              _vp, _vp, C.c_size_t, _vp]),
+    "ssdx_decode": (C.c_int, [_vp, _vp, C.c_int32, c_float_p, C.c_int, _vp, _vp]),
+    "ssdx_nms_workspace_bytes": (C.c_size_t, [C.c_int32] * 5),
+    "ssdx_nms": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                           _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "ssdx_eval_tp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_float, _vp, _vp, C.c_int, _vp]),
+    "ssdx_iou_pred_vs_true": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
+    "ssdx_parse_gt_csv": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_float, c_i32_p, c_float_p, C.c_int32,
+                                    c_i32_p]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+SSDX_ERR_INVALID, SSDX_ERR_CUDA, SSDX_ERR_WORKSPACE = -1, -2, -3
+DECODE_YXYX, DECODE_CENTROIDS_MASKED, DECODE_CORNERS_MASKED = 0, 1, 2
+
+
+def check(status: int) -> None:
+    """0 = OK.  Invalid arguments raise ValueError (the reference raises ValueError at its validation
+    sites, boxes.py:44,55, datacoder.py:56,75,108); everything else raises RuntimeError."""
+    if status == 0:
+        return
+    msg = lib.ssdx_last_error().decode(errors="replace")
+    if status == SSDX_ERR_INVALID:
+        raise ValueError(msg)
+    raise RuntimeError(f"libssdx error {status}: {msg}")
+
+
+def version() -> int:
+    return lib.ssdx_version()
+
+
+# ---------------------------------------------------------------------------------------------
+# device plumbing (torch)
+# ---------------------------------------------------------------------------------------------
+def _torch():
+    import torch
+
+    return torch
+
+
+def require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("ssdseglib (B200 build) needs a CUDA device: there is no CPU fallback for the "
+                           "encode/decode/NMS/eval path")
+    return torch
+
+
+def current_device() -> int:
+    return require_cuda().cuda.current_device()
+
+
+def stream_ptr(device: int) -> int:
+    return _torch().cuda.current_stream(device).cuda_stream
+
+
+_tls = threading.local()
+
+
+def workspace(nbytes: int, device: int):
+    """Per-thread, per-(device, stream) scratch buffer, grown geometrically (256-byte aligned by the
+    caching allocator).  Stream-ordered reuse is safe because every call on it is enqueued on that stream."""
+    torch = _torch()
+    cache = getattr(_tls, "ws", None)
+    if cache is None:
+        cache = _tls.ws = {}
+    key = (device, stream_ptr(device))
+    buf = cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=f"cuda:{device}")
+        cache[key] = buf
+    return buf
+
+
+def _pinned(shape, dtype, tag: str):
+    """Cached pinned staging buffer per (thread, tag, shape, dtype)."""
+    torch = _torch()
+    cache = getattr(_tls, "pin", None)
+    if cache is None:
+        cache = _tls.pin = {}
+    key = (tag, tuple(shape), dtype)
+    buf = cache.get(key)
+    if buf is None:
+        if len(cache) > 64:
+            cache.clear()
+        buf = cache[key] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+    return buf
+
+
+_NP2T = {np.dtype(np.float32): "float32", np.dtype(np.int32): "int32", np.dtype(np.uint8): "uint8",
+         np.dtype(np.int64): "int64"}
+
+
+def to_device(x: Any, np_dtype, device: Optional[int] = None, tag: str = "x") -> Tuple[Any, str]:
+    """Return (contiguous CUDA torch tensor of dtype, kind) for NumPy / list / torch / DLPack input.
+    kind is 'numpy' (host input: staged through pinned memory, result goes back to NumPy), 'torch'
+    (CUDA or CPU torch tensor; result is a torch tensor on the same device) or 'dlpack'."""
+    torch = require_cuda()
+    tdt = getattr(torch, _NP2T[np.dtype(np_dtype)])
+    if isinstance(x, torch.Tensor):
+        dev = device if device is not None else (x.device.index if x.is_cuda else torch.cuda.current_device())
+        t = x.to(device=f"cuda:{dev}", dtype=tdt, non_blocking=True).contiguous()
+        return t, ("torch" if x.is_cuda else "torch_cpu")
+    if not isinstance(x, np.ndarray) and hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+        if not t.is_cuda:
+            return to_device(t.numpy(), np_dtype, device, tag)
+        return t.to(dtype=tdt).contiguous(), "dlpack"
+    dev = device if device is not None else torch.cuda.current_device()
+    a = np.ascontiguousarray(np.asarray(x), dtype=np_dtype)
+    h = torch.from_numpy(a)
+    if a.size and not h.is_pinned():
+        p = _pinned(a.shape, tdt, tag)
+        p.copy_(h)
+        h = p
+    return h.to(f"cuda:{dev}", non_blocking=True), "numpy"
+
+
+def from_device(t, kind: str):
+    """Mirror the input kind on the way out."""
+    if kind == "numpy":
+        return t.cpu().numpy()
+    if kind == "torch_cpu":
+        return t.cpu()
+    return t
+
+
+def empty(shape, np_dtype, device: int):
+    torch = _torch()
+    return torch.empty(tuple(shape), dtype=getattr(torch, _NP2T[np.dtype(np_dtype)]), device=f"cuda:{device}")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class Anchors:
+    """Owner of one ssdx_anchors handle (device-resident, immutable)."""
+
+    def __init__(self, corners_xyxy: np.ndarray, centroids: Optional[np.ndarray], device: Optional[int] = None):
+        require_cuda()
+        self.device = current_device() if device is None else int(device)
+        corners = np.ascontiguousarray(corners_xyxy, dtype=np.float32)
+        if corners.ndim != 2 or corners.shape[1] != 4:
+            raise ValueError("anchors must have shape (A, 4)")
+        self.num_anchors = int(corners.shape[0])
+        cent = None if centroids is None else np.ascontiguousarray(centroids, dtype=np.float32)
+        if cent is not None and cent.shape != corners.shape:
+            raise ValueError("anchor centroids must have the same shape as the corners")
+        h = _vp()
+        check(lib.ssdx_anchors_create(corners.ctypes.data, None if cent is None else cent.ctypes.data,
+                                      self.num_anchors, self.device, C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                lib.ssdx_anchors_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+
+def std_array(std) -> Any:
+    arr = (C.c_float * 4)(*[float(np.float32(s)) for s in std])
+    return arr
+
+
+# ---------------------------------------------------------------------------------------------
+# thin typed wrappers over the exports (device tensors in, device tensors out)
+# ---------------------------------------------------------------------------------------------
+def encode(anchors: Anchors, gt_xyxy, gt_label, gt_count, num_classes: int, iou_threshold: float, std,
+           want_match: bool = False):
+    B, G = int(gt_xyxy.shape[0]), int(gt_xyxy.shape[1])
+    A, dev = anchors.num_anchors, anchors.device
+    labels = empty((B, A, num_classes), np.float32, dev)
+    offsets = empty((B, A, 4), np.float32, dev)
+    match = empty((B, A), np.int32, dev) if want_match else None
+    nbytes = lib.ssdx_encode_workspace_bytes(A, B, G)
+    ws = workspace(nbytes, dev)
+    check(lib.ssdx_encode(anchors.handle, ptr(gt_xyxy), ptr(gt_label), ptr(gt_count), B, G, num_classes,
+                          float(iou_threshold), std_array(std), ptr(labels), ptr(offsets), ptr(match), ptr(ws),
+                          ws.numel(), stream_ptr(dev)))
+    return labels, offsets, match
+
+
+def decode(anchors: Anchors, offsets, std, mode: int):
+    out = empty(tuple(offsets.shape), np.float32, anchors.device)
+    B = int(offsets.numel() // (anchors.num_anchors * 4))
+    check(lib.ssdx_decode(anchors.handle, ptr(offsets), B, std_array(std), mode, ptr(out),
+                          stream_ptr(anchors.device)))
+    return out
+
+
+def nms(boxes_yxyx, scores, max_per_class: int, max_total: int, iou_threshold: float, score_threshold: float,
+        want_aux: bool = False):
+    B, A, Cn = (int(v) for v in scores.shape)
+    dev = boxes_yxyx.device.index
+    out = empty((B, max_total, 6), np.float32, dev)
+    valid = empty((B,), np.int32, dev) if want_aux else None
+    aidx = empty((B, max_total), np.int32, dev) if want_aux else None
+    nbytes = lib.ssdx_nms_workspace_bytes(B, A, Cn, max_per_class, max_total)
+    ws = workspace(nbytes, dev)
+    check(lib.ssdx_nms(ptr(boxes_yxyx), ptr(scores), B, A, Cn, int(max_per_class), int(max_total),
+                       float(iou_threshold), float(score_threshold), ptr(out), ptr(valid), ptr(aidx), ptr(ws),
+                       ws.numel(), dev, stream_ptr(dev)))
+    return out, valid, aidx
+
+
+def eval_tp(pred_label, pred_xyxy, gt_xyxy, gt_label, gt_count, num_classes: int, background_label: int,
+            iou_threshold: float, counts=None):
+    torch = _torch()
+    B, K = int(pred_label.shape[0]), int(pred_label.shape[1])
+    G = int(gt_xyxy.shape[1])
+    dev = pred_label.device.index
+    tp = empty((B, K), np.uint8, dev)
+    if counts is None:
+        counts = torch.zeros((num_classes, 3), dtype=torch.int64, device=f"cuda:{dev}")
+    check(lib.ssdx_eval_tp(ptr(pred_label), ptr(pred_xyxy), ptr(gt_xyxy), ptr(gt_label), ptr(gt_count), B, K, G,
+                           num_classes, int(background_label), float(iou_threshold), ptr(tp), ptr(counts), dev,
+                           stream_ptr(dev)))
+    return tp, counts
+
+
+def iou_pred_vs_true(pred_label, pred_xyxy, gt_label, gt_xyxy):
+    P, G = int(pred_label.shape[0]), int(gt_label.shape[0])
+    dev = pred_xyxy.device.index
+    out = empty((P, G), np.float32, dev)
+    check(lib.ssdx_iou_pred_vs_true(ptr(pred_label), ptr(pred_xyxy), ptr(gt_label), ptr(gt_xyxy), P, G, ptr(out),
+                                    dev, stream_ptr(dev)))
+    return out
+
+
+def parse_gt_csv(text: bytes, crlf_only: bool, flip_width: float = 0.0, capacity: int = 0):
+    """Host-side C parser; returns (labels int32 (G,), boxes float32 (G,4))."""
+    if isinstance(text, str):
+        text = text.encode()
+    cap = capacity if capacity > 0 else max(16, text.count(b"\n") + 2)
+    labels = np.empty(cap, np.int32)
+    boxes = np.empty((cap, 4), np.float32)
+    n = C.c_int32(0)
+    st = lib.ssdx_parse_gt_csv(text, len(text), 1 if crlf_only else 0, float(flip_width),
+                               labels.ctypes.data_as(c_i32_p), boxes.ctypes.data_as(c_float_p), cap, C.byref(n))
+    check(st)
+    return labels[: n.value].copy(), boxes[: n.value].copy()

@@ -1,0 +1,120 @@
+"""Prediction post-processing - mirror of the reference's `ssdseglib/layers.py` (decode + NMS) over libssdx.
+
+`DecodeBoxesCentroidsOffsets` and `NonMaximumSuppression` keep the reference's constructor arguments, `call`
+signature, output layout and `get_config` (layers.py:4-177).  They are plain callables (TensorFlow/Keras is not a
+dependency of this package); `call` accepts NumPy arrays, torch tensors or DLPack objects and mirrors the input
+kind on return.  `SegmentationSuppression` and `Split` belong to the Keras model graph and are not part of this
+path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import _ssdx
+from .boxes import coordinates_centroids_to_corners
+
+
+def _vec(x) -> np.ndarray:
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().numpy()
+    elif hasattr(x, "numpy") and not isinstance(x, np.ndarray):
+        x = x.numpy()
+    return np.ascontiguousarray(np.asarray(x), dtype=np.float32).reshape(-1)
+
+
+class _Layer:
+    """Minimal stand-in for the `tf.keras.layers.Layer` call protocol."""
+
+    def __init__(self, name: Optional[str] = None, **kwargs) -> None:
+        self.name = name or type(self).__name__
+
+    def __call__(self, *args, **kwargs):
+        return self.call(*args, **kwargs)
+
+
+class DecodeBoxesCentroidsOffsets(_Layer):
+    def __init__(self, center_x_boxes_default, center_y_boxes_default, width_boxes_default, height_boxes_default,
+                 standard_deviation_center_x_offsets: float, standard_deviation_center_y_offsets: float,
+                 standard_deviation_width_offsets: float, standard_deviation_height_offsets: float,
+                 device: Optional[int] = None, **kwargs) -> None:
+        """Decode the centroid offsets predicted by the network (layers.py:6-43).  The four default-box
+        arrays have shape (total boxes,)."""
+        super().__init__(**kwargs)
+        self.center_x_boxes_default = _vec(center_x_boxes_default)
+        self.center_y_boxes_default = _vec(center_y_boxes_default)
+        self.width_boxes_default = _vec(width_boxes_default)
+        self.height_boxes_default = _vec(height_boxes_default)
+        self.standard_deviation_center_x_offsets = np.float32(standard_deviation_center_x_offsets)
+        self.standard_deviation_center_y_offsets = np.float32(standard_deviation_center_y_offsets)
+        self.standard_deviation_width_offsets = np.float32(standard_deviation_width_offsets)
+        self.standard_deviation_height_offsets = np.float32(standard_deviation_height_offsets)
+        cent = np.stack([self.center_x_boxes_default, self.center_y_boxes_default, self.width_boxes_default,
+                         self.height_boxes_default], axis=1)
+        corners = np.stack(coordinates_centroids_to_corners(cent[:, 0], cent[:, 1], cent[:, 2], cent[:, 3]), axis=1)
+        self._std = (float(self.standard_deviation_center_x_offsets), float(self.standard_deviation_center_y_offsets),
+                     float(self.standard_deviation_width_offsets), float(self.standard_deviation_height_offsets))
+        self._anchors = _ssdx.Anchors(corners, cent, device)
+
+    def call(self, boxes_centroids_offsets):
+        """(batch, total boxes, 4) offsets (cx, cy, w, h) -> (batch, total boxes, 4) corners in the order
+        (ymin, xmin, ymax, xmax) that the NMS layer expects; no background masking (layers.py:45-81)."""
+        off, kind = _ssdx.to_device(boxes_centroids_offsets, np.float32, self._anchors.device, "pred_offsets")
+        if off.dim() != 3 or off.shape[1] != self._anchors.num_anchors or off.shape[2] != 4:
+            raise ValueError(f"expected offsets of shape (batch, {self._anchors.num_anchors}, 4), got {tuple(off.shape)}")
+        return _ssdx.from_device(_ssdx.decode(self._anchors, off, self._std, _ssdx.DECODE_YXYX), kind)
+
+    def get_config(self):
+        return {
+            'center_x_boxes_default': self.center_x_boxes_default,
+            'center_y_boxes_default': self.center_y_boxes_default,
+            'width_boxes_default': self.width_boxes_default,
+            'height_boxes_default': self.height_boxes_default,
+            'standard_deviation_center_x_offsets': self.standard_deviation_center_x_offsets,
+            'standard_deviation_center_y_offsets': self.standard_deviation_center_y_offsets,
+            'standard_deviation_width_offsets': self.standard_deviation_width_offsets,
+            'standard_deviation_height_offsets': self.standard_deviation_height_offsets,
+        }
+
+
+class NonMaximumSuppression(_Layer):
+    def __init__(self, max_number_of_boxes_per_class: int, max_number_of_boxes_per_sample: int,
+                 boxes_iou_threshold: float, labels_probability_threshold: float, suppress_background_boxes: bool,
+                 **kwargs) -> None:
+        """Per-class non maximum suppression of the detection outputs (layers.py:97-125)."""
+        super().__init__(**kwargs)
+        self.max_number_of_boxes_per_class = max_number_of_boxes_per_class
+        self.max_number_of_boxes_per_sample = max_number_of_boxes_per_sample
+        self.boxes_iou_threshold = boxes_iou_threshold
+        self.labels_probability_threshold = labels_probability_threshold
+        self.suppress_background_boxes = suppress_background_boxes
+
+    def call(self, boxes_corners_coordinates, labels_probabilities, return_aux: bool = False):
+        """boxes (batch, total boxes, 4) as (ymin, xmin, ymax, xmax), probabilities (batch, total boxes, classes)
+        -> (batch, max boxes per sample, 6) rows [label, probability, xmin, ymin, xmax, ymax], zero padded.
+        With `suppress_background_boxes` the rows with label > 0 are returned flattened over the batch, as
+        the reference does (layers.py:127-168).  `return_aux=True` also returns (valid (batch,), source anchor
+        index (batch, max boxes per sample))."""
+        boxes, kind = _ssdx.to_device(boxes_corners_coordinates, np.float32, None, "nms_boxes")
+        scores, _ = _ssdx.to_device(labels_probabilities, np.float32, boxes.device.index, "nms_scores")
+        if boxes.dim() != 3 or boxes.shape[2] != 4 or scores.dim() != 3 or scores.shape[:2] != boxes.shape[:2]:
+            raise ValueError("expected boxes (batch, boxes, 4) and probabilities (batch, boxes, classes)")
+        out, valid, aidx = _ssdx.nms(boxes, scores, self.max_number_of_boxes_per_class,
+                                     self.max_number_of_boxes_per_sample, self.boxes_iou_threshold,
+                                     self.labels_probability_threshold, want_aux=return_aux)
+        if self.suppress_background_boxes:
+            out = out[out[..., 0] > 0.0]  # tf.boolean_mask over (batch, boxes): drops the batch axis
+        res = _ssdx.from_device(out, kind)
+        if return_aux:
+            return res, _ssdx.from_device(valid, kind), _ssdx.from_device(aidx, kind)
+        return res
+
+    def get_config(self):
+        return {
+            'max_number_of_boxes_per_class': self.max_number_of_boxes_per_class,
+            'max_number_of_boxes_per_sample': self.max_number_of_boxes_per_sample,
+            'boxes_iou_threshold': self.boxes_iou_threshold,
+            'labels_probability_threshold': self.labels_probability_threshold,
+            'suppress_background_boxes': self.suppress_background_boxes,
+        }

@@ -1,0 +1,202 @@
+"""CPU-only tests: the host-side mirror (anchors, CSV ingest, argument validation), the C-ABI surface
+(library loads and exports every symbol of include/ssdx.h) and the multi-rank host logic over gloo.
+No compute entry point is called here (no GPU in the build container)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from oracle import ssd_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "multi-task-learning-object-detection-semantic-segmentation_b200")
+
+
+@pytest.fixture(scope="module")
+def ssdseglib():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+
+    __graft_entry__.build()
+    import ssdseglib as m
+
+    return m
+
+
+def test_library_exports_every_header_symbol(ssdseglib):
+    header = open(os.path.join(ROOT, "include", "ssdx.h")).read()
+    declared = set(re.findall(r"SSDX_API[^;]*?\b(ssdx_\w+)\s*\(", header))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(os.path.join(PKG, "lib", "libssdx.so"))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in ssdx.h but not exported"
+    assert declared == set(ssdseglib._ssdx.SIGNATURES), "ctypes signatures out of sync with ssdx.h"
+    assert lib.ssdx_version() == 100
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(PKG, "lib", "libssdx.so")],
+                         capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (\w+)", out))
+    assert {e for e in exported if e.startswith("ssdx_")} == declared  # nothing undeclared leaks out
+
+
+def test_library_contains_sm100a_code():
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(PKG, "lib", "libssdx.so")], capture_output=True,
+                         text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_gpu(ssdseglib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    a = orc.anchors_generate(**orc.STD_ANCHOR_CFG)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ssdseglib.datacoder.DataEncoderDecoder(4, (480, 640), a[:, 0], a[:, 1], a[:, 2], a[:, 3])
+    with pytest.raises(RuntimeError):
+        ssdseglib.layers.NonMaximumSuppression(4, 10, 0.5, 0.5, False)(np.zeros((1, 8, 4), np.float32),
+                                                                      np.zeros((1, 8, 2), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, f"{f} mentions the oracle"
+
+
+# ---------------------------------------------------------------- anchors mirror (boxes.py)
+def test_boxes_mirror_matches_reference_fixtures(ssdseglib, golden):
+    g = golden("anchors")
+    B = ssdseglib.boxes.DefaultBoundingBoxes
+    std = B(((30, 40), (15, 20), (8, 10), (4, 5)), centers_padding_from_borders_percentage=(0.025, 0.05, 0.075, 0.1),
+            boxes_scales=(0.15, 0.95), additional_square_box=True)
+    assert std.feature_maps_boxes is None
+    std.rescale_boxes_coordinates(image_shape=(480, 640))
+    assert np.array_equal(std.get_boxes_coordinates_corners("ssd"), g["std_corners"])
+    assert np.array_equal(std.get_boxes_coordinates_centroids("ssd"), g["std_centroids"])
+    assert np.array_equal(std.boxes_scales, g["std_scales"])
+    assert np.array_equal(std.get_boxes_coordinates_xmin("ssd"), g["std_xmin"])
+    assert np.array_equal(std.get_boxes_coordinates_height("ssd"), g["std_height"])
+    assert np.array_equal(std.get_boxes_coordinates_corners("feature-maps")[1], g["std_fm1_corners"])
+    assert np.array_equal(std.get_boxes_coordinates_width("feature-maps")[3], g["std_fm3_width"])
+    assert std.get_boxes_coordinates_ymax("ssd").shape == (9600,)
+    assert len(std.get_boxes_coordinates_center_x("feature-maps")) == 4
+    odd = B(((3, 1), (2, 2)), ((1, 2), (1, 0.5, 3)), (0.3, 0.8), 0.1, False)
+    odd.rescale_boxes_coordinates((33, 65))
+    assert np.array_equal(odd.get_boxes_coordinates_corners("ssd"), g["odd_once"])
+    odd.rescale_boxes_coordinates((33, 65))  # reference quirk: in-place rescale compounds
+    assert np.array_equal(odd.get_boxes_coordinates_corners("ssd"), g["odd_twice"])
+    c = ssdseglib.boxes.coordinates_corners_to_centroids(*[g["std_corners"][:, i] for i in range(4)])
+    assert np.array_equal(np.stack(c, 1), g["conv_centroids"])
+    k = ssdseglib.boxes.coordinates_centroids_to_corners(*c)
+    assert np.array_equal(np.stack(k, 1), g["conv_corners"])
+
+
+def test_boxes_mirror_validation(ssdseglib):
+    B = ssdseglib.boxes.DefaultBoundingBoxes
+    with pytest.raises(ValueError):
+        B(((4, 4),), centers_padding_from_borders_percentage=0.5)
+    with pytest.raises(ValueError):
+        B(((4, 4), (2, 2)), centers_padding_from_borders_percentage=(0.1,))
+    with pytest.raises(ValueError):
+        B(((4, 4), (2, 2)), feature_maps_aspect_ratios=((1, 2),))
+
+
+# ---------------------------------------------------------------- GT ingest (host C parser)
+def test_csv_parser_matches_oracle(ssdseglib):
+    p = ssdseglib._ssdx.parse_gt_csv
+    text = "1,10.5,20,30.25,40\r\n3,1,2,3,4\r\n2,100,50.125,200,220.75\r\n"
+    l, b = p(text, True)
+    lo, bo = orc.parse_gt_csv_text(text)
+    assert np.array_equal(l, lo) and np.array_equal(b, bo) and b.dtype == np.float32
+    l, b = p(text, True, flip_width=640.0)
+    assert np.array_equal(b, orc.flip_boxes_horizontal(bo, 640))
+    l, b = p("1,1,2,3,4\n2,5,6,7,8\n", False)
+    assert l.tolist() == [1, 2] and b[1].tolist() == [5, 6, 7, 8]
+    l, b = p("  \r\n", True)
+    assert l.shape == (0,) and b.shape == (0, 4)
+    l, b = p("", False)
+    assert l.shape == (0,)
+    # repr round trip of arbitrary float32 values
+    vals = np.random.default_rng(0).uniform(-50, 700, (40, 4)).astype(np.float32)
+    text = "".join(f"2,{float(v[0])!r},{float(v[1])!r},{float(v[2])!r},{float(v[3])!r}\r\n" for v in vals)
+    l, b = p(text, True)
+    assert np.array_equal(b, vals)
+    with pytest.raises(ValueError):
+        p("1,2,3\r\n", True)
+    with pytest.raises(ValueError):
+        p("1,2,3,4,x\n", False)
+    with pytest.raises(ValueError):
+        p("1,1,2,3,4\n2,5,6,7,8\n", True)  # datacoder.py:195 splits on CRLF only -> one malformed record
+
+
+def test_datacoder_validation_before_device(ssdseglib):
+    D = ssdseglib.datacoder.DataEncoderDecoder
+    a = np.zeros(4, np.float32)
+    with pytest.raises(ValueError, match="corners"):
+        D(4, (480, 640), xmin_boxes_default=a)
+    with pytest.raises(ValueError, match="centroids"):
+        D(4, (480, 640), center_x_boxes_default=a)
+    with pytest.raises(ValueError):  # reference: passing both raises (unreachable branch, datacoder.py:92-108)
+        D(4, (480, 640), a, a, a, a, a, a, a, a)
+
+
+def test_average_precision_host_formula(ssdseglib, golden):
+    """The float64 AP tail (evaluators.py:164-185) from oracle TP flags reproduces the reference's numbers."""
+    g = golden("eval")
+    N = g["pred_labels"].shape[0]
+    no_gt = int(g["no_gt_image"][0])
+    for thr, key in ((0.5, "ap50"), (0.7, "ap70")):
+        tp = np.stack([orc.eval_tp_flags(g["pred_labels"][i], g["pred_boxes"][i],
+                                         g["gt_labels"][i] if i != no_gt else np.zeros(0, np.int32),
+                                         g["gt_boxes"][i] if i != no_gt else np.zeros((0, 4), np.float32), thr)
+                       for i in range(N)])
+        n_gt = {c: int(sum((g["gt_labels"][i] == c).sum() for i in range(N) if i != no_gt)) for c in (1, 2, 3)}
+        sc = g["pred_labels"] != 0
+        ap = ssdseglib.evaluators.average_precision_from_flags(tp[sc], g["pred_conf"][sc], g["pred_labels"][sc],
+                                                               n_gt, 0)
+        np.testing.assert_allclose([ap[1], ap[2], ap[3]], g[key], rtol=0, atol=1e-12)
+
+
+# ---------------------------------------------------------------- multi-rank host logic (gloo, world size 2)
+def test_shard_range(ssdseglib):
+    from ssdseglib._dist import shard_range
+
+    for n, w in ((1024, 8), (10, 4), (3, 8), (4096, 2)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_all_gather_counts_gloo_world2(tmp_path):
+    script = tmp_path / "rank.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {PKG!r})
+        import torch, torch.distributed as dist
+        from ssdseglib._dist import all_gather_counts, shard_range
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        lo, hi = shard_range(10, r, w)
+        counts = torch.tensor([[r + 1, 10 * (r + 1), hi - lo]] * 4, dtype=torch.int64)
+        g = all_gather_counts(counts)
+        assert g.shape == (w, 4, 3)
+        tot = g.sum(0)
+        assert tot[0].tolist() == [3, 30, 10], tot
+        dist.barrier()
+        if r == 0:
+            print("GATHER_OK")
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout + r.stderr

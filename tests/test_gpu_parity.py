@@ -1,0 +1,350 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the ssdseglib mirror) against the CPU oracle and
+the committed golden fixtures.  Bar: matched indices / labels / NMS keep-sets / TP flags / counts bit-exact;
+offsets and decoded coordinates within 1e-5 relative in fp32 (absolute floors stated at each check)."""
+import numpy as np
+import pytest
+
+from oracle import ssd_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+STD = (0.1, 0.1, 0.2, 0.2)
+RTOL = 1e-5  # BASELINE.json north_star: "within 1e-5 relative in fp32"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import ssdseglib
+
+    return ssdseglib
+
+
+@pytest.fixture(scope="module")
+def coder(lib, std_anchors):
+    return lib.datacoder.DataEncoderDecoder(
+        num_classes=4, image_shape=(480, 640), xmin_boxes_default=std_anchors[:, 0],
+        ymin_boxes_default=std_anchors[:, 1], xmax_boxes_default=std_anchors[:, 2],
+        ymax_boxes_default=std_anchors[:, 3], iou_threshold=0.5, standard_deviations_centroids_offsets=STD)
+
+
+def assert_offsets_close(got, ref):
+    # log() differs from NumPy/Eigen by a few ulp; tx,ty are exact IEEE divisions
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-6)
+
+
+def assert_coords_close(got, ref, anchor_wh):
+    # (exp(t)-1)*w cancels for tiny t: absolute floor 1e-5 * anchor size, as SURVEY.md section 7
+    floor = 1e-5 * np.maximum(anchor_wh.max(axis=-1), 1.0)[..., None]
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    assert np.all(err <= RTOL * np.abs(ref) + floor), f"max err {err.max()}"
+
+
+def encode_ref(anchors, labels, boxes, counts, C, thr):
+    return orc.encode_batch(anchors, labels, boxes, counts, C, thr, STD)
+
+
+# ------------------------------------------------------------------------------------------- encode
+CASES = ["cfg0", "cfg0_thr525_flip", "ties_int", "small", "label_oob"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_encode_golden(lib, golden, std_anchors, case):
+    g = golden("encode_decode")
+    labels, boxes = g[case + "_gt_labels"], g[case + "_gt_boxes"].copy()
+    thr, flip = float(g[case + "_thr"][0]), bool(g[case + "_flip"][0])
+    if flip:
+        boxes = np.stack([orc.flip_boxes_horizontal(b, 640) for b in boxes])
+    c = lib.datacoder.DataEncoderDecoder(4, (480, 640), std_anchors[:, 0], std_anchors[:, 1], std_anchors[:, 2],
+                                         std_anchors[:, 3], iou_threshold=thr)
+    L, O, M = c.encode_batch(boxes, labels, return_match=True)
+    assert L.dtype == np.float32 and O.dtype == np.float32 and M.dtype == np.int32
+    assert np.array_equal(L, g[case + "_labels"])                      # labels bit-exact
+    assert np.array_equal(O != 0, g[case + "_offsets"] != 0)
+    assert_offsets_close(O, g[case + "_offsets"])
+    _, _, Mref = encode_ref(std_anchors, labels, boxes, np.full(len(labels), labels.shape[1]), 4, thr)
+    assert np.array_equal(M, Mref)                                      # matched indices bit-exact
+
+
+def test_encode_config0_and_ragged(lib, coder, std_anchors):
+    rng = np.random.default_rng(1993)
+    labels, boxes, counts = orc.synth_gt(rng, 8, 16)
+    counts = np.array([16, 0, 1, 7, 16, 3, 0, 12], np.int32)          # ragged + empty images
+    L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(std_anchors, labels, boxes, counts, 4, 0.5)
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+    assert np.all(L[1, :, 0] == 1) and np.all(O[1] == 0) and np.all(M[1] == -1)
+
+
+def test_encode_tie_heavy_and_duplicates(lib, coder, std_anchors):
+    rng = np.random.default_rng(77)
+    labels, boxes, counts = orc.synth_gt(rng, 24, 12, integer=True)
+    boxes[:, 5] = boxes[:, 2]
+    boxes[:, 9] = boxes[:, 2]
+    labels[:, 5] = 1
+    L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(std_anchors, labels, boxes, counts, 4, 0.5)
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+
+
+@pytest.mark.parametrize("C,thr", [(1, 0.5), (3, 0.3), (6, 0.525), (21, 0.5)])
+def test_encode_other_class_counts(lib, std_anchors, C, thr):
+    rng = np.random.default_rng(C)
+    labels, boxes, counts = orc.synth_gt(rng, 5, 9, n_fg=max(C - 1, 1))
+    c = lib.datacoder.DataEncoderDecoder(C, (480, 640), std_anchors[:, 0], std_anchors[:, 1], std_anchors[:, 2],
+                                         std_anchors[:, 3], iou_threshold=thr)
+    L, O, M = c.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(std_anchors, labels, boxes, counts, C, thr)
+    assert L.shape == (5, 9600, C)
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+
+
+def test_encode_stress_shape_small_batch(lib):
+    """BASELINE config 3 shape (A = 100k, G = 256) at batch 2 against the oracle."""
+    anchors = orc.anchors_generate(**orc.STRESS_ANCHOR_CFG)
+    rng = np.random.default_rng(1996)
+    labels, boxes, counts = orc.synth_gt(rng, 2, 256, image_hw=(1000, 1280))
+    c = lib.datacoder.DataEncoderDecoder(4, (1000, 1280), anchors[:, 0], anchors[:, 1], anchors[:, 2], anchors[:, 3])
+    L, O, M = c.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(anchors, labels, boxes, counts, 4, 0.5)
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+
+
+def test_encode_more_gt_than_one_tile(lib, coder, std_anchors):
+    rng = np.random.default_rng(3)
+    labels, boxes, counts = orc.synth_gt(rng, 2, 300, wh_range=(10.0, 120.0))  # > 256 GT: two shared-memory tiles
+    L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(std_anchors, labels, boxes, counts, 4, 0.5)
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+
+
+def test_encode_per_image_file_api(lib, coder, std_anchors, tmp_path, golden):
+    g = golden("encode_decode")
+    p = tmp_path / "gt.csv"
+    rows = [f"{int(l)},{float(b[0])!r},{float(b[1])!r},{float(b[2])!r},{float(b[3])!r}"
+            for l, b in zip(g["cfg0_gt_labels"][0], g["cfg0_gt_boxes"][0])]
+    p.write_bytes(("\r\n".join(rows) + "\r\n").encode())
+    L, O = coder._encode_ground_truth_labels_boxes(str(p), False)
+    assert np.array_equal(L, g["cfg0_labels"][0])
+    assert_offsets_close(O, g["cfg0_offsets"][0])
+    Lf, Of = coder._encode_ground_truth_labels_boxes(str(p), True)
+    Lr, Or, _ = orc.encode_image(std_anchors, g["cfg0_gt_labels"][0],
+                                 orc.flip_boxes_horizontal(g["cfg0_gt_boxes"][0], 640), 4, 0.5, STD)
+    assert np.array_equal(Lf, Lr)
+    assert_offsets_close(Of, Or)
+
+
+# ------------------------------------------------------------------------------------------- decode
+def test_decode_golden_and_modes(lib, coder, golden):
+    g = golden("encode_decode")
+    anc = golden("anchors")["std_centroids"]
+    wh = anc[:, 2:]
+    for case in CASES:
+        off = g[case + "_offsets"]
+        cen = coder.decode_to_centroids(off)
+        cor = coder.decode_to_corners(off)
+        assert cen.shape == off.shape and cor.shape == off.shape
+        bg = np.abs(off).sum(-1) == 0
+        assert np.all(cen[bg] == 0) and np.all(cor[bg] == 0)           # background rows exactly zero
+        assert_coords_close(cen, g[case + "_dec_centroids"], wh[None])
+        assert_coords_close(cor, g[case + "_dec_corners"], wh[None])
+    x0, y0, x1, y1 = coder.decode_to_corners(g["cfg0_offsets"][0], output_decoded_corners_separately=True)
+    assert x0.shape == (9600,)
+
+
+def test_decode_layer_yxyx(lib, golden):
+    g = golden("layers")
+    a = golden("anchors")["std_centroids"]
+    layer = lib.layers.DecodeBoxesCentroidsOffsets(a[:, 0], a[:, 1], a[:, 2], a[:, 3], 0.1, 0.1, 0.2, 0.2)
+    out = layer(g["offsets"])
+    assert out.shape == g["decoded_yxyx"].shape and out.dtype == np.float32
+    assert_coords_close(out, g["decoded_yxyx"], a[None, :, 2:] * 8.0)  # decoded boxes ~ 2x anchor size here
+    # xy offsets are exact arithmetic (no transcendental): centre = (min + max) / 2 must be bit-stable
+    rng = np.random.default_rng(0)
+    off = rng.normal(0, 1, (3, 9600, 4)).astype(np.float32)
+    np.testing.assert_allclose(layer(off), orc.decode_batched_yxyx(off, a, STD), rtol=RTOL, atol=1e-3)
+
+
+def test_encode_decode_round_trip_full_batch(lib, coder, std_anchors):
+    """Size-independent property at the bench batch size (1024): decoding the encoded targets returns the
+    matched ground-truth box; background rows decode to zero."""
+    rng = np.random.default_rng(2024)
+    labels, boxes, counts = orc.synth_gt(rng, 1024, 16)
+    L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
+    dec = coder.decode_to_corners(O)
+    assert dec.shape == (1024, 9600, 4)
+    pos = M >= 0
+    assert 100 * 1024 < pos.sum() < 400 * 1024
+    gt = np.take_along_axis(boxes, np.maximum(M, 0)[..., None].repeat(4, -1), axis=1)
+    np.testing.assert_allclose(dec[pos], gt[pos], atol=5e-3, rtol=0)
+    assert np.all(dec[~pos] == 0)
+    assert np.array_equal(L.sum(-1), np.ones((1024, 9600), np.float32))
+    lab_gt = np.take_along_axis(labels, np.maximum(M, 0), axis=1)
+    assert np.array_equal(L.argmax(-1)[pos], lab_gt[pos]) and np.all(L[~pos][:, 0] == 1)
+    # every GT box got its best anchor (step 1) unless a later GT took the same anchor
+    assert np.all([(np.isin(np.arange(16), M[b][M[b] >= 0])).sum() >= 14 for b in range(0, 1024, 97)])
+
+
+# ------------------------------------------------------------------------------------------- NMS
+def nms_check(lib, yxyx, scores, mpc, mtot, iou, thr):
+    layer = lib.layers.NonMaximumSuppression(mpc, mtot, iou, thr, False)
+    out, valid, aidx = layer.call(yxyx, scores, return_aux=True)
+    ref, vref, aref = orc.combined_nms(yxyx, scores, mpc, mtot, iou, thr)
+    assert np.array_equal(valid, vref)
+    assert np.array_equal(aidx, aref)          # keep-set and order bit-exact
+    assert np.array_equal(out, ref)            # rows are copies of inputs: bit-exact
+    return out
+
+
+def test_nms_golden_layer_output(lib, golden):
+    g = golden("layers")
+    out = nms_check(lib, g["decoded_yxyx"], g["scores"], 200, 200, 0.45, 0.01)
+    assert np.array_equal(out, g["det_200"])
+    layer = lib.layers.NonMaximumSuppression(4, 10, 0.025, 0.2, True)
+    assert np.array_equal(layer(g["decoded_yxyx"], g["scores"]), g["det_bgdrop"])
+
+
+def test_nms_config1_batch(lib, golden):
+    """BASELINE config 1 generator (decode + NMS, thr .01, IoU .45, top-200) at batch 8."""
+    a = golden("anchors")["std_centroids"]
+    off, scores = orc.synth_predictions(np.random.default_rng(1994), 8, 9600, 4)
+    yxyx = orc.decode_batched_yxyx(off, a, STD)
+    out = nms_check(lib, yxyx, scores, 200, 200, 0.45, 0.01)
+    assert np.all(np.diff(out[..., 1], axis=1) <= 0)  # scores non-increasing
+
+
+@pytest.mark.parametrize("mpc,mtot,iou,thr", [(4, 10, 0.025, 0.725), (50, 20, 0.3, 0.3), (300, 1000, 0.6, 0.05),
+                                              (1, 1, 0.0, 0.0), (200, 200, 1.0, 0.01)])
+def test_nms_parameter_grid(lib, golden, mpc, mtot, iou, thr):
+    a = golden("anchors")["std_centroids"]
+    off, scores = orc.synth_predictions(np.random.default_rng(mpc), 3, 9600, 4)
+    nms_check(lib, orc.decode_batched_yxyx(off, a, STD), scores, mpc, mtot, iou, thr)
+
+
+def test_nms_deep_suppression_clusters(lib):
+    """Clustered boxes: thousands of candidates are visited before 200 survive (several selection rounds)."""
+    rng = np.random.default_rng(9)
+    B, A, C = 2, 6000, 3
+    centers = rng.uniform(100, 500, size=(B, 12, 2))
+    which = rng.integers(0, 12, size=(B, A))
+    c = np.take_along_axis(centers, which[..., None].repeat(2, -1), axis=1) + rng.normal(0, 6, size=(B, A, 2))
+    wh = rng.uniform(60, 90, size=(B, A, 2))
+    yxyx = np.concatenate([c - wh / 2, c + wh / 2], -1).astype(np.float32)
+    scores = orc.dedup_scores(rng.uniform(0.02, 1, size=(B, A, C)).astype(np.float32))
+    out = nms_check(lib, yxyx, scores, 200, 300, 0.45, 0.01)
+    assert (out[..., 1] > 0).sum() < 2 * 3 * 60  # far fewer than 200 per class survive
+
+
+def test_nms_massive_score_ties(lib):
+    """Thousands of scores exactly 1.0f (saturated soft-max): ties are visited lower anchor first."""
+    rng = np.random.default_rng(10)
+    B, A, C = 2, 5000, 2
+    ctr = rng.uniform(50, 600, size=(B, A, 2))
+    wh = rng.uniform(10, 40, size=(B, A, 2))
+    yxyx = np.concatenate([ctr - wh / 2, ctr + wh / 2], -1).astype(np.float32)
+    scores = np.ones((B, A, C), np.float32)
+    scores[:, ::7, 1] = 0.5
+    nms_check(lib, yxyx, scores, 200, 400, 0.3, 0.01)
+
+
+def test_nms_degenerate_boxes_and_small_sets(lib):
+    rng = np.random.default_rng(12)
+    # flipped corners + zero-area boxes (never suppress, never suppressed)
+    B, A, C = 3, 300, 5
+    yxyx = rng.uniform(0, 100, size=(B, A, 4)).astype(np.float32)
+    yxyx[:, ::5, 2] = yxyx[:, ::5, 0]
+    scores = orc.dedup_scores(rng.uniform(0, 1, size=(B, A, C)).astype(np.float32))
+    nms_check(lib, yxyx, scores, 200, 200, 0.45, 0.01)   # max_per_class < A
+    nms_check(lib, yxyx, scores, 500, 50, 0.45, 0.5)     # max_per_class > A
+    nms_check(lib, yxyx, scores, 10, 10, 0.45, 2.0)      # nothing passes the score threshold
+    out = nms_check(lib, yxyx[:, :1], scores[:, :1], 3, 4, 0.5, 0.0)  # a single box
+    assert out.shape == (3, 4, 6)
+
+
+def test_nms_torch_in_torch_out(lib, golden):
+    import torch
+
+    g = golden("layers")
+    boxes = torch.from_numpy(g["decoded_yxyx"]).cuda()
+    scores = torch.from_numpy(g["scores"]).cuda()
+    out = lib.layers.NonMaximumSuppression(200, 200, 0.45, 0.01, False)(boxes, scores)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    assert np.array_equal(out.cpu().numpy(), g["det_200"])
+
+
+def test_nms_rejects_bad_iou_threshold(lib, golden):
+    g = golden("layers")
+    with pytest.raises(ValueError):
+        lib.layers.NonMaximumSuppression(10, 10, 1.5, 0.1, False)(g["decoded_yxyx"], g["scores"])
+
+
+# ------------------------------------------------------------------------------------------- eval
+def test_eval_golden(lib, golden, tmp_path):
+    g = golden("eval")
+    N = g["pred_labels"].shape[0]
+    no_gt = int(g["no_gt_image"][0])
+    paths = []
+    for i in range(N):
+        p = tmp_path / f"gt_{i}.csv"
+        n = 0 if i == no_gt else g["gt_labels"].shape[1]
+        p.write_text("".join(f"{int(l)},{float(b[0])!r},{float(b[1])!r},{float(b[2])!r},{float(b[3])!r}\n"
+                             for l, b in zip(g["gt_labels"][i, :n], g["gt_boxes"][i, :n])))
+        paths.append(str(p))
+    for i in range(N):
+        iou = lib.evaluators._iou_boxes_pred_vs_true(g["pred_labels"][i], g["pred_boxes"][i], g["gt_labels"][i],
+                                                     g["gt_boxes"][i])
+        assert np.array_equal(iou, g["iou"][i])                          # IoU matrix bit-exact
+    z = lib.evaluators._iou_boxes_pred_vs_true(g["pred_labels"][0], g["pred_boxes"][0], [], np.zeros((0, 4)))
+    assert np.array_equal(z, g["iou_nogt"])
+    for thr, key in ((0.5, "ap50"), (0.6, "ap60"), (0.7, "ap70")):
+        ap = lib.evaluators.average_precision_object_detection(g["pred_labels"], g["pred_conf"], g["pred_boxes"], thr,
+                                                               paths, [0, 1, 2, 3], 0)
+        np.testing.assert_allclose([ap[1], ap[2], ap[3]], g[key], rtol=0, atol=1e-12)
+
+
+def test_eval_tp_flags_and_counts(lib):
+    rng = np.random.default_rng(1997)
+    N, K, G, C = 64, 200, 16, 4
+    gl, gb, gc = orc.synth_gt(rng, N, G, integer=True)
+    gc = rng.integers(0, G + 1, size=N).astype(np.int32)
+    pl = rng.integers(0, C, size=(N, K)).astype(np.int32)
+    pick = rng.integers(0, G, size=(N, K))
+    pb = (np.take_along_axis(gb, pick[..., None].repeat(4, -1), axis=1) + rng.normal(0, 10, (N, K, 4))).astype(np.float32)
+    for thr in (0.5, 0.6, 0.7):
+        tp, counts = lib.evaluators.true_positives_and_counts(pl, pb, gl, gb, gc, thr, C, 0)
+        ref = np.stack([orc.eval_tp_flags(pl[i], pb[i], gl[i, :gc[i]], gb[i, :gc[i]], thr, 0) for i in range(N)])
+        assert np.array_equal(tp, ref)
+        for c in range(C):
+            sc = (pl == c) & (pl != 0)
+            assert counts[c, 0] == ref[sc].sum() and counts[c, 1] == sc.sum() - ref[sc].sum()
+            assert counts[c, 2] == sum((gl[i, :gc[i]] == c).sum() for i in range(N))
+
+
+# ------------------------------------------------------------------------------------------- C ABI details
+def test_error_paths_and_workspace(lib, coder):
+    import ctypes as C
+
+    import torch
+
+    s = lib._ssdx
+    assert s.version() == 100
+    with pytest.raises(ValueError):
+        s.Anchors(np.zeros((0, 4), np.float32), None)
+    gt = torch.zeros((2, 4, 4), device="cuda")
+    lab = torch.zeros((2, 4), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((2,), dtype=torch.int32, device="cuda")
+    out_l = torch.empty((2, 9600, 4), device="cuda")
+    out_o = torch.empty((2, 9600, 4), device="cuda")
+    st = s.lib.ssdx_encode(coder._anchors.handle, gt.data_ptr(), lab.data_ptr(), cnt.data_ptr(), 2, 4, 4, 0.5,
+                           s.std_array(STD), out_l.data_ptr(), out_o.data_ptr(), None, None, 0, None)
+    assert st == s.SSDX_ERR_WORKSPACE and b"workspace" in s.lib.ssdx_last_error()
+    assert s.lib.ssdx_encode_workspace_bytes(9600, 2, 4) >= 2 * 9600 * 4 + 2 * 4 * 8
+    n = C.c_int(0)
+    assert s.lib.ssdx_device_count(C.byref(n)) == 0 and n.value >= 1
