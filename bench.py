@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py - images/s of the SSD box path (encode -> decode -> NMS round trip) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+    encode(GT boxes) -> labels, offsets ; decode(offsets) -> boxes ; NMS(boxes, scores) -> detections
+with B = 1024 images per GPU, A = 9600 anchors, G = 16 GT boxes, C = 4 classes, top-200.  Images are
+independent: ranks shard the batch with no data-path collective ("scaling": "weak", 1024 images per GPU).
+
+`value`  : device-timed (CUDA events, max over ranks), inputs resident in HBM, C ABI called directly.
+`e2e`    : same step through the public ssdseglib API; every step copies the step's inputs (GT + class
+           scores) from pinned host memory and reads the detections back to the host.
+`roofline`: dominant stage, algorithmic bytes / measured stage time vs the measured HBM copy peak.
+`cpu_baseline` / `--impl reference`: the C/OpenMP port of the reference path (oracle/ssd_oracle.c) on the
+           host cores of this box (TensorFlow 2.13, the reference's backend, cannot be installed here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "multi-task-learning-object-detection-semantic-segmentation_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+STD = (0.1, 0.1, 0.2, 0.2)
+A_STD, G_STD, C_STD, K_STD = 9600, 16, 4, 200
+BYTES_PER_IMAGE = {  # BASELINE.md section 3 (algorithmic / compulsory HBM traffic)
+    "encode": 20 * G_STD + 4 * A_STD * (C_STD + 4),
+    "decode": 32 * A_STD,
+    "nms": 16 * A_STD + 4 * A_STD * C_STD + 24 * K_STD,
+}
+WORKLOADS = {
+    "roundtrip_b1024": dict(batch=1024, stages=("encode", "decode", "nms")),
+    "decode_nms_b64": dict(batch=64, stages=("decode", "nms")),  # BASELINE config 1
+}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic inputs: GT generator of config 1; scores = 0.9*onehot + 0.1*softmax(noise)
+# ----------------------------------------------------------------------------------------------------------
+def make_inputs(batch: int, seed: int):
+    from oracle import ssd_oracle as orc  # generators only (input synthesis, not the measured path)
+
+    rng = np.random.default_rng(seed)
+    anchors = orc.anchors_generate(**orc.STD_ANCHOR_CFG)
+    labels, boxes, counts = orc.synth_gt(rng, batch, G_STD)
+    return anchors, labels, boxes, counts
+
+
+def make_scores_torch(onehot, seed: int):
+    """scores = 0.9 * one-hot targets + 0.1 * softmax(N(0,1) logits), generated on the device once (setup)."""
+    import torch
+
+    g = torch.Generator(device=onehot.device)
+    g.manual_seed(seed)
+    noise = torch.randn(onehot.shape, generator=g, device=onehot.device, dtype=torch.float32)
+    return (0.9 * onehot + 0.1 * torch.softmax(noise, dim=-1)).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) running during the timed regions
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: C/OpenMP port of the reference path
+# ----------------------------------------------------------------------------------------------------------
+def cpu_roundtrip(c_oracle, anchors, cent, labels, boxes, counts, scores, stages, threads):
+    """One pass of the same stages over `len(boxes)` images on the host."""
+    off = None
+    if "encode" in stages:
+        _, off, _ = c_oracle.encode_batch(anchors, labels, boxes, counts, C_STD, 0.5, STD, nthreads=threads,
+                                          want_match=False)
+    else:
+        off = scores[1]
+    yxyx = c_oracle.decode_batch(cent, off, STD, mode=0, nthreads=threads)
+    return c_oracle.combined_nms(yxyx, scores[0], K_STD, K_STD, 0.45, 0.01, nthreads=threads)
+
+
+def cpu_inputs(batch, seed, stages):
+    from oracle import ssd_oracle as orc
+
+    anchors, labels, boxes, counts = make_inputs(batch, seed)
+    cent = np.stack(orc.corners_to_centroids(*[anchors[:, i] for i in range(4)]), 1).astype(np.float32)
+    rng = np.random.default_rng(seed + 7)
+    if "encode" in stages:
+        onehot, _, _ = orc.encode_batch(anchors, labels, boxes, counts, C_STD, 0.5, STD)
+        scores = (np.float32(0.9) * onehot + np.float32(0.1) * orc.softmax_f32(rng.normal(0, 1, onehot.shape)))
+        pred_off = None
+    else:
+        pred_off, scores = orc.synth_predictions(rng, batch, A_STD, C_STD)
+    return anchors, cent, labels, boxes, counts, (scores.astype(np.float32), pred_off)
+
+
+def run_cpu_sample(stages, sample_images, seed, threads, repeats=1):
+    from oracle import c_oracle
+
+    c_oracle.build()
+    anchors, cent, labels, boxes, counts, scores = cpu_inputs(sample_images, seed, stages)
+    cpu_roundtrip(c_oracle, anchors, cent, labels[:threads], boxes[:threads], counts[:threads],
+                  (scores[0][:threads], None if scores[1] is None else scores[1][:threads]), stages, threads)  # warm
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_roundtrip(c_oracle, anchors, cent, labels, boxes, counts, scores, stages, threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample_images / best, best
+
+
+def reference_arm(args, rank):
+    """`--impl reference`: the host-CPU port of the reference path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    sample = max(threads * 8, 128)
+    from oracle import c_oracle
+
+    c_oracle.build()
+    anchors, cent, labels, boxes, counts, scores = cpu_inputs(sample, 1995, wl["stages"])
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        cpu_roundtrip(c_oracle, anchors, cent, labels, boxes, counts, scores, wl["stages"], threads)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "images/sec encode+decode+NMS", "value": value, "unit": "images/s",
+        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "stages": list(wl["stages"]), "anchors": A_STD, "gt_per_image": G_STD,
+                   "classes": C_STD, "max_total": K_STD, "images_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} images per step of the {args.workload} workload, C/OpenMP port "
+                                   f"(oracle/ssd_oracle.c), {threads} threads"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def gpu_arm(args, rank, world, local_rank):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    import __graft_entry__ as entry
+
+    if rank == 0:
+        entry.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    import ssdseglib
+    from ssdseglib import _ssdx as sx
+
+    wl = WORKLOADS[args.workload]
+    B, stages = wl["batch"], wl["stages"]
+    anchors, labels, boxes, counts = make_inputs(B, 1995 + rank)
+    coder = ssdseglib.datacoder.DataEncoderDecoder(C_STD, (480, 640), anchors[:, 0], anchors[:, 1], anchors[:, 2],
+                                                   anchors[:, 3], iou_threshold=0.5,
+                                                   standard_deviations_centroids_offsets=STD, device=dev)
+    dec_layer = ssdseglib.layers.DecodeBoxesCentroidsOffsets(coder.center_x_boxes_default, coder.center_y_boxes_default,
+                                                             coder.width_boxes_default, coder.height_boxes_default,
+                                                             *STD, device=dev)
+    nms_layer = ssdseglib.layers.NonMaximumSuppression(K_STD, K_STD, 0.45, 0.01, False)
+    handle = coder._anchors.handle
+
+    # pinned host inputs (the e2e leg copies from these every step)
+    h_boxes = torch.from_numpy(boxes).pin_memory()
+    h_labels = torch.from_numpy(labels).pin_memory()
+    h_counts = torch.from_numpy(counts).pin_memory()
+    d_boxes, d_labels, d_counts = h_boxes.cuda(dev), h_labels.cuda(dev), h_counts.cuda(dev)
+    # setup (untimed): class scores derived from the encoded targets, resident in HBM
+    if "encode" in stages:
+        onehot, _ = coder.encode_batch(d_boxes, d_labels, d_counts)
+        d_scores = make_scores_torch(onehot, 4242 + rank)
+        del onehot
+        d_pred_off = None
+    else:
+        from oracle import ssd_oracle as orc
+
+        off, sc = orc.synth_predictions(np.random.default_rng(1994 + rank), B, A_STD, C_STD)
+        d_scores, d_pred_off = torch.from_numpy(sc).cuda(dev), torch.from_numpy(off).cuda(dev)
+    h_scores = d_scores.cpu().pin_memory()
+    h_pred_off = None if d_pred_off is None else d_pred_off.cpu().pin_memory()
+
+    # preallocated outputs + workspaces; the C ABI is called directly (no allocation in the timed region)
+    f32 = dict(dtype=torch.float32, device=f"cuda:{dev}")
+    o_labels, o_offsets = torch.empty((B, A_STD, C_STD), **f32), torch.empty((B, A_STD, 4), **f32)
+    o_boxes, o_det = torch.empty((B, A_STD, 4), **f32), torch.empty((B, K_STD, 6), **f32)
+    o_valid = torch.empty((B,), dtype=torch.int32, device=f"cuda:{dev}")
+    ws_enc = torch.empty(max(sx.lib.ssdx_encode_workspace_bytes(A_STD, B, G_STD), 256), dtype=torch.uint8, device=f"cuda:{dev}")
+    ws_nms = torch.empty(max(sx.lib.ssdx_nms_workspace_bytes(B, A_STD, C_STD, K_STD, K_STD), 256), dtype=torch.uint8,
+                         device=f"cuda:{dev}")
+    std = sx.std_array(STD)
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    def step_device(events=None):
+        i = 0
+        if events is not None:
+            events[i].record(stream); i += 1
+        if "encode" in stages:
+            sx.check(sx.lib.ssdx_encode(handle, d_boxes.data_ptr(), d_labels.data_ptr(), d_counts.data_ptr(), B, G_STD,
+                                        C_STD, 0.5, std, o_labels.data_ptr(), o_offsets.data_ptr(), None,
+                                        ws_enc.data_ptr(), ws_enc.numel(), sp))
+            if events is not None:
+                events[i].record(stream); i += 1
+        src = o_offsets if "encode" in stages else d_pred_off
+        sx.check(sx.lib.ssdx_decode(dec_layer._anchors.handle, src.data_ptr(), B, std, 0, o_boxes.data_ptr(), sp))
+        if events is not None:
+            events[i].record(stream); i += 1
+        sx.check(sx.lib.ssdx_nms(o_boxes.data_ptr(), d_scores.data_ptr(), B, A_STD, C_STD, K_STD, K_STD, 0.45, 0.01,
+                                 o_det.data_ptr(), o_valid.data_ptr(), None, ws_nms.data_ptr(), ws_nms.numel(), dev, sp))
+        if events is not None:
+            events[i].record(stream)
+
+    kernels_per_step = (2 if "encode" in stages else 0) + 1 + 2  # + one memset node in encode
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    # ---------------- device-resident timing ----------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    n_ev = len(stages) + 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    t_start.record(stream)
+    for k in range(args.steps):
+        step_device(evs[k])
+    t_end.record(stream)
+    barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    stage_ms = {s: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
+                for i, s in enumerate(stages)}
+
+    # ---------------- end-to-end through the public API with host buffers ----------------
+    def step_e2e():
+        gb = h_boxes.to(f"cuda:{dev}", non_blocking=True)
+        gl = h_labels.to(f"cuda:{dev}", non_blocking=True)
+        gc = h_counts.to(f"cuda:{dev}", non_blocking=True)
+        sc = h_scores.to(f"cuda:{dev}", non_blocking=True)
+        if "encode" in stages:
+            _, off = coder.encode_batch(gb, gl, gc)
+        else:
+            off = h_pred_off.to(f"cuda:{dev}", non_blocking=True)
+        yx = dec_layer(off)
+        det = nms_layer(yx, sc)
+        return det.cpu()  # device -> host read of the step's result (synchronises)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        det_host = step_e2e()
+    e1.record(stream)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)
+    sampler.stop()
+
+    h2d = h_scores.numel() * 4 + (h_boxes.numel() * 4 + h_labels.numel() * 4 + h_counts.numel() * 4
+                                  if "encode" in stages else h_pred_off.numel() * 4)
+    d2h = det_host.numel() * 4
+
+    # ---------------- sanity: first images against the oracle (outside the timed regions) ----------------
+    check = "skipped"
+    if rank == 0:
+        from oracle import c_oracle
+        from oracle import ssd_oracle as orc
+
+        n_chk = 2
+        cent = np.stack(orc.corners_to_centroids(*[anchors[:, i] for i in range(4)]), 1).astype(np.float32)
+        yx = o_boxes[:n_chk].cpu().numpy()
+        ref_det, _, _ = c_oracle.combined_nms(yx, d_scores[:n_chk].cpu().numpy(), K_STD, K_STD, 0.45, 0.01)
+        ok = np.array_equal(ref_det, o_det[:n_chk].cpu().numpy())
+        if "encode" in stages:
+            rl, ro, _ = c_oracle.encode_batch(anchors, labels[:n_chk], boxes[:n_chk], counts[:n_chk], C_STD, 0.5, STD)
+            ok = ok and np.array_equal(rl, o_labels[:n_chk].cpu().numpy()) and np.allclose(
+                ro, o_offsets[:n_chk].cpu().numpy(), rtol=1e-5, atol=1e-6)
+        ok = ok and np.array_equal(det_host[:n_chk].numpy(), o_det[:n_chk].cpu().numpy())
+        check = "pass" if ok else "FAIL"
+
+    # ---------------- reduce over ranks ----------------
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms / 1e3)
+    e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        dom = max(stage_ms, key=stage_ms.get)
+        dom_bytes = BYTES_PER_IMAGE[dom] * B
+        achieved = dom_bytes / (stage_ms[dom] / 1e3) / 1e9
+        stage_roof = {s: {"ms": stage_ms[s], "gbs": BYTES_PER_IMAGE[s] * B / (stage_ms[s] / 1e3) / 1e9,
+                          "frac": BYTES_PER_IMAGE[s] * B / (stage_ms[s] / 1e3) / 1e9 / peak} for s in stages}
+        kernels = {"encode": "ssdx_encode_match_kernel + ssdx_encode_emit_kernel", "decode": "ssdx_decode_kernel",
+                   "nms": "ssdx_nms_class_kernel + ssdx_nms_merge_kernel"}
+        line = {
+            "metric": "images/sec encode+decode+NMS", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "stages": list(stages), "images_per_gpu": B, "global_batch": B * world,
+                       "anchors": A_STD, "gt_per_image": G_STD, "classes": C_STD, "max_total": K_STD,
+                       "score_thr": 0.01, "iou_thr": 0.45, "parallelism": f"batch-sharded x{world}, no collective",
+                       "l2": "no flush: each step streams %.0f MB (> 126 MB L2)" % (
+                           sum(BYTES_PER_IMAGE[s] for s in stages) * B / 1e6),
+                       "oracle_check": check},
+            "roofline": {"bound": "hbm", "kernel": kernels[dom], "stage": dom, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": dom_bytes, "stages": stage_roof,
+                         "roundtrip_frac": sum(BYTES_PER_IMAGE[s] for s in stages) * B / (ms_per_step / 1e3) / 1e9 / peak},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "ssdseglib.datacoder.DataEncoderDecoder.encode_batch -> layers.DecodeBoxesCentroidsOffsets"
+                           " -> layers.NonMaximumSuppression (inputs from pinned host memory, detections to host)"},
+            "gpu_launches": kernels_per_step * args.steps,
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = max(4 * threads, 64)
+            v, secs = run_cpu_sample(stages, sample, 1995, threads)
+            if secs < 3.0:
+                sample *= 4
+                v, secs = run_cpu_sample(stages, sample, 1995, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": f"{sample} images of the {args.workload} workload in {secs:.2f} s, "
+                                              f"C/OpenMP port of the reference (oracle/ssd_oracle.c)"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="roundtrip_b1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun so `python bench.py --gpus N` works on its own
+        import subprocess
+
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload",
+               args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+        raise SystemExit(subprocess.call(cmd))
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kMatchThreads)
       const unsigned mbits = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(mv));
       unsigned long long wb = 0ull;
       if (mbits != 0u) {  // warp-uniform
-        const unsigned tied = __ballot_sync(0xFFFFFFFFu, __float_as_uint(mv) == mbits);
-        const int amin = __reduce_min_sync(tied, ma);
+        // lowest anchor index among the lanes that tie on the maximum (every lane takes part in the REDUX)
+        const int amin = __reduce_min_sync(0xFFFFFFFFu, (__float_as_uint(mv) == mbits) ? ma : 0x7FFFFFFF);
         wb = pack_best(__uint_as_float(mbits), amin);
       }
       if (lane == 0) s_wbest[warp][g] = wb;  // each (warp, GT) is visited exactly once per tile

@@ -117,19 +117,32 @@ def workspace(nbytes: int, device: int):
     return buf
 
 
-def _pinned(shape, dtype, tag: str):
+class _PinnedSlot:
+    """Pinned staging buffer + the event of the last H2D copy that read it (the buffer must not be
+    overwritten by the host before that copy has executed)."""
+
+    __slots__ = ("buf", "event")
+
+    def __init__(self, buf):
+        self.buf = buf
+        self.event = None
+
+
+def _pinned(shape, dtype, tag: str) -> _PinnedSlot:
     """Cached pinned staging buffer per (thread, tag, shape, dtype)."""
     torch = _torch()
     cache = getattr(_tls, "pin", None)
     if cache is None:
         cache = _tls.pin = {}
     key = (tag, tuple(shape), dtype)
-    buf = cache.get(key)
-    if buf is None:
+    slot = cache.get(key)
+    if slot is None:
         if len(cache) > 64:
             cache.clear()
-        buf = cache[key] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
-    return buf
+        slot = cache[key] = _PinnedSlot(torch.empty(tuple(shape), dtype=dtype, pin_memory=True))
+    elif slot.event is not None:
+        slot.event.synchronize()
+    return slot
 
 
 _NP2T = {np.dtype(np.float32): "float32", np.dtype(np.int32): "int32", np.dtype(np.uint8): "uint8",
@@ -155,9 +168,12 @@ def to_device(x: Any, np_dtype, device: Optional[int] = None, tag: str = "x") ->
     a = np.ascontiguousarray(np.asarray(x), dtype=np_dtype)
     h = torch.from_numpy(a)
     if a.size and not h.is_pinned():
-        p = _pinned(a.shape, tdt, tag)
-        p.copy_(h)
-        h = p
+        slot = _pinned(a.shape, tdt, tag)
+        slot.buf.copy_(h)
+        d = slot.buf.to(f"cuda:{dev}", non_blocking=True)
+        slot.event = torch.cuda.Event()
+        slot.event.record(torch.cuda.current_stream(dev))
+        return d, "numpy"
     return h.to(f"cuda:{dev}", non_blocking=True), "numpy"
 
 
