@@ -22,6 +22,15 @@ def lib():
     return ssdseglib
 
 
+@pytest.fixture(autouse=True, params=["fused", "tiled"])
+def encode_path(request, monkeypatch):
+    """Every test runs against both encode drivers (one CTA per image / anchor-tiled + emit)."""
+    if request.param == "tiled" and "encode" not in request.node.name:
+        pytest.skip("encode driver does not matter for this test")
+    monkeypatch.setenv("SSDX_ENCODE_PATH", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def coder(lib, std_anchors):
     return lib.datacoder.DataEncoderDecoder(
