@@ -16,6 +16,11 @@ void ssdx_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool ssdx_debug_sync() {
+  const char* e = getenv("SSDX_DEBUG_SYNC");
+  return e != nullptr && e[0] == '1';
+}
+
 int ssdx_sm_count(int device) {
   static int cache[64] = {0};
   if (device < 0 || device >= 64) return 148;

@@ -36,11 +36,15 @@ void ssdx_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
+// SSDX_DEBUG_SYNC=1 in the environment makes every launch synchronous so a device fault names its kernel
+bool ssdx_debug_sync();
+
 #define SSDX_LAUNCH_CHECK(name)                                                     \
   do {                                                                              \
     cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ == cudaSuccess && ssdx_debug_sync()) e__ = cudaDeviceSynchronize();     \
     if (e__ != cudaSuccess) {                                                       \
-      ssdx_set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));     \
+      ssdx_set_error("kernel %s failed: %s", name, cudaGetErrorString(e__));        \
       return SSDX_ERR_CUDA;                                                         \
     }                                                                               \
   } while (0)

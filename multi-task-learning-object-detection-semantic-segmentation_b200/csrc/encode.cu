@@ -86,9 +86,9 @@ __device__ __forceinline__ void load_tile(AnchorTile& t, const float4* __restric
 }
 
 // All pairs (anchors of the tile) x (gn GT boxes in shared memory).  wrow[g] is this warp's running packed best.
-__device__ __forceinline__ void match_tile(AnchorTile& t, const float4* __restrict__ s_box,
-                                           const float* __restrict__ s_area, const int gn, const int g0,
-                                           u64* __restrict__ wrow, const int lane) {
+// (shared-memory pointers: no __restrict__, see nms.cu)
+__device__ __forceinline__ void match_tile(AnchorTile& t, const float4* s_box, const float* s_area, const int gn,
+                                           const int g0, u64* wrow, const int lane) {
   for (int g = 0; g < gn; ++g) {
     const float4 gb = s_box[g];
     // warp-uniform cull: the same expression as the pair intersection, evaluated on the tile's bounding box
@@ -131,7 +131,7 @@ __device__ __forceinline__ void match_tile(AnchorTile& t, const float4* __restri
 }
 
 // closed form of concat -> unique -> sequential scatter for one anchor
-__device__ __forceinline__ int resolve_match(int a, int g2, int s1max, const u64* __restrict__ gbest) {
+__device__ __forceinline__ int resolve_match(int a, int g2, int s1max, const u64* gbest) {
   if (g2 >= 0) {
     const u64 p = gbest[g2];
     const bool in_s1 = ((p >> 32) != 0ull) && (best_anchor(p) == a);

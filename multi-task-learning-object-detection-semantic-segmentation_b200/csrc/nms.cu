@@ -1,34 +1,66 @@
 // Per-class confidence-filtered NMS + cross-class merge
 // (reference: layers.py:127-168 -> tf.image.combined_non_max_suppression, q = 1, clip_boxes = False).
 //
-// Kernel 1, one CTA per (image, class):
-//   A. score filter (score > thr, strict) -> order-preserving 32-bit keys in shared memory;
-//   B. top-k' selection instead of a full sort: a 64-bit bisection on the composite key
-//      (score key << 32 | ~anchor) finds a threshold that leaves between kChunk/2 and kChunk
-//      candidates (all composite keys are distinct, so any tie pattern - e.g. thousands of scores equal
-//      to 1.0f - terminates and is visited lower anchor first);
-//   C. those candidates are compacted and bitonic-sorted in shared memory;
-//   D. greedy suppression in blocks of 64 sorted candidates: every candidate of the block is tested against
-//      the boxes already kept (8 threads per candidate), a 64x64 suppression bit-matrix of the block is built
-//      (one byte per thread), and one warp sweeps it cooperatively (ffs / shuffle / and-not), so the serial
-//      part is one step per KEPT box.  Stops at min(max_per_class, A); if the chunk runs dry the CTA goes
-//      back to B for the next k' candidates, so arbitrarily deep suppression chains stay exact.
-// Kernel 2, one CTA per image: rank-merges the C sorted pick lists (score desc; ties: lower class, lower
-//   anchor), keeps max_total rows and writes [label, prob, xmin, ymin, xmax, ymax] (layers.py:155-162),
-//   zero padding, valid counts and source anchor indices.
+// Pipeline (4 launches, stream-ordered, all state in the caller's workspace):
+//   1. select  : one CTA per (image, class group).  Scores are read coalesced (128-bit when C == 4).
+//                A 1/16 sample of the anchors gives, per class, the key of its m-th largest sample
+//                (warp-level bisection, REDUX only); a second pass appends every candidate with
+//                score > thr and key >= that threshold to a per-(image, class) list: the top ~400 of
+//                9600 candidates, unordered, as 64-bit composites (score key << 32 | ~anchor).
+//   2. fast    : one CTA per (image, class).  Sorts the list (bitonic, shared memory), then greedy
+//                suppression in blocks of 64 sorted candidates: each candidate is tested against the kept
+//                boxes (4 threads per candidate), the 64x64 overlap matrix of the block is built, and one
+//                warp resolves the block with a parallel fix-point (a candidate is kept once every earlier
+//                overlapping candidate is known suppressed; suppressed once one is known kept) - a few
+//                rounds instead of one serial step per box.  If the list overflowed, or ran dry before
+//                min(max_per_class, A) boxes were kept while candidates remain, the segment is flagged.
+//   3. generic : same grid, exits immediately unless flagged.  Exact for any input: keys of all
+//                candidates in shared memory, repeated top-k' selection by 64-bit bisection on the composite
+//                key (all keys distinct, so massive score ties terminate and are visited lower anchor first),
+//                bitonic sort, blocked suppression with a cooperative warp sweep.
+//   4. merge   : one CTA per image: rank-merges the C sorted pick lists (score desc; ties: lower class,
+//                lower anchor), keeps max_total rows and writes [label, prob, xmin, ymin, xmax, ymax]
+//                (layers.py:155-162), zero padding, valid counts and source anchor indices.
 //
 // IoU follows TF's IOU(): min/max-normalised corners, area = (y1-y0)*(x1-x0), 0 if either area <= 0,
 // inter / ((area_i + area_j) - inter) with IEEE division, suppressed iff IoU > iou_thr (strict).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int kNmsThreads = 512;
-constexpr int kChunk = 512;
+typedef unsigned long long u64;
+
+constexpr int kSelThreads = 256;
+constexpr int kSelGroup = 16;      // classes per select CTA
+constexpr int kSampleStride = 16;  // 1/16 of the anchors are sampled for the threshold estimate
+constexpr int kTierRank = 20;      // first tier ends at the 20th largest sample => ~320 +- 70 listed candidates
+constexpr int kInfo = 4;           // per segment: listed (tier 0), total candidates, key of the tier-0 threshold, pad
+constexpr int kCap = 1024;         // list capacity per (image, class) tier
+constexpr int kRefillTarget = 320; // candidates aimed at by each lazy refill of the fast kernel
+constexpr int kMaxRefills = 24;
+constexpr int kFastThreads = 256;
+constexpr int kFastMaxSel = 512;   // fast path keeps at most this many boxes per class
 constexpr int kBlk = 64;
+constexpr int kGenThreads = 512;
+constexpr int kChunk = 512;
 constexpr int kMergeThreads = 256;
 
-typedef unsigned long long u64;
+// Optional per-phase cycle counters of the fast kernel (debug builds only: -DSSDX_PHASE_TIMERS).
+#ifdef SSDX_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_T0() long long pt__ = clock64()
+#define PHASE_ADD(slot)                                                        \
+  do {                                                                         \
+    const long long now__ = clock64();                                         \
+    if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(now__ - pt__)); \
+    pt__ = now__;                                                              \
+  } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_ADD(slot) do {} while (0)
+#endif
 
 __device__ __forceinline__ unsigned score_to_key(float s) {
   const unsigned u = __float_as_uint(s);
@@ -49,63 +81,580 @@ __device__ __forceinline__ float4 normalise_box(const float4 b) {
 __device__ __forceinline__ float box_area(const float4 n) {
   return __fmul_rn(__fsub_rn(n.z, n.x), __fsub_rn(n.w, n.y));
 }
-__device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b, const float ab,
-                                            const float thr) {
-  if (!(aa > 0.0f) || !(ab > 0.0f)) return false;  // TF: IoU = 0, and thr >= 0
-  const float ih = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
-  const float iw = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
-  const float inter = __fmul_rn(ih, iw);
-  if (!(inter > 0.0f)) return false;  // IoU == 0 is never > thr >= 0
+// fl(x - y) > 0  <=>  x > y, so "intersection height and width > 0" is four compares on the normalised corners
+__device__ __forceinline__ bool boxes_overlap(const float4 a, const float4 b) {
+  return (a.z > b.x) & (b.z > a.x) & (a.w > b.y) & (b.w > a.y);  // predicate AND chain, no branches
+}
+// exact TF IoU test for a pair that overlaps
+__device__ __forceinline__ bool iou_exceeds_overlapping(const float4 a, const float aa, const float4 b, const float ab,
+                                                        const float thr) {
+  if (!(aa > 0.0f) || !(ab > 0.0f)) return false;  // TF: IoU = 0 when either area <= 0
+  const float ih = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  const float iw = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  const float inter = __fmul_rn(fmaxf(ih, 0.0f), fmaxf(iw, 0.0f));
   const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
   return iou > thr;
 }
+__device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b, const float ab,
+                                            const float thr) {
+  // disjoint boxes: IoU == 0 never exceeds thr >= 0
+  return boxes_overlap(a, b) && iou_exceeds_overlapping(a, aa, b, ab, thr);
+}
 
-struct NmsSmem {
-  unsigned* keys;   // [A]      0 = not a (remaining) candidate
-  u64* list;        // [kChunk] sorted composite keys of the current chunk
-  float4* cbox;     // [kChunk] normalised boxes of the chunk
-  float* carea;     // [kChunk]
-  float4* sbox;     // [limit]  normalised boxes kept so far
-  float* sarea;     // [limit]
-  u64* rowmask;     // [kBlk]   suppression bit-matrix of the current block
-  int* sup;         // [kBlk]   suppressed by an already kept box
-  int* ctr;         // [8]      0..2 rotating counters, 3 list_n, 4 n_sel, 5 candidates, 6 min key, 7 max key
+// in-place bitonic sort (descending) of N (power of two) u64 in shared memory by the whole CTA; N is a
+// compile-time constant so the stage/partner arithmetic folds into immediates
+template <int THREADS, int N>
+__device__ __forceinline__ void bitonic_sort_fixed(u64* v, const int tid) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int p0 = 0; p0 < (N >> 1); p0 += THREADS) {
+        const int p = p0 + tid;
+        if ((N >> 1) >= THREADS || p < (N >> 1)) {
+          const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+          const int q = i | j;
+          const u64 x = v[i], y = v[q];
+          const bool up = ((i & k) != 0);
+          if ((x < y) != up && x != y) {
+            v[i] = y;
+            v[q] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+template <int THREADS>
+__device__ __forceinline__ int bitonic_sort_desc(u64* v, const int n, const int tid) {
+  // pads [n, n_sort) with zeros (sorted last) and sorts; returns n_sort.  Uniform control flow.
+  int n_sort = 64;
+  while (n_sort < n) n_sort <<= 1;
+  for (int i = n + tid; i < n_sort; i += THREADS) v[i] = 0ull;
+  __syncthreads();
+  switch (n_sort) {
+    case 64: bitonic_sort_fixed<THREADS, 64>(v, tid); break;
+    case 128: bitonic_sort_fixed<THREADS, 128>(v, tid); break;
+    case 256: bitonic_sort_fixed<THREADS, 256>(v, tid); break;
+    case 512: bitonic_sort_fixed<THREADS, 512>(v, tid); break;
+    default: bitonic_sort_fixed<THREADS, 1024>(v, tid); break;
+  }
+  return n_sort;
+}
+
+// NOTE: helpers that take shared-memory pointers deliberately carry no __restrict__: with it nvcc moved the
+// caller's direct shared-memory accesses across the inlined exchange stages.
+// Bitonic sort (descending) of 256*EPT u64 held EPT per thread by a 256-thread CTA: element e = r*256 + tid.
+// Partner distance j < 32 -> warp shuffle, j >= 256 -> register exchange inside the thread, 32 <= j <= 128 ->
+// shared-memory exchange (double-buffered: one barrier per such stage).  9 barriers instead of 45 for 512 keys.
+template <int EPT>
+__device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64* buf1,
+                                                  const int tid) {
+  constexpr int N = 256 * EPT;
+  int flip = 0;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 256) {
+        constexpr int dummy = 0;
+        (void)dummy;
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+          const int rp = r ^ (j >> 8);
+          if (rp > r) {  // the pair (r, rp) lives in this thread; r is the lower index
+            const int e = r * 256 + tid;
+            const bool desc = ((e & k) == 0);
+            const u64 a = v[r], b = v[rp];
+            const bool swap = desc ? (a < b) : (a > b);
+            v[r] = swap ? b : a;
+            v[rp] = swap ? a : b;
+          }
+        }
+      } else if (j < 32) {
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+          const int e = r * 256 + tid;
+          const u64 p = __shfl_xor_sync(0xFFFFFFFFu, v[r], j);
+          const bool take_max = (((e & j) == 0) == ((e & k) == 0));
+          const u64 mx = v[r] > p ? v[r] : p, mn = v[r] > p ? p : v[r];
+          v[r] = take_max ? mx : mn;
+        }
+      } else {
+        u64* buf = flip ? buf1 : buf0;
+        flip ^= 1;
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) buf[r * 256 + tid] = v[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < EPT; ++r) {
+          const int e = r * 256 + tid;
+          const u64 p = buf[e ^ j];
+          const bool take_max = (((e & j) == 0) == ((e & k) == 0));
+          const u64 mx = v[r] > p ? v[r] : p, mn = v[r] > p ? p : v[r];
+          v[r] = take_max ? mx : mn;
+        }
+      }
+    }
+  }
+}
+
+// sort s_list[0..n) descending for the fast kernel (256 threads); uniform control flow
+__device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n,
+                                          const int tid) {
+  if (n <= 512) {
+    u64 v[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) v[r] = (r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
+    __syncthreads();
+    bitonic_sort_regs<2>(v, s_list, s_tmp, tid);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) s_list[r * 256 + tid] = v[r];
+  } else {
+    u64 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[r] = (r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
+    __syncthreads();
+    bitonic_sort_regs<4>(v, s_list, s_tmp, tid);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s_list[r * 256 + tid] = v[r];
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------ 1. select
+template <bool VEC4>
+__global__ void __launch_bounds__(kSelThreads)
+    ssdx_nms_select_kernel(const float* __restrict__ scores, const int A, const int C, const float score_thr,
+                           u64* __restrict__ lists, int* __restrict__ info, int* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * kSelGroup;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) flags[0] = 0;  // worklist of the generic kernel
+  const int cg = min(kSelGroup, C - c0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NS = (A + kSampleStride - 1) / kSampleStride;
+  unsigned* skeys = (unsigned*)smem_raw;          // [cg][NS] sample keys
+  unsigned* tk = skeys + (size_t)cg * NS;         // [kSelGroup] key of the tier-0 threshold per class
+  int* cnt = (int*)(tk + kSelGroup);              // [kSelGroup] listed candidates (tier 0)
+  int* tot = cnt + kSelGroup;                     // [kSelGroup] all candidates (score > thr)
+  const float* img = scores + (size_t)b * A * C;
+
+  if (tid < kSelGroup) {
+    cnt[tid] = 0;
+    tot[tid] = 0;
+  }
+  // ---- sample ----
+  for (int k = tid; k < NS; k += kSelThreads) {
+    int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
+    a = a < A ? a : A - 1;
+    if (VEC4) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(img) + a);
+      skeys[0 * NS + k] = (s.x > score_thr) ? score_to_key(s.x) : 0u;
+      skeys[1 * NS + k] = (s.y > score_thr) ? score_to_key(s.y) : 0u;
+      skeys[2 * NS + k] = (s.z > score_thr) ? score_to_key(s.z) : 0u;
+      skeys[3 * NS + k] = (s.w > score_thr) ? score_to_key(s.w) : 0u;
+    } else {
+      for (int c = 0; c < cg; ++c) {
+        const float s = __ldg(img + (size_t)a * C + c0 + c);
+        skeys[c * NS + k] = (s > score_thr) ? score_to_key(s) : 0u;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- tier-0 threshold: one warp per class finds a key with kTierRank .. kTierRank+3 samples at or above it
+  for (int c = warp; c < cg; c += kSelThreads / 32) {
+    const unsigned* keys = skeys + (size_t)c * NS;
+    int nv = 0;
+    unsigned kmax = 0u, kmin = 0xFFFFFFFFu;
+    for (int k = lane; k < NS; k += 32) {
+      const unsigned key = keys[k];
+      nv += key != 0u;
+      kmax = max(kmax, key);
+      kmin = min(kmin, key != 0u ? key : 0xFFFFFFFFu);
+    }
+    nv = __reduce_add_sync(0xFFFFFFFFu, nv);
+    kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+    kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
+    unsigned lo = 1u;  // count(key >= 1) = nv: every candidate
+    if (A > kCap && nv >= kTierRank) {
+      lo = kmin;                  // count(key >= kmin) = nv >= rank
+      unsigned hi = kmax + 1u;    // count = 0
+      while (hi - lo > 1u) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        int n = 0;
+        for (int k = lane; k < NS; k += 32) n += keys[k] >= mid;
+        n = __reduce_add_sync(0xFFFFFFFFu, n);
+        if (n >= kTierRank) {
+          lo = mid;
+          if (n <= kTierRank + 3) break;  // any threshold in this band will do
+        } else {
+          hi = mid;
+        }
+      }
+      if (lo == kmin && nv <= kTierRank + 3) lo = 1u;  // the whole sample is in the band: list every candidate
+    }
+    if (lane == 0) tk[c] = lo;
+  }
+  __syncthreads();
+  // ---- full scan: append every candidate of tier 0 (score >= first threshold) ----
+  u64* img_lists = lists + ((size_t)b * C + c0) * kCap;
+  if (VEC4) {
+    float tt[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tt[c] = (tk[c] <= 1u) ? -INFINITY : key_to_score(tk[c]);
+    int n_cand[4] = {0, 0, 0, 0};
+    constexpr int kBatch = 4;  // independent 128-bit streaming loads in flight per thread
+    for (int a0 = tid; a0 < A; a0 += kSelThreads * kBatch) {
+      float4 sb[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int a = a0 + u * kSelThreads;
+        sb[u] = (a < A) ? __ldcs(reinterpret_cast<const float4*>(img) + a) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int a = a0 + u * kSelThreads;
+        const float sv[4] = {sb[u].x, sb[u].y, sb[u].z, sb[u].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (sv[c] > score_thr) {  // false for the -inf padding
+            ++n_cand[c];
+            if (sv[c] >= tt[c]) {
+              const int pos = atomicAdd(&cnt[c], 1);
+              if (pos < kCap) img_lists[(size_t)c * kCap + pos] = make_comp(score_to_key(sv[c]), a);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = __reduce_add_sync(0xFFFFFFFFu, n_cand[c]);
+      if (lane == 0 && n) atomicAdd(&tot[c], n);
+    }
+  } else {
+    for (int c = 0; c < cg; ++c) {
+      const float t = (tk[c] <= 1u) ? -INFINITY : key_to_score(tk[c]);
+      int n_cand = 0;
+      for (int a = tid; a < A; a += kSelThreads) {
+        const float s = __ldg(img + (size_t)a * C + c0 + c);
+        if (s > score_thr) {
+          ++n_cand;
+          if (s >= t) {
+            const int pos = atomicAdd(&cnt[c], 1);
+            if (pos < kCap) img_lists[(size_t)c * kCap + pos] = make_comp(score_to_key(s), a);
+          }
+        }
+      }
+      n_cand = __reduce_add_sync(0xFFFFFFFFu, n_cand);
+      if (lane == 0 && n_cand) atomicAdd(&tot[c], n_cand);
+    }
+  }
+  __syncthreads();
+  if (tid < cg) {
+    int* dst = info + ((size_t)b * C + c0 + tid) * kInfo;
+    dst[0] = cnt[tid];
+    dst[1] = tot[tid];
+    dst[2] = (int)tk[tid];
+    dst[3] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ 2. fast path
+__global__ void __launch_bounds__(kFastThreads, 6)
+    ssdx_nms_fast_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                         const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
+                         const int limit, const float iou_thr, const float score_thr, u64* __restrict__ picks,
+                         int* __restrict__ pick_cnt, int* __restrict__ flags) {
+  __shared__ u64 s_list[kCap];
+  __shared__ u64 s_tmp[kCap];  // second exchange buffer of the sort
+  __shared__ float4 s_cbox[kFastThreads];
+  __shared__ float s_carea[kFastThreads];
+  __shared__ float4 s_sbox[kFastMaxSel];
+  __shared__ float s_sarea[kFastMaxSel];
+  __shared__ u64 s_row[kBlk];  // per candidate of the block: earlier candidates (j < i) that overlap it
+  __shared__ int s_sup[kBlk];
+  __shared__ int s_nsel, s_n;
+
+  const int c = blockIdx.x, b = blockIdx.y;
+  const size_t seg = (size_t)b * C + c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int* seg_info = info + seg * kInfo;
+  int n = seg_info[0];
+  const int total = seg_info[1];
+  if (n > kCap || limit > kFastMaxSel) {  // uniform
+    if (tid == 0) flags[1 + atomicAdd(&flags[0], 1)] = (int)seg;  // hand the segment to the generic kernel
+    return;
+  }
+  const float4* img_boxes = boxes + (size_t)b * A;
+  const float* img_scores = scores + (size_t)b * A * C + c;
+  u64* my_picks = picks + seg * limit;
+  const u64* lst = lists + seg * kCap;
+  PHASE_T0();
+  for (int i = tid; i < n; i += kFastThreads) s_list[i] = lst[i];
+  if (tid == 0) s_nsel = 0;
+  __syncthreads();
+  PHASE_ADD(0);  // list load
+
+  int n_sel = 0, consumed = 0, scans = 0;
+  bool failed = false;
+  unsigned key_hi = (unsigned)seg_info[2];  // every candidate with key >= key_hi has been listed
+  unsigned span = 0u;
+  while (true) {
+    // ---- sort the current tier (descending score, ties -> lower anchor) ----
+    fast_sort(s_list, s_tmp, n, tid);
+    PHASE_ADD(1);  // sort
+    consumed += n;
+    if (span == 0u) {  // key width that held the lower half of this tier -> width expected to hold kRefillTarget
+      const unsigned k_mid = (n >= 2) ? (unsigned)(s_list[n >> 1] >> 32) : 0u;
+      const unsigned k_bot = (n >= 2) ? (unsigned)(s_list[n - 1] >> 32) : 0u;
+      const u64 w = (n >= 2) ? (u64)(k_mid - k_bot) * (2ull * kRefillTarget) / (u64)n : 0ull;
+      span = (w == 0ull) ? 1024u : (w > 0x7FFFFFFFull ? 0x7FFFFFFFu : (unsigned)w);
+    }
+
+    for (int g0 = 0; g0 < n && n_sel < limit; g0 += kFastThreads) {
+      const int gn = min(kFastThreads, n - g0);
+      if (tid < gn) {  // gather the boxes of the next 256 sorted candidates
+        const float4 nb = normalise_box(__ldg(img_boxes + comp_idx(s_list[g0 + tid])));
+        s_cbox[tid] = nb;
+        s_carea[tid] = box_area(nb);
+      }
+      __syncthreads();
+      PHASE_ADD(2);  // box gather
+      for (int base = 0; base < gn && n_sel < limit; base += kBlk) {
+        const int m = min(kBlk, gn - base);
+        const int ci = tid >> 2, part = tid & 3;
+        {
+          bool hit = false;
+          float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+          float ai = 0.f;
+          if (ci < m) {
+            bi = s_cbox[base + ci];
+            ai = s_carea[base + ci];
+          }
+          if (ai > 0.0f) {  // a box without area is never suppressed
+            // kept boxes, newest first (similar scores overlap most); 4 independent loads + 16 compares per trip,
+            // the exact IoU only for the rare overlapping pair
+            int s = n_sel - 1 - part;
+            for (; s >= 12 && !hit; s -= 16) {
+              const float4 b0 = s_sbox[s], b1 = s_sbox[s - 4], b2 = s_sbox[s - 8], b3 = s_sbox[s - 12];
+              const bool o0 = boxes_overlap(bi, b0), o1 = boxes_overlap(bi, b1), o2 = boxes_overlap(bi, b2),
+                         o3 = boxes_overlap(bi, b3);
+              if (o0 | o1 | o2 | o3) {
+                hit = (o0 && iou_exceeds_overlapping(bi, ai, b0, s_sarea[s], iou_thr)) ||
+                      (o1 && iou_exceeds_overlapping(bi, ai, b1, s_sarea[s - 4], iou_thr)) ||
+                      (o2 && iou_exceeds_overlapping(bi, ai, b2, s_sarea[s - 8], iou_thr)) ||
+                      (o3 && iou_exceeds_overlapping(bi, ai, b3, s_sarea[s - 12], iou_thr));
+              }
+            }
+            for (; s >= 0 && !hit; s -= 4) {
+              const float4 b0 = s_sbox[s];
+              if (boxes_overlap(bi, b0)) hit = iou_exceeds_overlapping(bi, ai, b0, s_sarea[s], iou_thr);
+            }
+          }
+          const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+          if (part == 0) s_sup[ci] = (ci >= m) || (((bal >> (lane & 28)) & 0xFu) != 0u);
+          // earlier candidates j < ci that overlap ci; this thread tests j = 4*jj + part (interleaved slices keep
+          // the four parts of a candidate on consecutive shared-memory addresses)
+          unsigned lo = 0u, hi = 0u;
+          if (ai > 0.0f && part < ci) {
+            unsigned ov = 0u;
+            const int nj = (ci - part + 3) >> 2;  // number of jj with 4*jj + part < ci
+            const int nj4 = (nj + 3) & ~3;        // stale slots beyond m / ci are masked below
+            for (int j0 = 0; j0 < nj4; j0 += 4) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                ov |= (unsigned)boxes_overlap(bi, s_cbox[base + 4 * (j0 + jj) + part]) << (j0 + jj);
+            }
+            if (nj < 16) ov &= (1u << nj) - 1u;
+            while (ov) {  // exact test for the few overlapping pairs
+              const int jj = __ffs(ov) - 1;
+              ov &= ov - 1u;
+              const int j = 4 * jj + part;
+              if (iou_exceeds_overlapping(bi, ai, s_cbox[base + j], s_carea[base + j], iou_thr)) {
+                if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
+              }
+            }
+          }
+          lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 1);
+          hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 1);
+          lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 2);
+          hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 2);
+          if (part == 0) s_row[ci] = ((u64)hi << 32) | (u64)lo;
+        }
+        __syncthreads();
+        PHASE_ADD(3);  // pair tests
+        if (warp == kFastThreads / 32 - 1) {  // the arbiter favours the highest warp id: keep the serial part there
+          // lane l owns candidates l (A) and l+32 (B) of the block; all masks are pairs of 32-bit words
+          const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
+          const u64 ra = s_row[lane], rb = s_row[lane + 32];
+          const unsigned a_lo = (unsigned)ra & lt;  // earlier overlappers of A (all in the low word)
+          const unsigned b_lo = (unsigned)rb, b_hi = (unsigned)(rb >> 32) & lt;  // earlier overlappers of B
+          unsigned supp_lo = __ballot_sync(0xFFFFFFFFu, s_sup[lane] != 0);
+          unsigned supp_hi = __ballot_sync(0xFFFFFFFFu, s_sup[lane + 32] != 0);
+          unsigned kept_lo = 0u, kept_hi = 0u;
+          // fix-point: the lowest undecided candidate is decided in every round
+          while ((kept_lo | supp_lo) != 0xFFFFFFFFu || (kept_hi | supp_hi) != 0xFFFFFFFFu) {
+            const bool und_a = !((kept_lo | supp_lo) & me), und_b = !((kept_hi | supp_hi) & me);
+            const bool a_hit = (a_lo & kept_lo) != 0u;
+            const bool b_hit = ((b_lo & kept_lo) | (b_hi & kept_hi)) != 0u;
+            const bool a_free = (a_lo & ~supp_lo) == 0u;                          // every earlier overlapper suppressed
+            const bool b_free = ((b_lo & ~supp_lo) | (b_hi & ~supp_hi)) == 0u;
+            const unsigned nk_lo = __ballot_sync(0xFFFFFFFFu, und_a && !a_hit && a_free);
+            const unsigned ns_lo = __ballot_sync(0xFFFFFFFFu, und_a && a_hit);
+            const unsigned nk_hi = __ballot_sync(0xFFFFFFFFu, und_b && !b_hit && b_free);
+            const unsigned ns_hi = __ballot_sync(0xFFFFFFFFu, und_b && b_hit);
+            kept_lo |= nk_lo;
+            supp_lo |= ns_lo;
+            kept_hi |= nk_hi;
+            supp_hi |= ns_hi;
+          }
+          const int room = limit - n_sel;
+          const int n_lo = __popc(kept_lo);
+          if (kept_lo & me) {
+            const int r = __popc(kept_lo & lt);
+            if (r < room) {
+              s_sbox[n_sel + r] = s_cbox[base + lane];
+              s_sarea[n_sel + r] = s_carea[base + lane];
+              my_picks[n_sel + r] = s_list[g0 + base + lane];
+            }
+          }
+          if (kept_hi & me) {
+            const int r = n_lo + __popc(kept_hi & lt);
+            if (r < room) {
+              s_sbox[n_sel + r] = s_cbox[base + lane + 32];
+              s_sarea[n_sel + r] = s_carea[base + lane + 32];
+              my_picks[n_sel + r] = s_list[g0 + base + lane + 32];
+            }
+          }
+          if (lane == 0) s_nsel = n_sel + min(room, n_lo + __popc(kept_hi));
+        }
+        __syncthreads();
+        PHASE_ADD(4);  // block resolve
+        n_sel = s_nsel;
+      }
+    }
+    if (n_sel >= limit || consumed >= total) break;
+    // ---- the tier ran dry and candidates remain: fetch the next key band [key_lo, key_hi) from the scores.
+    //      The band width adapts to the density seen so far; an over-full band is narrowed and rescanned. ----
+    bool got = false;
+    while (!got && !failed) {
+      if (key_hi <= 1u || ++scans > kMaxRefills) {
+        failed = true;
+        break;
+      }
+      const unsigned key_lo = (key_hi - 1u > span) ? key_hi - span : 1u;
+      __syncthreads();
+      if (tid == 0) s_n = 0;
+      __syncthreads();
+      for (int a0 = tid; a0 < A; a0 += kFastThreads * 8) {  // 8 independent loads in flight per thread
+        float sv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int a = a0 + u * kFastThreads;
+          sv[u] = (a < A) ? __ldg(img_scores + (size_t)a * C) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (sv[u] > score_thr) {  // false for the -inf padding
+            const unsigned key = score_to_key(sv[u]);
+            if (key >= key_lo && key < key_hi) {
+              const int pos = atomicAdd(&s_n, 1);
+              if (pos < kCap) s_list[pos] = make_comp(key, a0 + u * kFastThreads);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const int n_new = s_n;
+      if (n_new > kCap) {
+        if (span <= 1u) failed = true;  // more than kCap equal scores: cannot be split by a threshold
+        span = max(span >> 2, 1u);
+      } else {
+        n = n_new;
+        key_hi = key_lo;
+        if (n_new < kRefillTarget / 8) span = (span > 0x1FFFFFFFu) ? 0x7FFFFFFFu : span << 2;
+        else if (n_new < kRefillTarget / 2) span = (span > 0x3FFFFFFFu) ? 0x7FFFFFFFu : span << 1;
+        else if (n_new > kRefillTarget * 2) span = max(span >> 1, 1u);
+        got = n_new > 0 || key_lo <= 1u;
+      }
+    }
+    if (failed) break;
+    __syncthreads();
+    PHASE_ADD(5);  // refill scans
+  }
+  PHASE_ADD(6);
+  if (tid == 0) {
+#ifdef SSDX_PHASE_TIMERS
+    atomicAdd(&g_phase_cycles[8], 1ull);
+    atomicAdd(&g_phase_cycles[9], (unsigned long long)scans);
+    atomicAdd(&g_phase_cycles[10], (unsigned long long)consumed);
+#endif
+    const bool complete = !failed && ((n_sel >= limit) || (consumed >= total));
+    pick_cnt[seg] = n_sel;
+    if (!complete) flags[1 + atomicAdd(&flags[0], 1)] = (int)seg;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ 3. generic path
+struct GenSmem {
+  unsigned* keys;  // [A]      0 = not a (remaining) candidate
+  u64* list;       // [kChunk] sorted composite keys of the current chunk
+  float4* cbox;    // [kChunk] normalised boxes of the chunk
+  float* carea;    // [kChunk]
+  float4* sbox;    // [limit]  normalised boxes kept so far
+  float* sarea;    // [limit]
+  u64* rowmask;    // [kBlk]   suppression bit-matrix of the current block
+  int* sup;        // [kBlk]   suppressed by an already kept box
+  int* ctr;        // [8]      0..2 rotating counters, 3 list_n, 4 n_sel, 5 candidates, 6 min key, 7 max key
 };
 
-__host__ __device__ inline size_t nms_smem_bytes(int A, int limit) {
+__host__ __device__ inline size_t gen_smem_bytes(int A, int limit) {
   size_t s = 0;
-  s += (size_t)((A + 3) / 4 * 4) * 4;  // keys
-  s += (size_t)kChunk * 8;             // list
-  s += (size_t)kChunk * 16;            // cbox
-  s += (size_t)kChunk * 4;             // carea
-  s += (size_t)((limit + 3) / 4 * 4) * 16;  // sbox
-  s += (size_t)((limit + 3) / 4 * 4) * 4;   // sarea
-  s += (size_t)kBlk * 8;               // rowmask
-  s += (size_t)kBlk * 4;               // sup
-  s += 64;                             // counters
+  s += (size_t)((A + 3) / 4 * 4) * 4;        // keys
+  s += (size_t)kChunk * 8;                   // list
+  s += (size_t)kChunk * 16;                  // cbox
+  s += (size_t)kChunk * 4;                   // carea
+  s += (size_t)((limit + 3) / 4 * 4) * 16;   // sbox
+  s += (size_t)((limit + 3) / 4 * 4) * 4;    // sarea
+  s += (size_t)kBlk * 8;                     // rowmask
+  s += (size_t)kBlk * 4;                     // sup
+  s += 64;                                   // counters
   return s;
 }
 
-__global__ void __launch_bounds__(kNmsThreads)
-    ssdx_nms_class_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int A, const int C,
-                          const int limit, const float iou_thr, const float score_thr, u64* __restrict__ picks,
-                          int* __restrict__ pick_cnt) {
+__global__ void __launch_bounds__(kGenThreads)
+    ssdx_nms_generic_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int A,
+                            const int C, const int limit, const float iou_thr, const float score_thr,
+                            u64* __restrict__ picks, int* __restrict__ pick_cnt, const int* __restrict__ flags,
+                            const int num_segments) {
+  // persistent CTAs over the worklist of segments the fast path handed over (flags[0] = count, then ids);
+  // without a worklist (flags == nullptr) every segment of the grid-stride range is processed
+  const int n_work = (flags != nullptr) ? flags[0] : num_segments;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+  const int seg_id = (flags != nullptr) ? flags[1 + work] : work;
+  const int b = seg_id / C, c = seg_id - b * C;
+  __syncthreads();  // shared memory is reused across worklist items
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  NmsSmem sm;
+  GenSmem sm;
   {
     unsigned char* p = smem_raw;
     const int A4 = (A + 3) / 4 * 4, L4 = (limit + 3) / 4 * 4;
-    sm.cbox = (float4*)p;  p += (size_t)kChunk * 16;
-    sm.sbox = (float4*)p;  p += (size_t)L4 * 16;
-    sm.list = (u64*)p;     p += (size_t)kChunk * 8;
-    sm.rowmask = (u64*)p;  p += (size_t)kBlk * 8;
+    sm.cbox = (float4*)p;   p += (size_t)kChunk * 16;
+    sm.sbox = (float4*)p;   p += (size_t)L4 * 16;
+    sm.list = (u64*)p;      p += (size_t)kChunk * 8;
+    sm.rowmask = (u64*)p;   p += (size_t)kBlk * 8;
     sm.keys = (unsigned*)p; p += (size_t)A4 * 4;
-    sm.carea = (float*)p;  p += (size_t)kChunk * 4;
-    sm.sarea = (float*)p;  p += (size_t)L4 * 4;
-    sm.sup = (int*)p;      p += (size_t)kBlk * 4;
+    sm.carea = (float*)p;   p += (size_t)kChunk * 4;
+    sm.sarea = (float*)p;   p += (size_t)L4 * 4;
+    sm.sup = (int*)p;       p += (size_t)kBlk * 4;
     sm.ctr = (int*)p;
   }
-  const int c = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* img_boxes = boxes + (size_t)b * A;
   const float* img_scores = scores + (size_t)b * A * C + c;
@@ -118,7 +667,7 @@ __global__ void __launch_bounds__(kNmsThreads)
   {
     int n = 0;
     unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
-    for (int i = tid; i < A; i += kNmsThreads) {
+    for (int i = tid; i < A; i += kGenThreads) {
       const float s = __ldg(img_scores + (size_t)i * C);
       unsigned k = 0u;
       if (s > score_thr) {
@@ -157,7 +706,7 @@ __global__ void __launch_bounds__(kNmsThreads)
       while (true) {
         const u64 mid = lo + ((hi - lo) >> 1);
         int cnt = 0;
-        for (int i = tid; i < A; i += kNmsThreads) cnt += (make_comp(sm.keys[i], i) >= mid && sm.keys[i] != 0u) ? 1 : 0;
+        for (int i = tid; i < A; i += kGenThreads) cnt += (make_comp(sm.keys[i], i) >= mid) ? 1 : 0;
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
         const int slot = it % 3;
         if (lane == 0 && cnt) atomicAdd(&sm.ctr[slot], cnt);
@@ -178,7 +727,7 @@ __global__ void __launch_bounds__(kNmsThreads)
     // ---- C. compact + sort the chunk ----
     if (tid == 0) sm.ctr[3] = 0;
     __syncthreads();
-    for (int i = tid; i < A; i += kNmsThreads) {
+    for (int i = tid; i < A; i += kGenThreads) {
       const unsigned k = sm.keys[i];
       if (k != 0u) {
         const u64 cp = make_comp(k, i);
@@ -193,27 +742,8 @@ __global__ void __launch_bounds__(kNmsThreads)
     const int n = sm.ctr[3];
     remaining -= n;
     consumed_from = T;
-    for (int i = n + tid; i < kChunk; i += kNmsThreads) sm.list[i] = 0ull;
-    __syncthreads();
-    // bitonic sort, descending, kChunk elements, one compare-exchange per thread pair
-    for (int k = 2; k <= kChunk; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = tid; t < kChunk; t += kNmsThreads) {
-          const int p = t ^ j;
-          if (p > t) {
-            const u64 x = sm.list[t], y = sm.list[p];
-            const bool desc = ((t & k) == 0);
-            if (desc ? (x < y) : (x > y)) {
-              sm.list[t] = y;
-              sm.list[p] = x;
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    // boxes of the chunk
-    for (int i = tid; i < n; i += kNmsThreads) {
+    bitonic_sort_desc<kGenThreads>(sm.list, n, tid);
+    for (int i = tid; i < n; i += kGenThreads) {
       const float4 nb = normalise_box(__ldg(img_boxes + comp_idx(sm.list[i])));
       sm.cbox[i] = nb;
       sm.carea[i] = box_area(nb);
@@ -284,10 +814,12 @@ __global__ void __launch_bounds__(kNmsThreads)
     }
   }
   if (tid == 0) pick_cnt[(size_t)b * C + c] = n_sel;
+  }  // worklist loop
 }
 
+// ------------------------------------------------------------------------------------------ 4. merge
 // number of entries of a descending list whose score key is > k (strict) or >= k
-__device__ __forceinline__ int count_before(const u64* __restrict__ lst, int n, unsigned k, bool inclusive) {
+__device__ __forceinline__ int count_before(const u64* lst, int n, unsigned k, bool inclusive) {
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -301,11 +833,22 @@ __device__ __forceinline__ int count_before(const u64* __restrict__ lst, int n, 
 __global__ void __launch_bounds__(kMergeThreads)
     ssdx_nms_merge_kernel(const float4* __restrict__ boxes, const u64* __restrict__ picks,
                           const int* __restrict__ pick_cnt, const int A, const int C, const int limit, const int K,
-                          float* __restrict__ out, int* __restrict__ out_valid, int* __restrict__ out_idx) {
+                          const int stage_in_smem, float* __restrict__ out, int* __restrict__ out_valid,
+                          int* __restrict__ out_idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const u64* img_picks = picks + (size_t)b * C * limit;
   const int* cnt = pick_cnt + (size_t)b * C;
+  if (stage_in_smem) {  // the binary searches below then run on shared memory instead of L2
+    u64* s = (u64*)smem_raw;
+    for (int e = tid; e < C * limit; e += kMergeThreads) {
+      const int c = e / limit, j = e - c * limit;
+      s[e] = (j < cnt[c]) ? img_picks[e] : 0ull;
+    }
+    __syncthreads();
+    img_picks = s;
+  }
   int total = 0;
   for (int c = 0; c < C; ++c) total += cnt[c];
   const int valid = min(total, K);
@@ -316,7 +859,7 @@ __global__ void __launch_bounds__(kMergeThreads)
     const u64 cp = img_picks[(size_t)c * limit + j];
     const unsigned k = (unsigned)(cp >> 32);
     int rank = j;
-    for (int c2 = 0; c2 < C; ++c2)
+    for (int c2 = 0; c2 < C && rank < K; ++c2)
       if (c2 != c) rank += count_before(img_picks + (size_t)c2 * limit, cnt[c2], k, c2 < c);
     if (rank < K) {
       const int idx = comp_idx(cp);
@@ -339,15 +882,41 @@ __global__ void __launch_bounds__(kMergeThreads)
 
 inline int nms_limit(int max_per_class, int A) { return max_per_class < A ? max_per_class : A; }
 
+struct NmsWorkspace {
+  size_t picks, pick_cnt, lists, info, flags, total;
+};
+
+inline NmsWorkspace nms_workspace(int batch, int A, int C, int max_per_class) {
+  NmsWorkspace w;
+  const size_t seg = (size_t)batch * C;
+  const size_t limit = (size_t)nms_limit(max_per_class, A);
+  size_t off = 0;
+  w.picks = off;    off += ssdx_align_up(seg * limit * sizeof(u64), 256);
+  w.pick_cnt = off; off += ssdx_align_up(seg * sizeof(int), 256);
+  w.lists = off;    off += ssdx_align_up(seg * kCap * sizeof(u64), 256);
+  w.info = off;     off += ssdx_align_up(seg * kInfo * sizeof(int), 256);
+  w.flags = off;    off += ssdx_align_up((seg + 1) * sizeof(int), 256);
+  w.total = off;
+  return w;
+}
+
 }  // namespace
+
+#ifdef SSDX_PHASE_TIMERS
+// debug builds only: read and reset the phase counters of ssdx_nms_fast_kernel
+extern "C" __attribute__((visibility("default"))) int ssdx_debug_phase_cycles(unsigned long long* out16) {
+  unsigned long long zero[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(zero)) != cudaSuccess) return -2;
+  if (cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return -2;
+  return 0;
+}
+#endif
 
 extern "C" size_t ssdx_nms_workspace_bytes(int32_t batch, int32_t num_anchors, int32_t num_classes,
                                            int32_t max_per_class, int32_t max_total) {
   (void)max_total;
   if (batch <= 0 || num_anchors <= 0 || num_classes <= 0 || max_per_class <= 0) return 256;
-  const size_t limit = (size_t)nms_limit(max_per_class, num_anchors);
-  return ssdx_align_up((size_t)batch * num_classes * limit * sizeof(u64), 256) +
-         ssdx_align_up((size_t)batch * num_classes * sizeof(int), 256);
+  return nms_workspace(batch, num_anchors, num_classes, max_per_class).total;
 }
 
 extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t batch, int32_t num_anchors,
@@ -360,31 +929,72 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
   SSDX_CHECK_ARG(max_per_class > 0 && max_total > 0, "ssdx_nms: max_per_class and max_total must be > 0");
   SSDX_CHECK_ARG(iou_threshold >= 0.0f && iou_threshold <= 1.0f, "iou_threshold must be in [0, 1]");
   SSDX_CHECK_ARG(((uintptr_t)boxes_yxyx & 15) == 0, "ssdx_nms: boxes must be 16-byte aligned");
-  SSDX_CHECK_ARG(batch <= 65535 && num_classes <= 65535, "ssdx_nms: batch and classes must be <= 65535 per call");
+  SSDX_CHECK_ARG(batch <= 65535 && num_classes <= 65535 && (long long)batch * num_classes < (1ll << 30),
+                 "ssdx_nms: batch and classes must be <= 65535 per call");
   if (batch == 0) return SSDX_OK;
-  const int limit = nms_limit(max_per_class, num_anchors);
-  const size_t need = ssdx_nms_workspace_bytes(batch, num_anchors, num_classes, max_per_class, max_total);
-  if (workspace == nullptr || workspace_bytes < need) {
-    ssdx_set_error("ssdx_nms: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+  const int A = num_anchors, C = num_classes;
+  const int limit = nms_limit(max_per_class, A);
+  const NmsWorkspace w = nms_workspace(batch, A, C, max_per_class);
+  if (workspace == nullptr || workspace_bytes < w.total) {
+    ssdx_set_error("ssdx_nms: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
     return SSDX_ERR_WORKSPACE;
   }
   SSDX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "ssdx_nms: workspace must be 256-byte aligned");
-  const size_t smem = nms_smem_bytes(num_anchors, limit);
-  SSDX_CHECK_ARG(smem <= 227 * 1024,
-                 "ssdx_nms: num_anchors=%d with max_per_class=%d needs %zu B of shared memory (limit 232448)",
-                 num_anchors, max_per_class, smem);
+  const size_t gen_smem = gen_smem_bytes(A, limit);
+  SSDX_CHECK_ARG(gen_smem <= 227 * 1024,
+                 "ssdx_nms: num_anchors=%d with max_per_class=%d needs %zu B of shared memory (limit 232448)", A,
+                 max_per_class, gen_smem);
   SSDX_CUDA(cudaSetDevice(device));
   cudaStream_t s = (cudaStream_t)stream;
-  u64* picks = (u64*)workspace;
-  int* pick_cnt = (int*)((char*)workspace + ssdx_align_up((size_t)batch * num_classes * limit * sizeof(u64), 256));
-  SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(num_classes, batch);
-  ssdx_nms_class_kernel<<<grid, kNmsThreads, smem, s>>>((const float4*)boxes_yxyx, scores, num_anchors, num_classes,
-                                                        limit, iou_threshold, score_threshold, picks, pick_cnt);
-  SSDX_LAUNCH_CHECK("ssdx_nms_class_kernel");
-  ssdx_nms_merge_kernel<<<batch, kMergeThreads, 0, s>>>((const float4*)boxes_yxyx, picks, pick_cnt, num_anchors,
-                                                        num_classes, limit, max_total, out, out_valid,
-                                                        out_anchor_idx);
+  char* base = (char*)workspace;
+  u64* picks = (u64*)(base + w.picks);
+  int* pick_cnt = (int*)(base + w.pick_cnt);
+  u64* lists = (u64*)(base + w.lists);
+  int* info = (int*)(base + w.info);
+  int* flags = (int*)(base + w.flags);
+  const float4* bx = (const float4*)boxes_yxyx;
+
+  // 1. select
+  const int NS = (A + kSampleStride - 1) / kSampleStride;
+  const size_t sel_smem = (size_t)(C < kSelGroup ? C : kSelGroup) * NS * 4 + kSelGroup * 12 + 16;
+  const bool vec4 = (C == 4) && (((uintptr_t)scores & 15) == 0);
+  const char* force = getenv("SSDX_NMS_PATH");  // "generic": test hook, both paths give identical results
+  const bool use_fast = sel_smem <= 200 * 1024 && !(force != nullptr && force[0] == 'g');
+  if (use_fast) {
+    dim3 gsel((C + kSelGroup - 1) / kSelGroup, batch);
+    if (vec4) {
+      SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sel_smem));
+      ssdx_nms_select_kernel<true><<<gsel, kSelThreads, sel_smem, s>>>(scores, A, C, score_threshold, lists, info, flags);
+    } else {
+      SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sel_smem));
+      ssdx_nms_select_kernel<false><<<gsel, kSelThreads, sel_smem, s>>>(scores, A, C, score_threshold, lists, info, flags);
+    }
+    SSDX_LAUNCH_CHECK("ssdx_nms_select_kernel");
+    // 2. fast path
+    dim3 gseg(C, batch);
+    ssdx_nms_fast_kernel<<<gseg, kFastThreads, 0, s>>>(bx, scores, lists, info, A, C, limit, iou_threshold,
+                                                       score_threshold, picks, pick_cnt, flags);
+    SSDX_LAUNCH_CHECK("ssdx_nms_fast_kernel");
+  }
+  // 3. generic path (flag-gated; handles every segment when the fast path is not applicable)
+  SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));
+  const int num_segments = batch * C;
+  const int gen_grid = use_fast ? min(num_segments, 2 * ssdx_sm_count(device)) : num_segments;
+  ssdx_nms_generic_kernel<<<gen_grid, kGenThreads, gen_smem, s>>>(bx, scores, A, C, limit, iou_threshold,
+                                                                  score_threshold, picks, pick_cnt,
+                                                                  use_fast ? flags : nullptr, num_segments);
+  SSDX_LAUNCH_CHECK("ssdx_nms_generic_kernel");
+  // 4. merge
+  const size_t merge_smem = (size_t)C * limit * sizeof(u64);
+  const int stage = merge_smem <= 96 * 1024;
+  if (stage)
+    SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)merge_smem));
+  ssdx_nms_merge_kernel<<<batch, kMergeThreads, stage ? merge_smem : 0, s>>>(bx, picks, pick_cnt, A, C, limit,
+                                                                             max_total, stage, out, out_valid,
+                                                                             out_anchor_idx);
   SSDX_LAUNCH_CHECK("ssdx_nms_merge_kernel");
   return SSDX_OK;
 }

@@ -31,6 +31,17 @@ def encode_path(request, monkeypatch):
     return request.param
 
 
+@pytest.fixture(autouse=True, params=["fast", "generic"])
+def nms_path(request, monkeypatch):
+    """NMS tests run on the fast pipeline (select + fast kernel, generic only for handed-over segments) and
+    with the exact generic kernel alone."""
+    if request.param == "generic":
+        if "nms" not in request.node.name:
+            pytest.skip("NMS driver does not matter for this test")
+        monkeypatch.setenv("SSDX_NMS_PATH", "generic")
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def coder(lib, std_anchors):
     return lib.datacoder.DataEncoderDecoder(
