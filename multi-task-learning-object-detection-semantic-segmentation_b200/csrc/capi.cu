@@ -3,6 +3,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <math.h>
+
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -73,25 +76,98 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
     memcpy(dec.data(), centroids_host, 4 * A * sizeof(float));
   else
     dec = enc;
+  // ---- match order (encode): sort by (area half-octave descending, Morton code of the centre), tile, bound ----
+  const float inf = INFINITY;
+  double cx_lo = 1e300, cx_hi = -1e300, cy_lo = 1e300, cy_hi = -1e300;
+  for (size_t a = 0; a < A; ++a) {
+    const double cx = enc[4 * a + 0], cy = enc[4 * a + 1];
+    if (std::isfinite(cx)) { cx_lo = std::min(cx_lo, cx); cx_hi = std::max(cx_hi, cx); }
+    if (std::isfinite(cy)) { cy_lo = std::min(cy_lo, cy); cy_hi = std::max(cy_hi, cy); }
+  }
+  auto spread = [](uint32_t v) {  // 16 bits -> even bit positions
+    v &= 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+  };
+  auto quant = [](double v, double lo, double hi) -> uint32_t {
+    if (!(hi > lo) || !std::isfinite(v)) return 0u;
+    const double q = (v - lo) / (hi - lo) * 1023.0;
+    return (uint32_t)std::min(1023.0, std::max(0.0, q));
+  };
+  std::vector<uint64_t> key(A);
+  for (size_t a = 0; a < A; ++a) {
+    const float ar = area[a];
+    int bucket = 0;  // degenerate anchors (area <= 0, NaN) sort last; they never intersect anything
+    if (ar > 0.0f && std::isfinite(ar)) bucket = 600 + (int)floor(2.0 * log2((double)ar));
+    bucket = std::min(1023, std::max(0, bucket));
+    const uint32_t m = spread(quant(enc[4 * a + 0], cx_lo, cx_hi)) | (spread(quant(enc[4 * a + 1], cy_lo, cy_hi)) << 1);
+    key[a] = ((uint64_t)(1023 - bucket) << 52) | ((uint64_t)m << 32) | (uint64_t)a;  // index: total order
+  }
+  std::sort(key.begin(), key.end());
+  const size_t n_tiles = (A + kSsdxTile - 1) / kSsdxTile, Ap = n_tiles * kSsdxTile;
+  std::vector<float> m_box(4 * Ap), m_area(Ap, 1.0f), t_bbox(4 * n_tiles), t_area(2 * n_tiles);
+  std::vector<int> m_idx(Ap, -1);
+  for (size_t i = 0; i < Ap; ++i) {
+    if (i < A) {
+      const size_t a = (size_t)(key[i] & 0xFFFFFFFFull);
+      memcpy(&m_box[4 * i], corners_xyxy_host + 4 * a, 4 * sizeof(float));
+      m_area[i] = area[a];
+      m_idx[i] = (int)a;
+    } else {
+      m_box[4 * i + 0] = inf; m_box[4 * i + 1] = inf; m_box[4 * i + 2] = -inf; m_box[4 * i + 3] = -inf;
+    }
+  }
+  for (size_t t = 0; t < n_tiles; ++t) {
+    float bx0 = inf, by0 = inf, bx1 = -inf, by1 = -inf, amin = inf, amax = -inf;
+    bool odd = false;
+    for (size_t i = t * kSsdxTile; i < (t + 1) * kSsdxTile && i < A; ++i) {
+      bx0 = std::min(bx0, m_box[4 * i + 0]); by0 = std::min(by0, m_box[4 * i + 1]);
+      bx1 = std::max(bx1, m_box[4 * i + 2]); by1 = std::max(by1, m_box[4 * i + 3]);
+      amin = std::min(amin, m_area[i]); amax = std::max(amax, m_area[i]);
+      odd = odd || !(m_area[i] > 0.0f) || !std::isfinite(m_area[i]) || !std::isfinite(m_box[4 * i + 0]) ||
+            !std::isfinite(m_box[4 * i + 1]) || !std::isfinite(m_box[4 * i + 2]) || !std::isfinite(m_box[4 * i + 3]);
+    }
+    if (odd) {  // no culling at all for a tile holding a degenerate or non-finite anchor
+      bx0 = by0 = -inf; bx1 = by1 = inf; amin = 0.0f; amax = inf;
+    }
+    t_bbox[4 * t + 0] = bx0; t_bbox[4 * t + 1] = by0; t_bbox[4 * t + 2] = bx1; t_bbox[4 * t + 3] = by1;
+    t_area[2 * t + 0] = amin; t_area[2 * t + 1] = amax;
+  }
+
   ssdx_anchors* h = (ssdx_anchors*)calloc(1, sizeof(ssdx_anchors));
   SSDX_CHECK_ARG(h != nullptr, "ssdx_anchors_create: out of host memory");
   h->device = device;
   h->A = num_anchors;
+  h->n_tiles = (int32_t)n_tiles;
   cudaError_t e = cudaSuccess;
-  // one allocation: corners | enc_cent | dec_cent | area
+  // one allocation: corners | enc_cent | dec_cent | m_box | t_bbox | t_area | area | m_area | m_idx
   char* base = nullptr;
-  const size_t bytes = A * (3 * sizeof(float4) + sizeof(float));
+  const size_t bytes = A * (3 * sizeof(float4) + sizeof(float)) + Ap * (sizeof(float4) + sizeof(float) + sizeof(int)) +
+                       n_tiles * (sizeof(float4) + sizeof(float2));
   e = cudaMalloc((void**)&base, bytes);
   if (e == cudaSuccess) {
     h->corners = (float4*)base;
     h->enc_cent = h->corners + A;
     h->dec_cent = h->enc_cent + A;
-    h->area = (float*)(h->dec_cent + A);
+    h->m_box = h->dec_cent + A;
+    h->t_bbox = h->m_box + Ap;
+    h->t_area = (float2*)(h->t_bbox + n_tiles);
+    h->area = (float*)(h->t_area + n_tiles);
+    h->m_area = h->area + A;
+    h->m_idx = (int*)(h->m_area + Ap);
     e = cudaMemcpy(h->corners, corners_xyxy_host, A * sizeof(float4), cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) e = cudaMemcpy(h->enc_cent, enc.data(), A * sizeof(float4), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->dec_cent, dec.data(), A * sizeof(float4), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->area, area.data(), A * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->m_box, m_box.data(), Ap * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->m_area, m_area.data(), Ap * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->m_idx, m_idx.data(), Ap * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->t_bbox, t_bbox.data(), n_tiles * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->t_area, t_area.data(), n_tiles * sizeof(float2), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     ssdx_set_error("ssdx_anchors_create: CUDA error: %s", cudaGetErrorString(e));
     if (base) cudaFree(base);

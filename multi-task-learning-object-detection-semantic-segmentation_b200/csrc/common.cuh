@@ -15,7 +15,19 @@ struct ssdx_anchors {
   float* area;       // (A) (y1-y0+1)*(x1-x0+1)                datacoder.py:111-114
   float4* enc_cent;  // (A) cx,cy,w,h re-derived from corners  datacoder.py:251-256
   float4* dec_cent;  // (A) cx,cy,w,h as the ctor holds them   datacoder.py:65-70 / :78-81
+  // "match order" copy for the encode pair loop: anchors sorted by (area half-octave, descending; Morton code of
+  // the centre) and cut into tiles of kSsdxTile, so that one tile is compact in space and in area and whole
+  // (tile, GT) pairs can be culled.  The permutation is free: both arg-max tie rules are index-based.
+  int32_t n_tiles;
+  float4* m_box;   // (n_tiles*kSsdxTile) corners; padding slots hold an empty box (+inf,+inf,-inf,-inf)
+  float* m_area;   // (n_tiles*kSsdxTile)
+  int* m_idx;      // (n_tiles*kSsdxTile) original anchor index, -1 for padding
+  float4* t_bbox;  // (n_tiles) bounding box of the tile's anchors
+  float2* t_area;  // (n_tiles) (min, max) anchor area in the tile
 };
+
+constexpr int kSsdxApt = 2;               // anchors per lane in one match tile
+constexpr int kSsdxTile = 32 * kSsdxApt;  // anchors per match tile
 
 void ssdx_set_error(const char* fmt, ...);
 

@@ -8,30 +8,43 @@
 //     g2(a) = argmax_g iou[a,:]  if  max_g iou[a,:] > thr
 //     match(a) = g2 if g2 exists and g2 not in S1(a);  else max(S1(a)) if non-empty;  else background.
 //
-// The A x G IoU matrix is never materialised.  The pair loop (match_tile) is shared by two drivers:
-//   fused  : one CTA per image (A and G small enough for shared memory: the reference configuration).
-//            Phase 1 walks the anchors in warp tiles of 32*kApt, keeps the per-anchor arg-max in
-//            registers -> int16 table in shared memory, and the per-GT arg-max per warp (REDUX on the IoU
-//            bit pattern, ties -> REDUX.MIN of the anchor index).  Phase 2 resolves the closed form and
-//            streams labels + offsets out with 128-bit coalesced stores.  No workspace traffic at all.
-//   tiled  : grid (anchor tiles, images) + a second emit kernel, for large A (dense stress: 100k anchors);
-//            the per-GT arg-max crosses CTAs through one 64-bit atomicMax per (CTA, GT).
-// Work reduction that keeps bit-exactness: (i) a warp tile whose bounding box misses the GT box skips its
-// 32*kApt pairs with one warp-uniform test (fp32 rounding is monotone, so the tile test is conservative);
-// (ii) pairs with empty intersection skip the division: their IoU is exactly +0 and can never win a strict
-// '>' comparison against a running best that starts at (0, index 0).
+// The A x G IoU matrix is never materialised and most of it is never evaluated.  Anchors are walked in the
+// "match order" built by ssdx_anchors_create (sorted by area half-octave, then Morton code of the centre; tiles of
+// kSsdxTile anchors with a bounding box and an area range).  A pair can only matter if
+//     iou > thr                 (anchor side, datacoder.py:236-241), or
+//     iou >= running best of g  (GT side, :230-231; '>=' because ties resolve to the lower anchor index),
+// i.e. if iou >= t(g) = min(max(thr,0), best(g)).  Three conservative tests (each one only ever skips pairs that
+// provably fail it; fp32 rounding is monotone, slack factors cover the rounding of the bounds themselves):
+//   (i)   tile bounding box misses the GT box           -> inter == 0 for every anchor of the tile;
+//   (ii)  area ratio: iou <= min(area)/max(area)         -> tile skipped if even that is < t(g);
+//   (iii) pair: iou <= inter / max(area_a, area_g)       -> division skipped if inter <= t(g)*max(area_g, tile min area).
+// (i)+(ii) are evaluated by 32 lanes for 32 GT boxes at once (ballot -> surviving GT list); (iii) costs one
+// compare per pair.  IoU == 0 pairs can never win a strict '>' against a running best that starts at (0, index 0).
+//
+// Two drivers share the pair loop:
+//   fused : one CTA per image (reference configuration).  98 % of the output rows are the constant background
+//           row, so the CTA starts by issuing TMA bulk stores (cp.async.bulk shared -> global) of constant
+//           background blocks for the whole image; they drain to HBM while the warps match.  After the match the
+//           few positive rows (~180 of 9600) are compacted, encoded densely and patched over the background.
+//   tiled : grid (anchor tiles, images) + a second emit kernel, for large A (dense stress: 100k anchors);
+//           the per-GT arg-max crosses CTAs through one 64-bit atomicMax per (CTA, GT).
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kApt = 4;             // anchors per thread per tile
+constexpr int kApt = kSsdxApt;      // anchors per lane per tile
 constexpr int kFusedThreads = 512;  // one CTA per image
-constexpr int kTiledThreads = 256;  // grid (tiles, images)
+constexpr int kTiledThreads = 256;  // grid (tile groups, images)
+constexpr int kTiledTilesPerCta = 16;
 constexpr int kGtTile = 256;        // GT boxes staged per shared-memory tile (tiled driver)
 constexpr int kEmitThreads = 256;
 constexpr int kFusedMaxG = 256;
+constexpr int kPosCap = 1024;   // compacted positives per image (more are encoded in place)
+constexpr int kBgRows = 512;    // background rows per bulk store (offsets: 8 KB per store)
+constexpr float kSlackUp = 1.0001f, kSlackDown = 0.9999f;
+constexpr unsigned kFull = 0xFFFFFFFFu;
 
 typedef unsigned long long u64;
 
@@ -40,6 +53,7 @@ __device__ __forceinline__ u64 pack_best(unsigned iou_bits, int a) {
   return ((u64)iou_bits << 32) | (u64)(0xFFFFFFFFu - (unsigned)a);
 }
 __device__ __forceinline__ int best_anchor(u64 p) { return (int)(0xFFFFFFFFu - (unsigned)(p & 0xFFFFFFFFull)); }
+__device__ __forceinline__ unsigned best_bits(const u64* p) { return reinterpret_cast<const unsigned*>(p)[1]; }
 
 __device__ __forceinline__ float gt_area(const float4 b) {
   // datacoder.py:206  (xmax-xmin+1)*(ymax-ymin+1)
@@ -49,95 +63,94 @@ __device__ __forceinline__ float gt_area(const float4 b) {
 struct AnchorTile {
   float4 box[kApt];
   float area[kApt];
-  int idx[kApt];
+  int idx[kApt];  // original anchor index, -1 = padding slot (empty box)
   float best_v[kApt];
   int best_g[kApt];
-  float4 bbox;  // warp-uniform bounding box of the 32*kApt anchors
 };
 
-// lane l of warp tile starting at `base` owns anchors base + u*32 + l (ascending in u)
-__device__ __forceinline__ void load_tile(AnchorTile& t, const float4* __restrict__ corners,
-                                          const float* __restrict__ area, int base, int lane, int A) {
-  const float inf = __int_as_float(0x7f800000);
-  float4 bb = make_float4(inf, inf, -inf, -inf);
+// lane l owns the match-order slots tile*kSsdxTile + u*32 + l
+__device__ __forceinline__ void load_tile(AnchorTile& t, const float4* __restrict__ m_box,
+                                          const float* __restrict__ m_area, const int* __restrict__ m_idx,
+                                          const int tile, const int lane) {
 #pragma unroll
   for (int u = 0; u < kApt; ++u) {
-    const int a = base + u * 32 + lane;
-    t.idx[u] = a;
-    const bool ok = a < A;
-    // out-of-range slot: empty box, inter == 0 against everything, neutral for the bounding box
-    t.box[u] = ok ? __ldg(corners + a) : make_float4(inf, inf, -inf, -inf);
-    t.area[u] = ok ? __ldg(area + a) : 1.0f;
+    const int i = tile * kSsdxTile + u * 32 + lane;
+    t.box[u] = __ldg(m_box + i);
+    t.area[u] = __ldg(m_area + i);
+    t.idx[u] = __ldg(m_idx + i);
     t.best_v[u] = 0.0f;  // np.argmax over an all-zero row -> index 0
     t.best_g[u] = 0;
-    bb.x = fminf(bb.x, t.box[u].x);
-    bb.y = fminf(bb.y, t.box[u].y);
-    bb.z = fmaxf(bb.z, t.box[u].z);
-    bb.w = fmaxf(bb.w, t.box[u].w);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    bb.x = fminf(bb.x, __shfl_xor_sync(0xFFFFFFFFu, bb.x, o));
-    bb.y = fminf(bb.y, __shfl_xor_sync(0xFFFFFFFFu, bb.y, o));
-    bb.z = fmaxf(bb.z, __shfl_xor_sync(0xFFFFFFFFu, bb.z, o));
-    bb.w = fmaxf(bb.w, __shfl_xor_sync(0xFFFFFFFFu, bb.w, o));
-  }
-  t.bbox = bb;
 }
 
-// All pairs (anchors of the tile) x (gn GT boxes in shared memory).  wrow[g] is this warp's running packed best.
+// One anchor tile against gn GT boxes in shared memory (s_best: CTA-shared packed running best per GT).
 // (shared-memory pointers: no __restrict__, see nms.cu)
-__device__ __forceinline__ void match_tile(AnchorTile& t, const float4* s_box, const float* s_area, const int gn,
-                                           const int g0, u64* wrow, const int lane) {
-  for (int g = 0; g < gn; ++g) {
-    const float4 gb = s_box[g];
-    // warp-uniform cull: the same expression as the pair intersection, evaluated on the tile's bounding box
-    const float tw = __fadd_rn(__fsub_rn(fminf(t.bbox.z, gb.z), fmaxf(t.bbox.x, gb.x)), 1.0f);
-    const float th = __fadd_rn(__fsub_rn(fminf(t.bbox.w, gb.w), fmaxf(t.bbox.y, gb.y)), 1.0f);
-    if (!(tw > 0.0f) || !(th > 0.0f)) continue;
-    const float ga = s_area[g];
-    float mv = 0.0f;
-    int ma = 0x7FFFFFFF;
+__device__ __forceinline__ void match_tile(AnchorTile& t, const float4 tb, const float2 ta, const float4* s_box,
+                                           const float* s_area, u64* s_best, const int gn, const int g0,
+                                           const float thr_eff, const int lane) {
+  for (int c0 = 0; c0 < gn; c0 += 32) {
+    // ---- tests (i) and (ii): lane l decides for GT box c0 + l ----
+    const int gl = c0 + lane;
+    bool keep = false;
+    float tgp_lane = 0.0f;
+    if (gl < gn) {
+      const float4 gb = s_box[gl];
+      const float ga = s_area[gl];
+      const float tw = __fadd_rn(__fsub_rn(fminf(tb.z, gb.z), fmaxf(tb.x, gb.x)), 1.0f);
+      const float th = __fadd_rn(__fsub_rn(fminf(tb.w, gb.w), fmaxf(tb.y, gb.y)), 1.0f);
+      const float tg = fminf(thr_eff, __uint_as_float(best_bits(s_best + gl)));  // >= 0
+      bool area_ok = true;  // min(area)/max(area) * (1+slack) >= t, written without a division
+      if (ga < ta.x) area_ok = __fmul_rn(ga, kSlackUp) >= __fmul_rn(tg, ta.x);
+      else if (ga > ta.y) area_ok = __fmul_rn(ta.y, kSlackUp) >= __fmul_rn(tg, ga);
+      keep = (tw > 0.0f) && (th > 0.0f) && area_ok;
+      tgp_lane = __fmul_rn(__fmul_rn(tg, fmaxf(ga, ta.x)), kSlackDown);
+    }
+    unsigned mask = __ballot_sync(kFull, keep);
+    while (mask != 0u) {  // ascending GT index: the anchor-side arg-max keeps the lower GT on ties
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1u;
+      const int g = c0 + src;
+      const float4 gb = s_box[g];
+      const float tgp = __shfl_sync(kFull, tgp_lane, src);
+      float inter[kApt];
+      bool cand[kApt];
+      bool any = false;
 #pragma unroll
-    for (int u = 0; u < kApt; ++u) {
-      // datacoder.py:210-216
-      const float iw = __fadd_rn(__fsub_rn(fminf(t.box[u].z, gb.z), fmaxf(t.box[u].x, gb.x)), 1.0f);
-      const float ih = __fadd_rn(__fsub_rn(fminf(t.box[u].w, gb.w), fmaxf(t.box[u].y, gb.y)), 1.0f);
-      const float inter = __fmul_rn(fmaxf(0.0f, iw), fmaxf(0.0f, ih));
-      if (inter > 0.0f) {
-        // datacoder.py:220  inter / ((area_a + area_g) - inter), IEEE division
-        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(t.area[u], ga), inter));
-        if (iou > t.best_v[u]) {  // strict: ties keep the lower GT index
-          t.best_v[u] = iou;
-          t.best_g[u] = g0 + g;
-        }
-        if (iou > mv) {  // strict: ties keep the lower anchor index (u ascending)
-          mv = iou;
-          ma = t.idx[u];
+      for (int u = 0; u < kApt; ++u) {
+        // datacoder.py:210-216 without the max(0, .): a pair with iw <= 0 or ih <= 0 is never a candidate
+        const float iw = __fadd_rn(__fsub_rn(fminf(t.box[u].z, gb.z), fmaxf(t.box[u].x, gb.x)), 1.0f);
+        const float ih = __fadd_rn(__fsub_rn(fminf(t.box[u].w, gb.w), fmaxf(t.box[u].y, gb.y)), 1.0f);
+        inter[u] = __fmul_rn(iw, ih);
+        cand[u] = (iw > 0.0f) && (inter[u] > tgp);  // tgp >= 0: implies ih > 0.  Test (iii).
+        any = any || cand[u];
+      }
+      if (!__any_sync(kFull, any)) continue;
+      const float ga = s_area[g];
+      float mv = 0.0f;
+      int ma = 0x7FFFFFFF;
+#pragma unroll
+      for (int u = 0; u < kApt; ++u) {
+        if (cand[u]) {
+          // datacoder.py:220  inter / ((area_a + area_g) - inter), IEEE division
+          const float iou = __fdiv_rn(inter[u], __fsub_rn(__fadd_rn(t.area[u], ga), inter[u]));
+          if (iou > t.best_v[u]) {  // strict: ties keep the lower GT index
+            t.best_v[u] = iou;
+            t.best_g[u] = g0 + g;
+          }
+          if (iou > mv || (iou == mv && t.idx[u] < ma)) {  // ties -> lower original anchor index
+            mv = iou;
+            ma = t.idx[u];
+          }
         }
       }
-    }
-    // warp arg-max for this GT: IoU >= 0 so the bit pattern is monotone
-    const unsigned mbits = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(mv));
-    if (mbits != 0u) {  // warp-uniform
-      // lowest anchor index among the lanes that tie on the maximum (every lane takes part in the REDUX)
-      const int amin = __reduce_min_sync(0xFFFFFFFFu, (__float_as_uint(mv) == mbits) ? ma : 0x7FFFFFFF);
-      if (lane == 0) {
-        const u64 wb = pack_best(mbits, amin);
-        if (wb > wrow[g]) wrow[g] = wb;
+      // warp arg-max for this GT: IoU >= 0 so the bit pattern is monotone
+      const unsigned mbits = __reduce_max_sync(kFull, __float_as_uint(mv));
+      if (mbits != 0u && mbits >= best_bits(s_best + g)) {  // warp-uniform (one shared word, broadcast)
+        const int amin = __reduce_min_sync(kFull, (__float_as_uint(mv) == mbits) ? ma : 0x7FFFFFFF);
+        if (lane == 0) atomicMax(s_best + g, pack_best(mbits, amin));
       }
     }
   }
-}
-
-// closed form of concat -> unique -> sequential scatter for one anchor
-__device__ __forceinline__ int resolve_match(int a, int g2, int s1max, const u64* gbest) {
-  if (g2 >= 0) {
-    const u64 p = gbest[g2];
-    const bool in_s1 = ((p >> 32) != 0ull) && (best_anchor(p) == a);
-    return in_s1 ? s1max : g2;
-  }
-  return s1max;
 }
 
 // datacoder.py:251-269 for one matched pair
@@ -155,139 +168,236 @@ __device__ __forceinline__ float4 pair_offsets(const float4 gb, const float4 d, 
   return off;
 }
 
-// ------------------------------------------------------------------------------------------ fused driver
-struct FusedSmem {
-  float4* box;    // [G]
-  u64* wbest;     // [warps][G]
-  u64* gbest;     // [G]
-  float* area;    // [G]
-  int* lab;       // [G]
-  short* g2;      // [A]  per-anchor arg-max GT (or -1); later: matched label
-  short* s1;      // [A]  max GT index whose best anchor is this anchor (or -1)
-};
+// ---- TMA bulk store (shared -> global), one bulk group per issuing thread ----
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__host__ __device__ inline size_t fused_smem_bytes(int A, int G) {
+// ------------------------------------------------------------------------------------------ fused driver
+__host__ __device__ inline int fused_label_rows(int C) {  // rows per constant label block (multiple of 4)
+  int r = (8192 / (4 * C)) & ~3;
+  return r < 4 ? 4 : r;
+}
+__host__ __device__ inline bool fused_bulk_labels(int A, int C) { return ((A * (long long)C) % 4) == 0 && C <= 1024; }
+
+__host__ __device__ inline size_t fused_smem_bytes(int A, int G, int C) {
   const size_t g = (size_t)(G > 0 ? G : 1);
-  return g * 16 + g * (kFusedThreads / 32) * 8 + g * 8 + g * 4 + g * 4 + (size_t)((A + 7) / 8 * 8) * 2 * 2 + 16;
+  size_t n = (size_t)kBgRows * 16;                                                   // bg_off
+  n += fused_bulk_labels(A, C) ? (size_t)fused_label_rows(C) * C * 4 : 16;           // bg_lab
+  n += g * 16 + g * 8 + g * 4 + g * 4 + g * 4;                                       // box, best, area, lab, s1a
+  n = (n + 15) / 16 * 16;
+  n += (size_t)kPosCap * 4 + 16;                                                     // pos, ctrl
+  n += (size_t)((A + 7) / 8 * 8) * 2;                                                // table
+  return n + 16;
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 2)
-    ssdx_encode_fused_kernel(const float4* __restrict__ anc_corners, const float* __restrict__ anc_area,
+    ssdx_encode_fused_kernel(const float4* __restrict__ m_box, const float* __restrict__ m_area,
+                             const int* __restrict__ m_idx, const float4* __restrict__ t_bbox,
+                             const float2* __restrict__ t_area, const int n_tiles,
                              const float4* __restrict__ anc_cent, const float4* __restrict__ gt_xyxy,
                              const int* __restrict__ gt_label, const int* __restrict__ gt_count, const int A,
                              const int Gmax, const int C, const float iou_thr, const float sx, const float sy,
                              const float sw, const float sh, float* __restrict__ out_labels,
                              float4* __restrict__ out_offsets, int* __restrict__ out_match) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kFusedThreads / 32;
   int G = gt_count[b];
   G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
   const int Gs = Gmax > 0 ? Gmax : 1;
-  FusedSmem sm;
+  const bool bulk_lab = fused_bulk_labels(A, C);
+  const int lab_rows = fused_label_rows(C);
+  const int A8 = (A + 7) / 8 * 8;
+
+  float4* bg_off;
+  float* bg_lab;
+  float4* s_box;
+  u64* s_best;
+  float* s_area;
+  int* s_lab;
+  int* s_s1a;
+  int* s_pos;
+  int* s_ctrl;
+  short* s_tab;
   {
     unsigned char* p = smem_raw;
-    sm.box = (float4*)p;  p += (size_t)Gs * 16;
-    sm.wbest = (u64*)p;   p += (size_t)Gs * kWarps * 8;
-    sm.gbest = (u64*)p;   p += (size_t)Gs * 8;
-    sm.area = (float*)p;  p += (size_t)Gs * 4;
-    sm.lab = (int*)p;     p += (size_t)Gs * 4;
-    sm.g2 = (short*)p;    p += (size_t)((A + 7) / 8 * 8) * 2;
-    sm.s1 = (short*)p;
+    bg_off = (float4*)p;  p += (size_t)kBgRows * 16;
+    bg_lab = (float*)p;   p += bulk_lab ? (size_t)lab_rows * C * 4 : 16;
+    s_box = (float4*)p;   p += (size_t)Gs * 16;
+    s_best = (u64*)p;     p += (size_t)Gs * 8;
+    s_area = (float*)p;   p += (size_t)Gs * 4;
+    s_lab = (int*)p;      p += (size_t)Gs * 4;
+    s_s1a = (int*)p;      p += (size_t)Gs * 4;
+    p = smem_raw + ((size_t)(p - smem_raw) + 15) / 16 * 16;
+    s_pos = (int*)p;      p += (size_t)kPosCap * 4;
+    s_ctrl = (int*)p;     p += 16;
+    s_tab = (short*)p;
   }
+
+  // ---- phase 0: constant background blocks, GT staging, tables ----
+  for (int i = tid; i < kBgRows; i += kFusedThreads) bg_off[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bulk_lab)
+    for (int e = tid; e < lab_rows * C; e += kFusedThreads) bg_lab[e] = (e % C == 0) ? 1.0f : 0.0f;
   for (int g = tid; g < G; g += kFusedThreads) {
     const float4 bx = __ldg(gt_xyxy + (size_t)b * Gmax + g);
-    sm.box[g] = bx;
-    sm.area[g] = gt_area(bx);
-    sm.lab[g] = __ldg(gt_label + (size_t)b * Gmax + g);
+    s_box[g] = bx;
+    s_area[g] = gt_area(bx);
+    s_lab[g] = __ldg(gt_label + (size_t)b * Gmax + g);
+    s_best[g] = 0ull;
   }
-  for (int i = tid; i < G * kWarps; i += kFusedThreads) sm.wbest[i] = 0ull;
-  for (int i = tid; i < (A + 1) / 2; i += kFusedThreads) reinterpret_cast<int*>(sm.s1)[i] = -1;  // two int16 -1
+  for (int i = tid; i < A8 / 8; i += kFusedThreads) reinterpret_cast<int4*>(s_tab)[i] = make_int4(-1, -1, -1, -1);
+  if (tid == 0) {
+    s_ctrl[0] = kWarps;  // next tile to hand out (the first kWarps tiles are taken statically)
+    s_ctrl[1] = 0;       // number of positives
+  }
+  fence_async_smem();  // the background blocks are read by the async proxy
   __syncthreads();
 
-  // ---- phase 1: all pairs ----
+  float4* offs = out_offsets + (size_t)b * A;
+  float* labs = out_labels + (size_t)b * A * C;
+  if (lane == 0) {  // background for the whole image, drained by the TMA unit while the warps match
+    const int n_off = (A + kBgRows - 1) / kBgRows;
+    const int n_lab = bulk_lab ? (A + lab_rows - 1) / lab_rows : 0;
+    for (int i = warp; i < n_off + n_lab; i += kWarps) {
+      if (i < n_off) {
+        const int r0 = i * kBgRows;
+        bulk_store(offs + r0, bg_off, (unsigned)(min(kBgRows, A - r0) * 16));
+      } else {
+        const int r0 = (i - n_off) * lab_rows;
+        bulk_store(labs + (size_t)r0 * C, bg_lab, (unsigned)(min(lab_rows, A - r0) * C * 4));
+      }
+    }
+    bulk_commit();
+  }
+  __syncwarp();
+
+  // ---- phase 1: match (dynamic tile hand-out; tile 0 holds the largest anchors) ----
   if (G > 0) {
-    u64* wrow = sm.wbest + (size_t)warp * G;
-    for (int base = warp * (32 * kApt); base < A; base += kWarps * 32 * kApt) {
+    const float thr_eff = fmaxf(iou_thr, 0.0f);
+    int tile = warp;
+    while (tile < n_tiles) {
       AnchorTile t;
-      load_tile(t, anc_corners, anc_area, base, lane, A);
-      match_tile(t, sm.box, sm.area, G, 0, wrow, lane);
+      load_tile(t, m_box, m_area, m_idx, tile, lane);
+      match_tile(t, __ldg(t_bbox + tile), __ldg(t_area + tile), s_box, s_area, s_best, G, 0, thr_eff, lane);
 #pragma unroll
       for (int u = 0; u < kApt; ++u)
-        if (t.idx[u] < A) sm.g2[t.idx[u]] = (short)((t.best_v[u] > iou_thr) ? t.best_g[u] : -1);
+        if (t.idx[u] >= 0 && t.best_v[u] > iou_thr) s_tab[t.idx[u]] = (short)t.best_g[u];
+      int nxt = 0;
+      if (lane == 0) nxt = atomicAdd(&s_ctrl[0], 1);
+      tile = __shfl_sync(kFull, nxt, 0);
     }
-  } else {
-    for (int i = tid; i < (A + 1) / 2; i += kFusedThreads) reinterpret_cast<int*>(sm.g2)[i] = -1;
+  }
+  if (lane == 0) bulk_wait_all();  // background rows are in place before anything is patched
+  __syncthreads();
+
+  // ---- closed form: only the <= G anchors that are some GT's best anchor need more than g2 ----
+  for (int g = tid; g < G; g += kFusedThreads) {
+    const u64 p = s_best[g];
+    s_s1a[g] = ((p >> 32) != 0ull) ? best_anchor(p) : -1;
   }
   __syncthreads();
   for (int g = tid; g < G; g += kFusedThreads) {
-    u64 m = 0ull;
-    for (int w = 0; w < kWarps; ++w) {
-      const u64 v = sm.wbest[(size_t)w * G + g];
-      m = v > m ? v : m;
+    const int a = s_s1a[g];
+    if (a < 0) continue;
+    bool is_max = true;  // g == max(S1(a)) ?
+    for (int h = g + 1; h < G; ++h) is_max = is_max && (s_s1a[h] != a);
+    if (is_max) {
+      const int g2 = s_tab[a];
+      s_tab[a] = (short)((g2 >= 0 && s_s1a[g2] != a) ? g2 : g);
     }
-    sm.gbest[g] = m;
   }
-  __syncthreads();
-  if (tid == 0)  // ascending g: the last writer is max(S1(a)); G is small on this path
-    for (int g = 0; g < G; ++g) {
-      const u64 p = sm.gbest[g];
-      if ((p >> 32) != 0ull) sm.s1[best_anchor(p)] = (short)g;
-    }
   __syncthreads();
 
-  // ---- phase 2: resolve + emit (coalesced 128-bit streaming stores) ----
-  float4* offs = out_offsets + (size_t)b * A;
-  for (int a = tid; a < A; a += kFusedThreads) {
-    const int match = resolve_match(a, sm.g2[a], sm.s1[a], sm.gbest);
-    float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
-    int lab = 0;  // background row = one_hot(0)
-    if (match >= 0) {
-      lab = sm.lab[match];
-      off = pair_offsets(sm.box[match], __ldg(anc_cent + a), sx, sy, sw, sh);
+  // ---- compact the positives, encode them densely, patch them over the background ----
+  auto emit_positive = [&](const int a, const int g) {
+    st_stream_f4(offs + a, pair_offsets(s_box[g], __ldg(anc_cent + a), sx, sy, sw, sh));
+    if (bulk_lab) {
+      const int lab = s_lab[g];
+      if (C == 4) {
+        const float4 oh = make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f,
+                                      lab == 3 ? 1.f : 0.f);
+        st_stream_f4(reinterpret_cast<float4*>(labs) + a, oh);
+      } else {  // the background row is [1,0,...]; a label outside [0,C) gives an all-zero row (tf.one_hot)
+        labs[(size_t)a * C] = (lab == 0) ? 1.0f : 0.0f;
+        if (lab > 0 && lab < C) labs[(size_t)a * C + lab] = 1.0f;
+      }
     }
-    st_stream_f4(offs + a, off);
-    if (out_match) out_match[(size_t)b * A + a] = match;
-    if (C == 4) {
-      const float4 oh = make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f,
-                                    lab == 3 ? 1.f : 0.f);
-      st_stream_f4(reinterpret_cast<float4*>(out_labels) + (size_t)b * A + a, oh);
-    } else {
-      // own slot only; a label outside [0, C) can never equal a class index, so clamping to int16 is safe
-      sm.g2[a] = (short)((lab >= 0 && lab < 32767) ? lab : 32767);
+  };
+  for (int i = tid; i < A8 / 8; i += kFusedThreads) {
+    const int4 v = reinterpret_cast<const int4*>(s_tab)[i];
+    if (((unsigned)(v.x & v.y & v.z & v.w) & 0x80008000u) == 0x80008000u) continue;  // 8 background rows
+    const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int m = (int)(short)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xFFFF));
+      if (m >= 0) {
+        const int a = i * 8 + k;
+        const int slot = atomicAdd(&s_ctrl[1], 1);
+        if (slot < kPosCap) s_pos[slot] = (a << 8) | m;
+        else emit_positive(a, m);
+      }
     }
   }
-  if (C != 4) {
-    __syncthreads();
-    float* dst = out_labels + (size_t)b * A * C;
-    const int total = A * C;  // flat coalesced walk
+  __syncthreads();
+  const int npos = min(s_ctrl[1], kPosCap);
+  for (int s = tid; s < npos; s += kFusedThreads) emit_positive(s_pos[s] >> 8, s_pos[s] & 255);
+
+  if (!bulk_lab) {  // label rows that cannot be bulk-stored (unaligned image stride): flat coalesced walk
+    const int total = A * C;
     for (int e = tid; e < total; e += kFusedThreads) {
       const int a = e / C;
       const int c = e - a * C;
-      dst[e] = ((int)sm.g2[a] == c) ? 1.0f : 0.0f;
+      const int m = s_tab[a];
+      labs[e] = ((m >= 0 ? s_lab[m] : 0) == c) ? 1.0f : 0.0f;
     }
   }
+  if (out_match)
+    for (int a = tid; a < A; a += kFusedThreads) out_match[(size_t)b * A + a] = s_tab[a];
 }
 
 // ------------------------------------------------------------------------------------------ tiled driver
+// closed form of concat -> unique -> sequential scatter for one anchor
+__device__ __forceinline__ int resolve_match(int a, int g2, int s1max, const u64* gbest) {
+  if (g2 >= 0) {
+    const u64 p = gbest[g2];
+    const bool in_s1 = ((p >> 32) != 0ull) && (best_anchor(p) == a);
+    return in_s1 ? s1max : g2;
+  }
+  return s1max;
+}
+
+// grid (ceil(n_tiles / kTiledTilesPerCta), B).  anchor_g2 is pre-set to -1; only anchors above the threshold write.
 __global__ void __launch_bounds__(kTiledThreads)
-    ssdx_encode_match_kernel(const float4* __restrict__ anc_corners, const float* __restrict__ anc_area,
+    ssdx_encode_match_kernel(const float4* __restrict__ m_box, const float* __restrict__ m_area,
+                             const int* __restrict__ m_idx, const float4* __restrict__ t_bbox,
+                             const float2* __restrict__ t_area, const int n_tiles,
                              const float4* __restrict__ gt_xyxy, const int* __restrict__ gt_count, const int A,
                              const int Gmax, const float iou_thr, u64* __restrict__ gt_best,
                              int* __restrict__ anchor_g2) {
   __shared__ float4 s_box[kGtTile];
   __shared__ float s_area[kGtTile];
-  __shared__ u64 s_wbest[(kTiledThreads / 32)][kGtTile];  // warp-private running best per GT
+  __shared__ u64 s_best[kGtTile];
+  __shared__ u64 s_seen[kGtTile];
+  __shared__ float s_bv[kTiledTilesPerCta * kSsdxTile];  // per-anchor running best across GT tiles
+  __shared__ int s_bg[kTiledTilesPerCta * kSsdxTile];
 
+  constexpr int kWarps = kTiledThreads / 32;
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int G = gt_count[b];
   G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
-  const int base = blockIdx.x * (kTiledThreads * kApt) + warp * (32 * kApt);
-
-  AnchorTile t;
-  load_tile(t, anc_corners, anc_area, base, lane, A);
+  if (G == 0) return;
+  const int tile0 = blockIdx.x * kTiledTilesPerCta;
+  const int tiles_here = min(kTiledTilesPerCta, n_tiles - tile0);
+  const float thr_eff = fmaxf(iou_thr, 0.0f);
+  const bool multi = G > kGtTile;
 
   for (int g0 = 0; g0 < G; g0 += kGtTile) {
     const int gn = min(kGtTile, G - g0);
@@ -296,26 +406,41 @@ __global__ void __launch_bounds__(kTiledThreads)
       const float4 bx = __ldg(gt_xyxy + (size_t)b * Gmax + g0 + g);
       s_box[g] = bx;
       s_area[g] = gt_area(bx);
+      // whatever other CTAs have published so far is a true IoU of this GT box: a valid lower bound
+      const u64 seen = *((volatile u64*)(gt_best + (size_t)b * Gmax + g0 + g));
+      s_best[g] = seen;
+      s_seen[g] = seen;
     }
-    for (int i = tid; i < kGtTile * (kTiledThreads / 32); i += kTiledThreads) (&s_wbest[0][0])[i] = 0ull;
     __syncthreads();
-    match_tile(t, s_box, s_area, gn, g0, s_wbest[warp], lane);
-    __syncthreads();
-    // one global atomic per (CTA, GT) that saw a positive IoU
-    for (int g = tid; g < gn; g += kTiledThreads) {
-      u64 m = 0ull;
+    for (int k = warp; k < tiles_here; k += kWarps) {
+      AnchorTile t;
+      load_tile(t, m_box, m_area, m_idx, tile0 + k, lane);
+      if (multi && g0 > 0) {
 #pragma unroll
-      for (int w = 0; w < kTiledThreads / 32; ++w) {
-        const u64 v = s_wbest[w][g];
-        m = v > m ? v : m;
+        for (int u = 0; u < kApt; ++u) {
+          t.best_v[u] = s_bv[k * kSsdxTile + u * 32 + lane];
+          t.best_g[u] = s_bg[k * kSsdxTile + u * 32 + lane];
+        }
       }
-      if (m != 0ull) atomicMax(gt_best + (size_t)b * Gmax + g0 + g, m);
-    }
-  }
+      match_tile(t, __ldg(t_bbox + tile0 + k), __ldg(t_area + tile0 + k), s_box, s_area, s_best, gn, g0, thr_eff,
+                 lane);
+      if (g0 + kGtTile >= G) {  // last GT tile: publish the anchors above the threshold
 #pragma unroll
-  for (int u = 0; u < kApt; ++u)
-    if (t.idx[u] < A)
-      anchor_g2[(size_t)b * A + t.idx[u]] = (G > 0 && t.best_v[u] > iou_thr) ? t.best_g[u] : -1;
+        for (int u = 0; u < kApt; ++u)
+          if (t.idx[u] >= 0 && t.best_v[u] > iou_thr) anchor_g2[(size_t)b * A + t.idx[u]] = t.best_g[u];
+      } else {
+#pragma unroll
+        for (int u = 0; u < kApt; ++u) {
+          s_bv[k * kSsdxTile + u * 32 + lane] = t.best_v[u];
+          s_bg[k * kSsdxTile + u * 32 + lane] = t.best_g[u];
+        }
+      }
+    }
+    __syncthreads();
+    // one global atomic per (CTA, GT) that improved on what it saw
+    for (int g = tid; g < gn; g += kTiledThreads)
+      if (s_best[g] > s_seen[g]) atomicMax(gt_best + (size_t)b * Gmax + g0 + g, s_best[g]);
+  }
 }
 
 __global__ void __launch_bounds__(kEmitThreads)
@@ -380,9 +505,9 @@ __global__ void __launch_bounds__(kEmitThreads)
   }
 }
 
-inline bool use_fused(int A, int gmax, int batch, int sms) {
+inline bool use_fused(int A, int gmax, int C, int batch, int sms) {
   // one CTA per image needs enough images to fill the GPU, and A/G small enough for shared memory
-  const bool fits = gmax <= kFusedMaxG && A <= 32768 && fused_smem_bytes(A, gmax) <= 100 * 1024;
+  const bool fits = gmax <= kFusedMaxG && A <= 32768 && fused_smem_bytes(A, gmax, C) <= 100 * 1024;
   const char* force = getenv("SSDX_ENCODE_PATH");  // "fused" | "tiled": test hook, both paths are bit-identical
   if (force != nullptr && force[0] == 't') return false;
   if (force != nullptr && force[0] == 'f') return fits;
@@ -425,11 +550,12 @@ extern "C" int ssdx_encode(const ssdx_anchors* anchors, const float* gt_xyxy, co
   cudaStream_t s = (cudaStream_t)stream;
   const int gm = gmax > 0 ? gmax : 1;
 
-  if (use_fused(A, gmax, batch, ssdx_sm_count(anchors->device))) {
-    const size_t smem = fused_smem_bytes(A, gmax);
+  if (use_fused(A, gmax, num_classes, batch, ssdx_sm_count(anchors->device))) {
+    const size_t smem = fused_smem_bytes(A, gmax, num_classes);
     SSDX_CUDA(cudaFuncSetAttribute(ssdx_encode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ssdx_encode_fused_kernel<<<batch, kFusedThreads, smem, s>>>(
-        anchors->corners, anchors->area, anchors->enc_cent, (const float4*)gt_xyxy, gt_label, gt_count, A, gmax,
+        anchors->m_box, anchors->m_area, anchors->m_idx, anchors->t_bbox, anchors->t_area, anchors->n_tiles,
+        anchors->enc_cent, (const float4*)gt_xyxy, gt_label, gt_count, A, gmax,
         num_classes, iou_threshold, std_host[0], std_host[1], std_host[2], std_host[3], out_labels,
         (float4*)out_offsets, out_match);
     SSDX_LAUNCH_CHECK("ssdx_encode_fused_kernel");
@@ -440,9 +566,12 @@ extern "C" int ssdx_encode(const ssdx_anchors* anchors, const float* gt_xyxy, co
   u64* gt_best = (u64*)workspace;
   int* anchor_g2 = (int*)((char*)workspace + best_bytes);
   SSDX_CUDA(cudaMemsetAsync(gt_best, 0, (size_t)batch * gm * sizeof(u64), s));
-  dim3 g1((A + kTiledThreads * kApt - 1) / (kTiledThreads * kApt), batch);
-  ssdx_encode_match_kernel<<<g1, kTiledThreads, 0, s>>>(anchors->corners, anchors->area, (const float4*)gt_xyxy,
-                                                        gt_count, A, gm, iou_threshold, gt_best, anchor_g2);
+  SSDX_CUDA(cudaMemsetAsync(anchor_g2, 0xFF, (size_t)batch * A * sizeof(int), s));  // -1: below the threshold
+  dim3 g1((anchors->n_tiles + kTiledTilesPerCta - 1) / kTiledTilesPerCta, batch);
+  ssdx_encode_match_kernel<<<g1, kTiledThreads, 0, s>>>(anchors->m_box, anchors->m_area, anchors->m_idx,
+                                                        anchors->t_bbox, anchors->t_area, anchors->n_tiles,
+                                                        (const float4*)gt_xyxy, gt_count, A, gm, iou_threshold,
+                                                        gt_best, anchor_g2);
   SSDX_LAUNCH_CHECK("ssdx_encode_match_kernel");
   dim3 g2((A + kEmitThreads - 1) / kEmitThreads, batch);
   ssdx_encode_emit_kernel<<<g2, kEmitThreads, 0, s>>>(anchors->enc_cent, (const float4*)gt_xyxy, gt_label, gt_count,
