@@ -43,25 +43,39 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug_timers: bool = False, variant=None) -> str:
+    """debug_timers: also build lib/libssdx_dbg.so with -DSSDX_PHASE_TIMERS (tools/phase_timers.py).
+    variant: (name, [-D flags]) builds lib/libssdx_<name>.so for tuning sweeps (tools/time_stage.py)."""
+    if variant is not None:
+        return _compile(os.path.join(LIBDIR, f"libssdx_{variant[0]}.so"), verbose, list(variant[1]))
+    if debug_timers:
+        return _compile(os.path.join(LIBDIR, "libssdx_dbg.so"), verbose, ["-DSSDX_PHASE_TIMERS"])
     if not force and not needs_build():
         return LIB
+    return _compile(LIB, verbose, [])
+
+
+def _compile(out: str, verbose: bool, extra) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC]
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + ["-I", INCLUDE, "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libssdx.so")
-    return LIB
+        raise RuntimeError("nvcc failed building " + os.path.basename(out))
+    return out
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--debug-timers", action="store_true")
+    ap.add_argument("--variant", help="NAME: build lib/libssdx_NAME.so with the --define values (tuning sweeps)")
+    ap.add_argument("--define", action="append", default=[], help="KEY=VALUE passed to nvcc as -DKEY=VALUE")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    var = (a.variant, ["-D" + d for d in a.define]) if a.variant else None
+    print(build(force=a.force, verbose=a.verbose, debug_timers=a.debug_timers, variant=var))

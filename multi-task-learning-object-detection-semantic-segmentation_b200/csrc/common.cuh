@@ -26,7 +26,10 @@ struct ssdx_anchors {
   float2* t_area;  // (n_tiles) (min, max) anchor area in the tile
 };
 
-constexpr int kSsdxApt = 2;               // anchors per lane in one match tile
+#ifndef SSDX_APT
+#define SSDX_APT 2
+#endif
+constexpr int kSsdxApt = SSDX_APT;        // anchors per lane in one match tile
 constexpr int kSsdxTile = 32 * kSsdxApt;  // anchors per match tile
 
 void ssdx_set_error(const char* fmt, ...);
@@ -78,3 +81,19 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+
+// Optional per-phase cycle counters (debug builds only: -DSSDX_PHASE_TIMERS).  Each translation unit that uses
+// them defines its own `static __device__ unsigned long long g_phase_cycles[32]` and a reader
+// (ssdx_debug_phase_cycles for nms.cu, ssdx_debug_phase_cycles_encode for encode.cu).
+#ifdef SSDX_PHASE_TIMERS
+#define PHASE_T0() long long pt__ = clock64()
+#define PHASE_ADD(slot)                                                        \
+  do {                                                                         \
+    const long long now__ = clock64();                                         \
+    if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(now__ - pt__)); \
+    pt__ = now__;                                                              \
+  } while (0)
+#else
+#define PHASE_T0() do {} while (0)
+#define PHASE_ADD(slot) do {} while (0)
+#endif

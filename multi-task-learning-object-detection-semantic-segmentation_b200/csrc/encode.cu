@@ -32,17 +32,33 @@
 
 #include "common.cuh"
 
+#ifdef SSDX_PHASE_TIMERS
+static __device__ unsigned long long g_phase_cycles[32];
+extern "C" __attribute__((visibility("default"))) int ssdx_debug_phase_cycles_encode(unsigned long long* out32) {
+  unsigned long long zero[32] = {0};
+  if (cudaMemcpyFromSymbol(out32, g_phase_cycles, sizeof(zero)) != cudaSuccess) return -2;
+  if (cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return -2;
+  return 0;
+}
+#endif
+
 namespace {
 
 constexpr int kApt = kSsdxApt;      // anchors per lane per tile
-constexpr int kFusedThreads = 512;  // one CTA per image
+#ifndef SSDX_ENC_THREADS
+#define SSDX_ENC_THREADS 256
+#endif
+#ifndef SSDX_ENC_BGROWS
+#define SSDX_ENC_BGROWS 512
+#endif
+constexpr int kFusedThreads = SSDX_ENC_THREADS;  // one CTA per image
 constexpr int kTiledThreads = 256;  // grid (tile groups, images)
 constexpr int kTiledTilesPerCta = 16;
 constexpr int kGtTile = 256;        // GT boxes staged per shared-memory tile (tiled driver)
 constexpr int kEmitThreads = 256;
 constexpr int kFusedMaxG = 256;
 constexpr int kPosCap = 1024;   // compacted positives per image (more are encoded in place)
-constexpr int kBgRows = 512;    // background rows per bulk store (offsets: 8 KB per store)
+constexpr int kBgRows = SSDX_ENC_BGROWS;  // background rows per bulk store (offsets: 16 B per row)
 constexpr float kSlackUp = 1.0001f, kSlackDown = 0.9999f;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -99,13 +115,16 @@ __device__ __forceinline__ void match_tile(AnchorTile& t, const float4 tb, const
       const float tw = __fadd_rn(__fsub_rn(fminf(tb.z, gb.z), fmaxf(tb.x, gb.x)), 1.0f);
       const float th = __fadd_rn(__fsub_rn(fminf(tb.w, gb.w), fmaxf(tb.y, gb.y)), 1.0f);
       const float tg = fminf(thr_eff, __uint_as_float(best_bits(s_best + gl)));  // >= 0
-      bool area_ok = true;  // min(area)/max(area) * (1+slack) >= t, written without a division
-      if (ga < ta.x) area_ok = __fmul_rn(ga, kSlackUp) >= __fmul_rn(tg, ta.x);
-      else if (ga > ta.y) area_ok = __fmul_rn(ta.y, kSlackUp) >= __fmul_rn(tg, ga);
-      keep = (tw > 0.0f) && (th > 0.0f) && area_ok;
-      tgp_lane = __fmul_rn(__fmul_rn(tg, fmaxf(ga, ta.x)), kSlackDown);
+      // test (ii): iou <= min(amax, ga, inter(tile box, gt)) / max(amin, ga), written without a division
+      const float gm = fmaxf(ga, ta.x);
+      const float num = fminf(fminf(ta.y, ga), __fmul_rn(tw, th));
+      keep = (tw > 0.0f) && (th > 0.0f) && (__fmul_rn(num, kSlackUp) >= __fmul_rn(tg, gm));
+      tgp_lane = __fmul_rn(__fmul_rn(tg, gm), kSlackDown);
     }
     unsigned mask = __ballot_sync(kFull, keep);
+#ifdef SSDX_PHASE_TIMERS
+    if (lane == 0) atomicAdd(&g_phase_cycles[25], (unsigned long long)__popc(mask));  // surviving (tile, GT)
+#endif
     while (mask != 0u) {  // ascending GT index: the anchor-side arg-max keeps the lower GT on ties
       const int src = __ffs(mask) - 1;
       mask &= mask - 1u;
@@ -125,14 +144,26 @@ __device__ __forceinline__ void match_tile(AnchorTile& t, const float4 tb, const
         any = any || cand[u];
       }
       if (!__any_sync(kFull, any)) continue;
+#ifdef SSDX_PHASE_TIMERS
+      if (lane == 0) atomicAdd(&g_phase_cycles[26], 1ull);  // slow-path entries
+#endif
       const float ga = s_area[g];
+      const unsigned cur = best_bits(s_best + g);
+      const float tg = fminf(thr_eff, __uint_as_float(cur));
+      const float tg1 = __fadd_rn(1.0f, tg), tgs = __fmul_rn(tg, kSlackDown);
       float mv = 0.0f;
       int ma = 0x7FFFFFFF;
 #pragma unroll
       for (int u = 0; u < kApt; ++u) {
-        if (cand[u]) {
+        // iou >= tg  <=>  inter * (1 + tg) >= tg * (area_a + area_g): the same decision without the division,
+        // up to rounding (slack on the right-hand side), taken with the current bound
+        const float asum = __fadd_rn(t.area[u], ga);
+        if (cand[u] && __fmul_rn(inter[u], tg1) >= __fmul_rn(asum, tgs)) {
           // datacoder.py:220  inter / ((area_a + area_g) - inter), IEEE division
-          const float iou = __fdiv_rn(inter[u], __fsub_rn(__fadd_rn(t.area[u], ga), inter[u]));
+          const float iou = __fdiv_rn(inter[u], __fsub_rn(asum, inter[u]));
+#ifdef SSDX_PHASE_TIMERS
+          atomicAdd(&g_phase_cycles[27], 1ull);  // divisions
+#endif
           if (iou > t.best_v[u]) {  // strict: ties keep the lower GT index
             t.best_v[u] = iou;
             t.best_g[u] = g0 + g;
@@ -143,14 +174,70 @@ __device__ __forceinline__ void match_tile(AnchorTile& t, const float4 tb, const
           }
         }
       }
-      // warp arg-max for this GT: IoU >= 0 so the bit pattern is monotone
-      const unsigned mbits = __reduce_max_sync(kFull, __float_as_uint(mv));
-      if (mbits != 0u && mbits >= best_bits(s_best + g)) {  // warp-uniform (one shared word, broadcast)
-        const int amin = __reduce_min_sync(kFull, (__float_as_uint(mv) == mbits) ? ma : 0x7FFFFFFF);
-        if (lane == 0) atomicMax(s_best + g, pack_best(mbits, amin));
+      // GT side: only when some lane reaches the running best (IoU >= 0, so the bit pattern is monotone)
+      const unsigned mvb = __float_as_uint(mv);
+      if (!__any_sync(kFull, mvb != 0u && mvb >= cur)) continue;
+#ifdef SSDX_PHASE_TIMERS
+      if (lane == 0) atomicAdd(&g_phase_cycles[28], 1ull);  // GT-side updates
+#endif
+      const unsigned mbits = __reduce_max_sync(kFull, mvb);
+      const int amin = __reduce_min_sync(kFull, (mvb == mbits) ? ma : 0x7FFFFFFF);
+      if (lane == 0) atomicMax(s_best + g, pack_best(mbits, amin));
+    }
+  }
+}
+
+// Seed of the GT-side bound: one warp evaluates, for GT box g, the tile that looks most promising (largest
+// bound (ii), then nearest centre) and publishes the best real pair it finds.  Any real pair is a valid lower bound
+// of max_a iou[a,g]; a good one lets tests (ii) and (iii) cull from the first tile on.
+__device__ __forceinline__ void seed_gt_best(const float4* __restrict__ m_box, const float* __restrict__ m_area,
+                                             const int* __restrict__ m_idx, const float4* __restrict__ t_bbox,
+                                             const float2* __restrict__ t_area, const int n_tiles, const float4 gb,
+                                             const float ga, u64* s_best_g, const int lane) {
+  float best_score = -1.0f;
+  int best_tile = 0;
+  const float gcx = 0.5f * (gb.x + gb.z), gcy = 0.5f * (gb.y + gb.w);
+  for (int tile = lane; tile < n_tiles; tile += 32) {
+    const float4 tb = __ldg(t_bbox + tile);
+    const float2 ta = __ldg(t_area + tile);
+    const float tw = fminf(tb.z, gb.z) - fmaxf(tb.x, gb.x) + 1.0f;
+    const float th = fminf(tb.w, gb.w) - fmaxf(tb.y, gb.y) + 1.0f;
+    if (tw > 0.0f && th > 0.0f) {
+      const float ub = fminf(fminf(ta.y, ga), tw * th) / fmaxf(fmaxf(ta.x, ga), 1e-30f);
+      const float dx = 0.5f * (tb.x + tb.z) - gcx, dy = 0.5f * (tb.y + tb.w) - gcy;
+      const float score = ub / (1.0f + (dx * dx + dy * dy) / fmaxf(ga, 1e-30f));  // heuristic only
+      if (score > best_score) {
+        best_score = score;
+        best_tile = tile;
       }
     }
   }
+  const unsigned sb = __reduce_max_sync(kFull, __float_as_uint(fmaxf(best_score, 0.0f)));
+  if (sb == 0u) return;  // no tile touches this GT box
+  const int tile = __reduce_min_sync(kFull, (__float_as_uint(fmaxf(best_score, 0.0f)) == sb) ? best_tile : 0x7FFFFFFF);
+  float mv = 0.0f;
+  int ma = 0x7FFFFFFF;
+#pragma unroll
+  for (int u = 0; u < kApt; ++u) {
+    const int i = tile * kSsdxTile + u * 32 + lane;
+    const float4 ab = __ldg(m_box + i);
+    const float iw = __fadd_rn(__fsub_rn(fminf(ab.z, gb.z), fmaxf(ab.x, gb.x)), 1.0f);
+    const float ih = __fadd_rn(__fsub_rn(fminf(ab.w, gb.w), fmaxf(ab.y, gb.y)), 1.0f);
+    const float inter = __fmul_rn(iw, ih);
+    if (iw > 0.0f && inter > 0.0f) {
+      const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(__ldg(m_area + i), ga), inter));
+      const int idx = __ldg(m_idx + i);
+      if (iou > mv || (iou == mv && idx < ma)) {
+        mv = iou;
+        ma = idx;
+      }
+    }
+  }
+  const unsigned mvb = __float_as_uint(mv);
+  const unsigned mbits = __reduce_max_sync(kFull, mvb);
+  if (mbits == 0u) return;
+  const int amin = __reduce_min_sync(kFull, (mvb == mbits) ? ma : 0x7FFFFFFF);
+  if (lane == 0) atomicMax(s_best_g, pack_best(mbits, amin));
 }
 
 // datacoder.py:251-269 for one matched pair
@@ -180,7 +267,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ------------------------------------------------------------------------------------------ fused driver
 __host__ __device__ inline int fused_label_rows(int C) {  // rows per constant label block (multiple of 4)
-  int r = (8192 / (4 * C)) & ~3;
+  int r = ((kBgRows * 16) / (4 * C)) & ~3;
   return r < 4 ? 4 : r;
 }
 __host__ __device__ inline bool fused_bulk_labels(int A, int C) { return ((A * (long long)C) % 4) == 0 && C <= 1024; }
@@ -196,7 +283,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int A, int G, int C) {
   return n + 16;
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 2)
+__global__ void __launch_bounds__(kFusedThreads, 1024 / kFusedThreads)
     ssdx_encode_fused_kernel(const float4* __restrict__ m_box, const float* __restrict__ m_area,
                              const int* __restrict__ m_idx, const float4* __restrict__ t_bbox,
                              const float2* __restrict__ t_area, const int n_tiles,
@@ -242,9 +329,13 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
   }
 
   // ---- phase 0: constant background blocks, GT staging, tables ----
+  PHASE_T0();
   for (int i = tid; i < kBgRows; i += kFusedThreads) bg_off[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (bulk_lab)
-    for (int e = tid; e < lab_rows * C; e += kFusedThreads) bg_lab[e] = (e % C == 0) ? 1.0f : 0.0f;
+    for (int r = tid; r < lab_rows; r += kFusedThreads) {
+      bg_lab[r * C] = 1.0f;
+      for (int c = 1; c < C; ++c) bg_lab[r * C + c] = 0.0f;
+    }
   for (int g = tid; g < G; g += kFusedThreads) {
     const float4 bx = __ldg(gt_xyxy + (size_t)b * Gmax + g);
     s_box[g] = bx;
@@ -259,13 +350,15 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
   }
   fence_async_smem();  // the background blocks are read by the async proxy
   __syncthreads();
+  PHASE_ADD(16);  // init
 
   float4* offs = out_offsets + (size_t)b * A;
   float* labs = out_labels + (size_t)b * A * C;
-  if (lane == 0) {  // background for the whole image, drained by the TMA unit while the warps match
+#ifndef SSDX_EXP_SKIP_BULK
+  if (warp == kWarps - 1 && lane == 0) {  // background for the whole image, drained by the TMA unit during the match
     const int n_off = (A + kBgRows - 1) / kBgRows;
     const int n_lab = bulk_lab ? (A + lab_rows - 1) / lab_rows : 0;
-    for (int i = warp; i < n_off + n_lab; i += kWarps) {
+    for (int i = 0; i < n_off + n_lab; ++i) {
       if (i < n_off) {
         const int r0 = i * kBgRows;
         bulk_store(offs + r0, bg_off, (unsigned)(min(kBgRows, A - r0) * 16));
@@ -276,11 +369,21 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
     }
     bulk_commit();
   }
+#endif
   __syncwarp();
 
   // ---- phase 1: match (dynamic tile hand-out; tile 0 holds the largest anchors) ----
+#ifdef SSDX_EXP_SKIP_MATCH
+  if (G > 1000000) {
+#else
   if (G > 0) {
+#endif
     const float thr_eff = fmaxf(iou_thr, 0.0f);
+#ifndef SSDX_EXP_SKIP_SEED
+    for (int g = warp; g < G; g += kWarps)
+      seed_gt_best(m_box, m_area, m_idx, t_bbox, t_area, n_tiles, s_box[g], s_area[g], s_best + g, lane);
+#endif
+    PHASE_ADD(17);  // seed (no barrier: the other warps' seeds arrive through s_best whenever they are ready)
     int tile = warp;
     while (tile < n_tiles) {
       AnchorTile t;
@@ -294,8 +397,10 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
       tile = __shfl_sync(kFull, nxt, 0);
     }
   }
-  if (lane == 0) bulk_wait_all();  // background rows are in place before anything is patched
+  PHASE_ADD(18);  // match (warp 0)
+  if (warp == kWarps - 1 && lane == 0) bulk_wait_all();  // background rows are in place before any patch
   __syncthreads();
+  PHASE_ADD(19);  // wait for the other warps and the bulk stores
 
   // ---- closed form: only the <= G anchors that are some GT's best anchor need more than g2 ----
   for (int g = tid; g < G; g += kFusedThreads) {
@@ -315,6 +420,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
   }
   __syncthreads();
 
+  PHASE_ADD(20);  // closed form
   // ---- compact the positives, encode them densely, patch them over the background ----
   auto emit_positive = [&](const int a, const int g) {
     st_stream_f4(offs + a, pair_offsets(s_box[g], __ldg(anc_cent + a), sx, sy, sw, sh));
@@ -360,6 +466,10 @@ __global__ void __launch_bounds__(kFusedThreads, 2)
   }
   if (out_match)
     for (int a = tid; a < A; a += kFusedThreads) out_match[(size_t)b * A + a] = s_tab[a];
+  PHASE_ADD(21);  // compact + patch
+#ifdef SSDX_PHASE_TIMERS
+  if (tid == 0) atomicAdd(&g_phase_cycles[24], 1ull);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ tiled driver

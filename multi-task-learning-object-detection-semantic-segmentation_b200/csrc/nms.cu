@@ -47,19 +47,8 @@ constexpr int kGenThreads = 512;
 constexpr int kChunk = 512;
 constexpr int kMergeThreads = 256;
 
-// Optional per-phase cycle counters of the fast kernel (debug builds only: -DSSDX_PHASE_TIMERS).
 #ifdef SSDX_PHASE_TIMERS
-__device__ unsigned long long g_phase_cycles[16];
-#define PHASE_T0() long long pt__ = clock64()
-#define PHASE_ADD(slot)                                                        \
-  do {                                                                         \
-    const long long now__ = clock64();                                         \
-    if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[slot], (unsigned long long)(now__ - pt__)); \
-    pt__ = now__;                                                              \
-  } while (0)
-#else
-#define PHASE_T0() do {} while (0)
-#define PHASE_ADD(slot) do {} while (0)
+static __device__ unsigned long long g_phase_cycles[32];
 #endif
 
 __device__ __forceinline__ unsigned score_to_key(float s) {
@@ -904,9 +893,9 @@ inline NmsWorkspace nms_workspace(int batch, int A, int C, int max_per_class) {
 
 #ifdef SSDX_PHASE_TIMERS
 // debug builds only: read and reset the phase counters of ssdx_nms_fast_kernel
-extern "C" __attribute__((visibility("default"))) int ssdx_debug_phase_cycles(unsigned long long* out16) {
-  unsigned long long zero[16] = {0};
-  if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(zero)) != cudaSuccess) return -2;
+extern "C" __attribute__((visibility("default"))) int ssdx_debug_phase_cycles(unsigned long long* out32) {
+  unsigned long long zero[32] = {0};
+  if (cudaMemcpyFromSymbol(out32, g_phase_cycles, sizeof(zero)) != cudaSuccess) return -2;
   if (cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return -2;
   return 0;
 }
