@@ -22,6 +22,21 @@
 //                lower anchor), keeps max_total rows and writes [label, prob, xmin, ymin, xmax, ymax]
 //                (layers.py:155-162), zero padding, valid counts and source anchor indices.
 //
+// Merged pipeline (2 launches + 2 gated fallbacks), used when max_per_class >= max_total (the per-class cap can
+// then never bind before the image has max_total rows), C <= 256 and A <= 2^24:
+//   The K = max_total output rows are the first K boxes selected when the candidates of ALL classes are visited in
+//   one descending order (score, then lower class, then lower anchor) and each one is tested only against the
+//   boxes already selected for its own class: within a class that is exactly the per-class greedy order, and the
+//   visiting order is the merge order, so everything after the K-th selection can never reach the output.  One
+//   list, one sort and one greedy pass per image instead of one per (image, class), and no merge kernel.
+//   1m. select_all : one CTA per image: threshold from a 1/16 sample of all classes (CTA-wide bisection), then one
+//                    streaming pass with a single compare per score; ~400 composites
+//                    (score key << 32 | ~class << 24 | ~anchor) per image.
+//   2m. fast_all   : one CTA per image: register bitonic sort, blocked greedy suppression with a class-equality
+//                    test on the rare overlapping pairs, adaptive refills, rows written in place.  An image whose list
+//                    overflowed or whose refills failed (massive score ties) is handed to the exact per-class
+//                    generic kernel + a merge over the handed-over images only.
+//
 // IoU follows TF's IOU(): min/max-normalised corners, area = (y1-y0)*(x1-x0), 0 if either area <= 0,
 // inter / ((area_i + area_j) - inter) with IEEE division, suppressed iff IoU > iou_thr (strict).
 #include <stdlib.h>
@@ -46,6 +61,8 @@ constexpr int kBlk = 64;
 constexpr int kGenThreads = 512;
 constexpr int kChunk = 512;
 constexpr int kMergeThreads = 256;
+constexpr int kAllRank = 26;       // merged select: threshold at the 26th largest sample => ~416 +- 80 listed
+constexpr int kAllRefillTarget = 384;
 
 #ifdef SSDX_PHASE_TIMERS
 static __device__ unsigned long long g_phase_cycles[32];
@@ -62,6 +79,12 @@ __device__ __forceinline__ u64 make_comp(unsigned key, int idx) {
   return ((u64)key << 32) | (u64)(0xFFFFFFFFu - (unsigned)idx);
 }
 __device__ __forceinline__ int comp_idx(u64 c) { return (int)(0xFFFFFFFFu - (unsigned)(c & 0xFFFFFFFFull)); }
+// merged order: score descending, then lower class, then lower anchor (class < 256, anchor < 2^24)
+__device__ __forceinline__ u64 make_comp_all(unsigned key, int cls, int idx) {
+  return ((u64)key << 32) | ((u64)(0xFFu - (unsigned)cls) << 24) | (u64)(0xFFFFFFu - (unsigned)idx);
+}
+__device__ __forceinline__ int comp_all_cls(u64 c) { return (int)(0xFFu - (unsigned)((c >> 24) & 0xFFull)); }
+__device__ __forceinline__ int comp_all_idx(u64 c) { return (int)(0xFFFFFFu - (unsigned)(c & 0xFFFFFFull)); }
 
 // box normalised as TF does: (y0, x0, y1, x1) with y0<=y1, x0<=x1
 __device__ __forceinline__ float4 normalise_box(const float4 b) {
@@ -590,6 +613,408 @@ __global__ void __launch_bounds__(kFastThreads, 6)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ 1m. merged select
+// info per image: [0] listed candidates (may exceed kCap), [1] threshold key (every candidate with key >= it is listed)
+template <bool VEC4>
+__global__ void __launch_bounds__(kSelThreads)
+    ssdx_nms_select_all_kernel(const float* __restrict__ scores, const int A, const int C, const float score_thr,
+                               u64* __restrict__ lists, int* __restrict__ info, int* __restrict__ flags,
+                               int* __restrict__ iflags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (b == 0 && tid == 0) {  // worklists of the fallback kernels
+    flags[0] = 0;
+    iflags[0] = 0;
+  }
+  const int NS = (A + kSampleStride - 1) / kSampleStride;
+  const int NK = NS * C;
+  unsigned* skeys = (unsigned*)smem_raw;  // [NS*C] sample keys, 0 = not a candidate
+  int* ctr = (int*)(skeys + NK);          // 0..2 rotating counts, 3 listed, 4 valid samples, 5 min key, 6 max key
+  const float* img = scores + (size_t)b * A * C;
+  if (tid < 8) ctr[tid] = (tid == 5) ? -1 : 0;
+  __syncthreads();
+
+  // ---- sample: every 16th anchor (jittered), all classes ----
+  {
+    int nv = 0;
+    unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+    for (int k = tid; k < NS; k += kSelThreads) {
+      int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
+      a = a < A ? a : A - 1;
+      if (VEC4) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(img) + a);
+        const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const unsigned key = (sv[c] > score_thr) ? score_to_key(sv[c]) : 0u;
+          skeys[k * 4 + c] = key;
+          if (key) {
+            ++nv;
+            kmin = min(kmin, key);
+            kmax = max(kmax, key);
+          }
+        }
+      } else {
+        for (int c = 0; c < C; ++c) {
+          const float s = __ldg(img + (size_t)a * C + c);
+          const unsigned key = (s > score_thr) ? score_to_key(s) : 0u;
+          skeys[k * C + c] = key;
+          if (key) {
+            ++nv;
+            kmin = min(kmin, key);
+            kmax = max(kmax, key);
+          }
+        }
+      }
+    }
+    nv = __reduce_add_sync(0xFFFFFFFFu, nv);
+    kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
+    kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+    if (lane == 0 && nv) {
+      atomicAdd(&ctr[4], nv);
+      atomicMin((unsigned*)&ctr[5], kmin);
+      atomicMax((unsigned*)&ctr[6], kmax);
+    }
+  }
+  __syncthreads();
+  // ---- threshold: CTA-wide bisection for a key with kAllRank .. kAllRank+3 samples at or above it ----
+  const int nv = ctr[4];
+  const unsigned kmin = (unsigned)ctr[5], kmax = (unsigned)ctr[6];
+  unsigned T = 1u;  // count(key >= 1) = nv: list every candidate
+  if ((long long)A * C > kCap && nv >= kAllRank) {
+    unsigned lo = kmin;        // count(key >= kmin) = nv >= rank
+    unsigned hi = kmax + 1u;   // count = 0
+    int it = 0;
+    while (hi - lo > 1u) {
+      const unsigned mid = lo + ((hi - lo) >> 1);
+      int cnt = 0;
+      for (int i = tid; i < NK; i += kSelThreads) cnt += skeys[i] >= mid;
+      cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+      const int slot = it % 3;
+      if (lane == 0 && cnt) atomicAdd(&ctr[slot], cnt);
+      __syncthreads();
+      cnt = ctr[slot];
+      if (tid == 0) ctr[(it + 2) % 3] = 0;
+      ++it;
+      if (cnt >= kAllRank) {
+        lo = mid;
+        if (cnt <= kAllRank + 3) break;  // any threshold in this band will do
+      } else {
+        hi = mid;
+      }
+    }
+    T = lo;
+    if (lo == kmin && nv <= kAllRank + 3) T = 1u;  // the whole sample is in the band: list every candidate
+  }
+  if (T == 0x80000000u) T = 0x7FFFFFFFu;  // +0.0 -> -0.0: keeps "s >= t_lo" and "key >= T" the same set
+  // listed  <=>  s > score_thr and key(s) >= T  <=>  s >= t_lo   (one compare per score)
+  const float tf = (T <= 1u) ? -INFINITY : key_to_score(T);
+  const float t_lo = (tf > score_thr) ? tf : nextafterf(score_thr, INFINITY);
+  // ---- one streaming pass ----
+  u64* lst = lists + (size_t)b * kCap;
+  int* cnt_listed = &ctr[3];
+  if (VEC4) {
+    constexpr int kBatch = 4;  // independent 128-bit streaming loads in flight per thread
+    for (int a0 = tid; a0 < A; a0 += kSelThreads * kBatch) {
+      float4 sb[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int a = a0 + u * kSelThreads;
+        sb[u] = (a < A) ? __ldcs(reinterpret_cast<const float4*>(img) + a)
+                        : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const float m = fmaxf(fmaxf(sb[u].x, sb[u].y), fmaxf(sb[u].z, sb[u].w));
+        if (m >= t_lo) {  // rare (~1 % of the scores are listed)
+          const int a = a0 + u * kSelThreads;
+          const float sv[4] = {sb[u].x, sb[u].y, sb[u].z, sb[u].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (sv[c] >= t_lo) {
+              const int pos = atomicAdd(cnt_listed, 1);
+              if (pos < kCap) lst[pos] = make_comp_all(score_to_key(sv[c]), c, a);
+            }
+        }
+      }
+    }
+  } else {
+    const int total = A * C;  // flat coalesced walk
+    for (int e = tid; e < total; e += kSelThreads) {
+      const float s = __ldcs(img + e);
+      if (s >= t_lo) {
+        const int a = e / C;
+        const int pos = atomicAdd(cnt_listed, 1);
+        if (pos < kCap) lst[pos] = make_comp_all(score_to_key(s), e - a * C, a);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    info[(size_t)b * kInfo + 0] = ctr[3];
+    info[(size_t)b * kInfo + 1] = (int)T;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ 2m. merged fast path
+__global__ void __launch_bounds__(kFastThreads, 6)
+    ssdx_nms_fast_all_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                             const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
+                             const int K, const float iou_thr, const float score_thr, float* __restrict__ out,
+                             int* __restrict__ out_valid, int* __restrict__ out_idx, int* __restrict__ flags,
+                             int* __restrict__ iflags) {
+  __shared__ u64 s_list[kCap];
+  __shared__ u64 s_tmp[kCap];  // second exchange buffer of the sort; the candidate arrays below alias it
+  __shared__ float4 s_sbox[kFastMaxSel];
+  __shared__ float s_sarea[kFastMaxSel];
+  __shared__ u64 s_pick[kFastMaxSel];
+  __shared__ unsigned char s_scls[kFastMaxSel];
+  __shared__ u64 s_row[kBlk];  // per candidate of the block: earlier candidates (j < i) that suppress it
+  __shared__ int s_sup[kBlk];
+  __shared__ int s_nsel, s_n;
+  float4* s_cbox = reinterpret_cast<float4*>(s_tmp);                              // [kFastThreads]
+  float* s_carea = reinterpret_cast<float*>(s_cbox + kFastThreads);               // [kFastThreads]
+  unsigned char* s_ccls = reinterpret_cast<unsigned char*>(s_carea + kFastThreads);  // [kFastThreads]
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int n = info[(size_t)b * kInfo + 0];
+  if (n > kCap) {  // uniform: hand the image to the per-class generic kernel + merge
+    if (tid == 0) {
+      const int at = atomicAdd(&flags[0], C);
+      for (int c = 0; c < C; ++c) flags[1 + at + c] = b * C + c;
+      iflags[1 + atomicAdd(&iflags[0], 1)] = b;
+    }
+    return;
+  }
+  const float4* img_boxes = boxes + (size_t)b * A;
+  const float* img_scores = scores + (size_t)b * A * C;
+  const u64* lst = lists + (size_t)b * kCap;
+  for (int i = tid; i < n; i += kFastThreads) s_list[i] = lst[i];
+  if (tid == 0) s_nsel = 0;
+  __syncthreads();
+
+  int n_sel = 0, scans = 0;
+  bool failed = false;
+  unsigned key_hi = (unsigned)info[(size_t)b * kInfo + 1];  // every candidate with key >= key_hi has been listed
+  unsigned span = 0u;
+  while (true) {
+    // ---- sort the current tier (merged order) ----
+    fast_sort(s_list, s_tmp, n, tid);
+    if (span == 0u) {  // key width that held the lower half of this tier -> width expected to hold the refill target
+      const unsigned k_mid = (n >= 2) ? (unsigned)(s_list[n >> 1] >> 32) : 0u;
+      const unsigned k_bot = (n >= 2) ? (unsigned)(s_list[n - 1] >> 32) : 0u;
+      const u64 w = (n >= 2) ? (u64)(k_mid - k_bot) * (2ull * kAllRefillTarget) / (u64)n : 0ull;
+      span = (w == 0ull) ? 1024u : (w > 0x7FFFFFFFull ? 0x7FFFFFFFu : (unsigned)w);
+    }
+
+    for (int g0 = 0; g0 < n && n_sel < K; g0 += kFastThreads) {
+      const int gn = min(kFastThreads, n - g0);
+      __syncthreads();  // s_tmp (sort buffer / previous candidate arrays) is free
+      if (tid < gn) {   // gather the boxes of the next 256 sorted candidates
+        const u64 cp = s_list[g0 + tid];
+        const float4 nb = normalise_box(__ldg(img_boxes + comp_all_idx(cp)));
+        s_cbox[tid] = nb;
+        s_carea[tid] = box_area(nb);
+        s_ccls[tid] = (unsigned char)comp_all_cls(cp);
+      }
+      __syncthreads();
+      for (int base = 0; base < gn && n_sel < K; base += kBlk) {
+        const int m = min(kBlk, gn - base);
+        const int ci = tid >> 2, part = tid & 3;
+        {
+          bool hit = false;
+          float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+          float ai = 0.f;
+          unsigned cls = 0u;
+          if (ci < m) {
+            bi = s_cbox[base + ci];
+            ai = s_carea[base + ci];
+            cls = s_ccls[base + ci];
+          }
+          if (ai > 0.0f) {  // a box without area is never suppressed
+            // kept boxes of every class, newest first; the class test and the exact IoU only for overlapping pairs
+            int s = n_sel - 1 - part;
+            for (; s >= 12 && !hit; s -= 16) {
+              const float4 b0 = s_sbox[s], b1 = s_sbox[s - 4], b2 = s_sbox[s - 8], b3 = s_sbox[s - 12];
+              const bool o0 = boxes_overlap(bi, b0), o1 = boxes_overlap(bi, b1), o2 = boxes_overlap(bi, b2),
+                         o3 = boxes_overlap(bi, b3);
+              if (o0 | o1 | o2 | o3) {
+                hit = (o0 && s_scls[s] == cls && iou_exceeds_overlapping(bi, ai, b0, s_sarea[s], iou_thr)) ||
+                      (o1 && s_scls[s - 4] == cls && iou_exceeds_overlapping(bi, ai, b1, s_sarea[s - 4], iou_thr)) ||
+                      (o2 && s_scls[s - 8] == cls && iou_exceeds_overlapping(bi, ai, b2, s_sarea[s - 8], iou_thr)) ||
+                      (o3 && s_scls[s - 12] == cls && iou_exceeds_overlapping(bi, ai, b3, s_sarea[s - 12], iou_thr));
+              }
+            }
+            for (; s >= 0 && !hit; s -= 4) {
+              const float4 b0 = s_sbox[s];
+              if (boxes_overlap(bi, b0) && s_scls[s] == cls)
+                hit = iou_exceeds_overlapping(bi, ai, b0, s_sarea[s], iou_thr);
+            }
+          }
+          const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+          if (part == 0) s_sup[ci] = (ci >= m) || (((bal >> (lane & 28)) & 0xFu) != 0u);
+          // earlier candidates j < ci of the same class that suppress ci; this thread tests j = 4*jj + part
+          unsigned lo = 0u, hi = 0u;
+          if (ai > 0.0f && part < ci) {
+            unsigned ov = 0u;
+            const int nj = (ci - part + 3) >> 2;  // number of jj with 4*jj + part < ci
+            const int nj4 = (nj + 3) & ~3;        // stale slots beyond m / ci are masked below
+            for (int j0 = 0; j0 < nj4; j0 += 4) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                ov |= (unsigned)boxes_overlap(bi, s_cbox[base + 4 * (j0 + jj) + part]) << (j0 + jj);
+            }
+            if (nj < 16) ov &= (1u << nj) - 1u;
+            while (ov) {  // class + exact test for the few overlapping pairs
+              const int jj = __ffs(ov) - 1;
+              ov &= ov - 1u;
+              const int j = 4 * jj + part;
+              if (s_ccls[base + j] == cls &&
+                  iou_exceeds_overlapping(bi, ai, s_cbox[base + j], s_carea[base + j], iou_thr)) {
+                if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
+              }
+            }
+          }
+          lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 1);
+          hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 1);
+          lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 2);
+          hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 2);
+          if (part == 0) s_row[ci] = ((u64)hi << 32) | (u64)lo;
+        }
+        __syncthreads();
+        if (warp == kFastThreads / 32 - 1) {  // the arbiter favours the highest warp id: keep the serial part there
+          const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
+          const u64 ra = s_row[lane], rb = s_row[lane + 32];
+          const unsigned a_lo = (unsigned)ra & lt;
+          const unsigned b_lo = (unsigned)rb, b_hi = (unsigned)(rb >> 32) & lt;
+          unsigned supp_lo = __ballot_sync(0xFFFFFFFFu, s_sup[lane] != 0);
+          unsigned supp_hi = __ballot_sync(0xFFFFFFFFu, s_sup[lane + 32] != 0);
+          unsigned kept_lo = 0u, kept_hi = 0u;
+          // fix-point: the lowest undecided candidate is decided in every round
+          while ((kept_lo | supp_lo) != 0xFFFFFFFFu || (kept_hi | supp_hi) != 0xFFFFFFFFu) {
+            const bool und_a = !((kept_lo | supp_lo) & me), und_b = !((kept_hi | supp_hi) & me);
+            const bool a_hit = (a_lo & kept_lo) != 0u;
+            const bool b_hit = ((b_lo & kept_lo) | (b_hi & kept_hi)) != 0u;
+            const bool a_free = (a_lo & ~supp_lo) == 0u;
+            const bool b_free = ((b_lo & ~supp_lo) | (b_hi & ~supp_hi)) == 0u;
+            const unsigned nk_lo = __ballot_sync(0xFFFFFFFFu, und_a && !a_hit && a_free);
+            const unsigned ns_lo = __ballot_sync(0xFFFFFFFFu, und_a && a_hit);
+            const unsigned nk_hi = __ballot_sync(0xFFFFFFFFu, und_b && !b_hit && b_free);
+            const unsigned ns_hi = __ballot_sync(0xFFFFFFFFu, und_b && b_hit);
+            kept_lo |= nk_lo;
+            supp_lo |= ns_lo;
+            kept_hi |= nk_hi;
+            supp_hi |= ns_hi;
+          }
+          const int room = K - n_sel;
+          const int n_lo = __popc(kept_lo);
+          if (kept_lo & me) {
+            const int r = __popc(kept_lo & lt);
+            if (r < room) {
+              s_sbox[n_sel + r] = s_cbox[base + lane];
+              s_sarea[n_sel + r] = s_carea[base + lane];
+              s_scls[n_sel + r] = s_ccls[base + lane];
+              s_pick[n_sel + r] = s_list[g0 + base + lane];
+            }
+          }
+          if (kept_hi & me) {
+            const int r = n_lo + __popc(kept_hi & lt);
+            if (r < room) {
+              s_sbox[n_sel + r] = s_cbox[base + lane + 32];
+              s_sarea[n_sel + r] = s_carea[base + lane + 32];
+              s_scls[n_sel + r] = s_ccls[base + lane + 32];
+              s_pick[n_sel + r] = s_list[g0 + base + lane + 32];
+            }
+          }
+          if (lane == 0) s_nsel = n_sel + min(room, n_lo + __popc(kept_hi));
+        }
+        __syncthreads();
+        n_sel = s_nsel;
+      }
+    }
+    if (n_sel >= K || key_hi <= 1u) break;  // done, or every candidate has been visited
+    // ---- the tier ran dry: fetch the next key band [key_lo, key_hi) of all classes from the scores ----
+    bool got = false;
+    while (!got && !failed) {
+      if (++scans > kMaxRefills) {
+        failed = true;
+        break;
+      }
+      const unsigned key_lo = (key_hi - 1u > span) ? key_hi - span : 1u;
+      __syncthreads();
+      if (tid == 0) s_n = 0;
+      __syncthreads();
+      const int total = A * C;
+      for (int e0 = tid; e0 < total; e0 += kFastThreads * 8) {  // 8 independent loads in flight per thread
+        float sv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * kFastThreads;
+          sv[u] = (e < total) ? __ldg(img_scores + e) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (sv[u] > score_thr) {  // false for the -inf padding
+            const unsigned key = score_to_key(sv[u]);
+            if (key >= key_lo && key < key_hi) {
+              const int e = e0 + u * kFastThreads;
+              const int a = e / C;
+              const int pos = atomicAdd(&s_n, 1);
+              if (pos < kCap) s_list[pos] = make_comp_all(key, e - a * C, a);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const int n_new = s_n;
+      if (n_new > kCap) {
+        if (span <= 1u) failed = true;  // more than kCap equal scores: cannot be split by a threshold
+        span = max(span >> 2, 1u);
+      } else {
+        n = n_new;
+        key_hi = key_lo;
+        if (n_new < kAllRefillTarget / 8) span = (span > 0x1FFFFFFFu) ? 0x7FFFFFFFu : span << 2;
+        else if (n_new < kAllRefillTarget / 2) span = (span > 0x3FFFFFFFu) ? 0x7FFFFFFFu : span << 1;
+        else if (n_new > kAllRefillTarget * 2) span = max(span >> 1, 1u);
+        got = n_new > 0 || key_lo <= 1u;
+      }
+    }
+    if (failed) break;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (failed) {
+    if (tid == 0) {
+      const int at = atomicAdd(&flags[0], C);
+      for (int c = 0; c < C; ++c) flags[1 + at + c] = b * C + c;
+      iflags[1 + atomicAdd(&iflags[0], 1)] = b;
+    }
+    return;
+  }
+  // ---- rows, already in merge order: [label, prob, xmin, ymin, xmax, ymax] (layers.py:155-162), zero padding ----
+  float* o = out + (size_t)b * K * 6;
+  for (int r = tid; r < n_sel; r += kFastThreads) {
+    const u64 cp = s_pick[r];
+    const int idx = comp_all_idx(cp);
+    const float4 bx = __ldg(img_boxes + idx);  // raw (ymin, xmin, ymax, xmax)
+    float* row = o + (size_t)r * 6;
+    row[0] = (float)comp_all_cls(cp);
+    row[1] = key_to_score((unsigned)(cp >> 32));
+    row[2] = bx.y;  // gather [1,0,3,2], layers.py:155
+    row[3] = bx.x;
+    row[4] = bx.w;
+    row[5] = bx.z;
+    if (out_idx) out_idx[(size_t)b * K + r] = idx;
+  }
+  for (int e = n_sel * 6 + tid; e < K * 6; e += kFastThreads) o[e] = 0.0f;
+  if (out_idx)
+    for (int e = n_sel + tid; e < K; e += kFastThreads) out_idx[(size_t)b * K + e] = -1;
+  if (out_valid && tid == 0) out_valid[b] = n_sel;
+}
+
 // ------------------------------------------------------------------------------------------ 3. generic path
 struct GenSmem {
   unsigned* keys;  // [A]      0 = not a (remaining) candidate
@@ -823,10 +1248,14 @@ __global__ void __launch_bounds__(kMergeThreads)
     ssdx_nms_merge_kernel(const float4* __restrict__ boxes, const u64* __restrict__ picks,
                           const int* __restrict__ pick_cnt, const int A, const int C, const int limit, const int K,
                           const int stage_in_smem, float* __restrict__ out, int* __restrict__ out_valid,
-                          int* __restrict__ out_idx) {
+                          int* __restrict__ out_idx, const int* __restrict__ iflags, const int batch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x;
   const int tid = threadIdx.x;
+  // without a worklist every image of the batch is merged; with one (merged pipeline) only the handed-over images
+  const int n_work = (iflags != nullptr) ? iflags[0] : batch;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+  const int b = (iflags != nullptr) ? iflags[1 + work] : work;
+  __syncthreads();  // shared memory is reused across worklist items
   const u64* img_picks = picks + (size_t)b * C * limit;
   const int* cnt = pick_cnt + (size_t)b * C;
   if (stage_in_smem) {  // the binary searches below then run on shared memory instead of L2
@@ -867,12 +1296,13 @@ __global__ void __launch_bounds__(kMergeThreads)
   if (out_idx)
     for (int e = valid + tid; e < K; e += kMergeThreads) out_idx[(size_t)b * K + e] = -1;
   if (out_valid && tid == 0) out_valid[b] = valid;
+  }  // worklist loop
 }
 
 inline int nms_limit(int max_per_class, int A) { return max_per_class < A ? max_per_class : A; }
 
 struct NmsWorkspace {
-  size_t picks, pick_cnt, lists, info, flags, total;
+  size_t picks, pick_cnt, lists, info, flags, iflags, total;
 };
 
 inline NmsWorkspace nms_workspace(int batch, int A, int C, int max_per_class) {
@@ -885,6 +1315,7 @@ inline NmsWorkspace nms_workspace(int batch, int A, int C, int max_per_class) {
   w.lists = off;    off += ssdx_align_up(seg * kCap * sizeof(u64), 256);
   w.info = off;     off += ssdx_align_up(seg * kInfo * sizeof(int), 256);
   w.flags = off;    off += ssdx_align_up((seg + 1) * sizeof(int), 256);
+  w.iflags = off;   off += ssdx_align_up(((size_t)batch + 1) * sizeof(int), 256);
   w.total = off;
   return w;
 }
@@ -943,12 +1374,60 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
   int* flags = (int*)(base + w.flags);
   const float4* bx = (const float4*)boxes_yxyx;
 
-  // 1. select
+  int* iflags = (int*)(base + w.iflags);
   const int NS = (A + kSampleStride - 1) / kSampleStride;
-  const size_t sel_smem = (size_t)(C < kSelGroup ? C : kSelGroup) * NS * 4 + kSelGroup * 12 + 16;
   const bool vec4 = (C == 4) && (((uintptr_t)scores & 15) == 0);
-  const char* force = getenv("SSDX_NMS_PATH");  // "generic": test hook, both paths give identical results
-  const bool use_fast = sel_smem <= 200 * 1024 && !(force != nullptr && force[0] == 'g');
+  // test hooks: "generic" = exact generic kernel alone, "perclass" = per-class fast pipeline even when the merged
+  // one applies.  All paths give identical results.
+  const char* force = getenv("SSDX_NMS_PATH");
+  const bool force_generic = force != nullptr && force[0] == 'g';
+  const bool force_perclass = force != nullptr && force[0] == 'p';
+  const size_t gen_smem_attr = gen_smem;
+  SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gen_smem_attr));
+  const int num_segments = batch * C;
+  const size_t merge_smem = (size_t)C * limit * sizeof(u64);
+  const int stage = merge_smem <= 96 * 1024;
+  if (stage)
+    SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)merge_smem));
+
+  // ---- merged pipeline: one list / sort / greedy pass per image ----
+  const size_t sel_all_smem = (size_t)NS * C * 4 + 64;
+  const bool merged = !force_generic && !force_perclass && max_per_class >= max_total && C <= 256 &&
+                      A <= (1 << 24) && max_total <= kFastMaxSel && sel_all_smem <= 64 * 1024;
+  if (merged) {
+    if (vec4) {
+      SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sel_all_smem));
+      ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, sel_all_smem, s>>>(scores, A, C, score_threshold, lists,
+                                                                                info, flags, iflags);
+    } else {
+      SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sel_all_smem));
+      ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, sel_all_smem, s>>>(scores, A, C, score_threshold, lists,
+                                                                                 info, flags, iflags);
+    }
+    SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
+    ssdx_nms_fast_all_kernel<<<batch, kFastThreads, 0, s>>>(bx, scores, lists, info, A, C, max_total, iou_threshold,
+                                                            score_threshold, out, out_valid, out_anchor_idx, flags,
+                                                            iflags);
+    SSDX_LAUNCH_CHECK("ssdx_nms_fast_all_kernel");
+    // handed-over images only (both kernels return at once when the worklists are empty)
+    const int sms = ssdx_sm_count(device);
+    ssdx_nms_generic_kernel<<<min(num_segments, 2 * sms), kGenThreads, gen_smem, s>>>(
+        bx, scores, A, C, limit, iou_threshold, score_threshold, picks, pick_cnt, flags, num_segments);
+    SSDX_LAUNCH_CHECK("ssdx_nms_generic_kernel");
+    ssdx_nms_merge_kernel<<<min(batch, 2 * sms), kMergeThreads, stage ? merge_smem : 0, s>>>(
+        bx, picks, pick_cnt, A, C, limit, max_total, stage, out, out_valid, out_anchor_idx, iflags, batch);
+    SSDX_LAUNCH_CHECK("ssdx_nms_merge_kernel");
+    return SSDX_OK;
+  }
+
+  // ---- per-class pipeline ----
+  // 1. select
+  const size_t sel_smem = (size_t)(C < kSelGroup ? C : kSelGroup) * NS * 4 + kSelGroup * 12 + 16;
+  const bool use_fast = sel_smem <= 200 * 1024 && !force_generic;
   if (use_fast) {
     dim3 gsel((C + kSelGroup - 1) / kSelGroup, batch);
     if (vec4) {
@@ -968,22 +1447,15 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_kernel");
   }
   // 3. generic path (flag-gated; handles every segment when the fast path is not applicable)
-  SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));
-  const int num_segments = batch * C;
   const int gen_grid = use_fast ? min(num_segments, 2 * ssdx_sm_count(device)) : num_segments;
   ssdx_nms_generic_kernel<<<gen_grid, kGenThreads, gen_smem, s>>>(bx, scores, A, C, limit, iou_threshold,
                                                                   score_threshold, picks, pick_cnt,
                                                                   use_fast ? flags : nullptr, num_segments);
   SSDX_LAUNCH_CHECK("ssdx_nms_generic_kernel");
   // 4. merge
-  const size_t merge_smem = (size_t)C * limit * sizeof(u64);
-  const int stage = merge_smem <= 96 * 1024;
-  if (stage)
-    SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)merge_smem));
   ssdx_nms_merge_kernel<<<batch, kMergeThreads, stage ? merge_smem : 0, s>>>(bx, picks, pick_cnt, A, C, limit,
                                                                              max_total, stage, out, out_valid,
-                                                                             out_anchor_idx);
+                                                                             out_anchor_idx, nullptr, batch);
   SSDX_LAUNCH_CHECK("ssdx_nms_merge_kernel");
   return SSDX_OK;
 }

@@ -31,14 +31,15 @@ def encode_path(request, monkeypatch):
     return request.param
 
 
-@pytest.fixture(autouse=True, params=["fast", "generic"])
+@pytest.fixture(autouse=True, params=["fast", "perclass", "generic"])
 def nms_path(request, monkeypatch):
-    """NMS tests run on the fast pipeline (select + fast kernel, generic only for handed-over segments) and
-    with the exact generic kernel alone."""
-    if request.param == "generic":
+    """NMS tests run on the default dispatch (merged one-pass-per-image pipeline when max_per_class >= max_total,
+    else the per-class fast pipeline; generic only for handed-over work), with the per-class fast pipeline forced,
+    and with the exact generic kernel alone."""
+    if request.param != "fast":
         if "nms" not in request.node.name:
             pytest.skip("NMS driver does not matter for this test")
-        monkeypatch.setenv("SSDX_NMS_PATH", "generic")
+        monkeypatch.setenv("SSDX_NMS_PATH", request.param)
     return request.param
 
 
@@ -286,6 +287,38 @@ def test_nms_degenerate_boxes_and_small_sets(lib):
     nms_check(lib, yxyx, scores, 10, 10, 0.45, 2.0)      # nothing passes the score threshold
     out = nms_check(lib, yxyx[:, :1], scores[:, :1], 3, 4, 0.5, 0.0)  # a single box
     assert out.shape == (3, 4, 6)
+
+
+def test_nms_many_classes_and_cross_class_ties(lib):
+    """C = 21 (scalar score path) with max_per_class >= max_total (merged one-pass pipeline), plus scores that tie
+    ACROSS classes: the merge takes the lower class first, then the lower anchor."""
+    rng = np.random.default_rng(21)
+    B, A, C = 3, 2500, 21
+    ctr = rng.uniform(40, 600, size=(B, A, 2))
+    wh = rng.uniform(20, 120, size=(B, A, 2))
+    yxyx = np.concatenate([ctr - wh / 2, ctr + wh / 2], -1).astype(np.float32)
+    scores = orc.dedup_scores(rng.uniform(0, 1, size=(B, A, C)).astype(np.float32))
+    nms_check(lib, yxyx, scores, 100, 100, 0.5, 0.3)
+    nms_check(lib, yxyx, scores, 300, 150, 0.45, 0.05)
+    tied = scores.copy()
+    tied[:, :, 5] = tied[:, :, 2]          # every score of class 5 ties with class 2 on the same anchor
+    tied[:, 100:200, 7] = tied[:, 300:400, 2]  # ties across classes on different anchors
+    nms_check(lib, yxyx, tied, 100, 100, 0.5, 0.3)
+
+
+def test_nms_merged_runs_dry_and_refills(lib):
+    """Heavily clustered boxes with max_total = max_per_class: the first list of the merged pipeline runs dry and
+    the key-band refills have to fetch more candidates of all classes."""
+    rng = np.random.default_rng(31)
+    B, A, C = 2, 8000, 4
+    centers = rng.uniform(80, 560, size=(B, 40, 2))
+    which = rng.integers(0, 40, size=(B, A))
+    c = np.take_along_axis(centers, which[..., None].repeat(2, -1), axis=1) + rng.normal(0, 4, size=(B, A, 2))
+    wh = rng.uniform(50, 70, size=(B, A, 2))
+    yxyx = np.concatenate([c - wh / 2, c + wh / 2], -1).astype(np.float32)
+    scores = orc.dedup_scores(rng.uniform(0.02, 1, size=(B, A, C)).astype(np.float32))
+    out = nms_check(lib, yxyx, scores, 200, 200, 0.45, 0.01)
+    assert (out[..., 1] > 0).sum(axis=1).max() <= 4 * 40 + 40  # ~ one survivor per (cluster, class)
 
 
 def test_nms_torch_in_torch_out(lib, golden):
