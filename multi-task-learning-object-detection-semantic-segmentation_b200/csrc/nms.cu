@@ -61,6 +61,9 @@ constexpr int kBlk = 64;
 constexpr int kGenThreads = 512;
 constexpr int kChunk = 512;
 constexpr int kMergeThreads = 256;
+#ifndef SSDX_FAST_MINB
+#define SSDX_FAST_MINB 7
+#endif
 constexpr int kAllRank = 26;       // merged select: threshold at the 26th largest sample => ~416 +- 80 listed
 constexpr int kAllRefillTarget = 384;
 
@@ -191,8 +194,7 @@ __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64*
           const int e = r * 256 + tid;
           const u64 p = __shfl_xor_sync(0xFFFFFFFFu, v[r], j);
           const bool take_max = (((e & j) == 0) == ((e & k) == 0));
-          const u64 mx = v[r] > p ? v[r] : p, mn = v[r] > p ? p : v[r];
-          v[r] = take_max ? mx : mn;
+          v[r] = ((v[r] > p) == take_max) ? v[r] : p;  // keys are distinct or equal: one compare, one select
         }
       } else {
         u64* buf = flip ? buf1 : buf0;
@@ -205,8 +207,7 @@ __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64*
           const int e = r * 256 + tid;
           const u64 p = buf[e ^ j];
           const bool take_max = (((e & j) == 0) == ((e & k) == 0));
-          const u64 mx = v[r] > p ? v[r] : p, mn = v[r] > p ? p : v[r];
-          v[r] = take_max ? mx : mn;
+          v[r] = ((v[r] > p) == take_max) ? v[r] : p;
         }
       }
     }
@@ -621,7 +622,9 @@ __global__ void __launch_bounds__(kSelThreads)
     ssdx_nms_select_all_kernel(const float* __restrict__ scores, const int A, const int C, const float score_thr,
                                u64* __restrict__ lists, int* __restrict__ info, int* __restrict__ flags,
                                int* __restrict__ iflags) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned s_max[kSelThreads];  // per-thread maximum of the sampled keys
+  __shared__ unsigned s_T;
+  __shared__ int s_cnt;
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
   if (b == 0 && tid == 0) {  // worklists of the fallback kernels
@@ -629,94 +632,78 @@ __global__ void __launch_bounds__(kSelThreads)
     iflags[0] = 0;
   }
   const int NS = (A + kSampleStride - 1) / kSampleStride;
-  const int NK = NS * C;
-  unsigned* skeys = (unsigned*)smem_raw;  // [NS*C] sample keys, 0 = not a candidate
-  int* ctr = (int*)(skeys + NK);          // 0..2 rotating counts, 3 listed, 4 valid samples, 5 min key, 6 max key
   const float* img = scores + (size_t)b * A * C;
-  if (tid < 8) ctr[tid] = (tid == 5) ? -1 : 0;
-  __syncthreads();
+  if (tid == 0) s_cnt = 0;
 
-  // ---- sample: every 16th anchor (jittered), all classes ----
+  // ---- sample: every 16th anchor (jittered), all classes; each thread keeps the largest key it sees ----
   {
-    int nv = 0;
-    unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+    unsigned kmax = 0u;  // 0 = no candidate
     for (int k = tid; k < NS; k += kSelThreads) {
       int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
       a = a < A ? a : A - 1;
       if (VEC4) {
         const float4 s = __ldg(reinterpret_cast<const float4*>(img) + a);
-        const float sv[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const unsigned key = (sv[c] > score_thr) ? score_to_key(sv[c]) : 0u;
-          skeys[k * 4 + c] = key;
-          if (key) {
-            ++nv;
-            kmin = min(kmin, key);
-            kmax = max(kmax, key);
-          }
-        }
+        const float m = fmaxf(fmaxf(s.x, s.y), fmaxf(s.z, s.w));
+        if (m > score_thr) kmax = max(kmax, score_to_key(m));
       } else {
         for (int c = 0; c < C; ++c) {
           const float s = __ldg(img + (size_t)a * C + c);
-          const unsigned key = (s > score_thr) ? score_to_key(s) : 0u;
-          skeys[k * C + c] = key;
-          if (key) {
-            ++nv;
-            kmin = min(kmin, key);
-            kmax = max(kmax, key);
-          }
+          if (s > score_thr) kmax = max(kmax, score_to_key(s));
         }
       }
     }
-    nv = __reduce_add_sync(0xFFFFFFFFu, nv);
-    kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
-    kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
-    if (lane == 0 && nv) {
-      atomicAdd(&ctr[4], nv);
-      atomicMin((unsigned*)&ctr[5], kmin);
-      atomicMax((unsigned*)&ctr[6], kmax);
-    }
+    s_max[tid] = kmax;
   }
   __syncthreads();
-  // ---- threshold: CTA-wide bisection for a key with kAllRank .. kAllRank+3 samples at or above it ----
-  const int nv = ctr[4];
-  const unsigned kmin = (unsigned)ctr[5], kmax = (unsigned)ctr[6];
-  unsigned T = 1u;  // count(key >= 1) = nv: list every candidate
-  if ((long long)A * C > kCap && nv >= kAllRank) {
-    unsigned lo = kmin;        // count(key >= kmin) = nv >= rank
-    unsigned hi = kmax + 1u;   // count = 0
-    int it = 0;
-    while (hi - lo > 1u) {
-      const unsigned mid = lo + ((hi - lo) >> 1);
-      int cnt = 0;
-      for (int i = tid; i < NK; i += kSelThreads) cnt += skeys[i] >= mid;
-      cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-      const int slot = it % 3;
-      if (lane == 0 && cnt) atomicAdd(&ctr[slot], cnt);
-      __syncthreads();
-      cnt = ctr[slot];
-      if (tid == 0) ctr[(it + 2) % 3] = 0;
-      ++it;
-      if (cnt >= kAllRank) {
-        lo = mid;
-        if (cnt <= kAllRank + 3) break;  // any threshold in this band will do
-      } else {
-        hi = mid;
-      }
+  // ---- threshold: the kAllRank-th largest of the per-thread maxima.  At least kAllRank sampled keys are at or
+  //      above it (usually just that many: the top keys of a sample sit in different threads), so ~16 * kAllRank
+  //      candidates get listed.  One warp bisects over the 256 maxima held in registers. ----
+  if (tid < 32) {
+    unsigned v[kSelThreads / 32];
+    int nz = 0;
+    unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+    for (int r = 0; r < kSelThreads / 32; ++r) {
+      v[r] = s_max[r * 32 + lane];
+      nz += v[r] != 0u;
+      kmax = max(kmax, v[r]);
+      kmin = min(kmin, v[r] != 0u ? v[r] : 0xFFFFFFFFu);
     }
-    T = lo;
-    if (lo == kmin && nv <= kAllRank + 3) T = 1u;  // the whole sample is in the band: list every candidate
+    nz = __reduce_add_sync(0xFFFFFFFFu, nz);
+    kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+    kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
+    unsigned T = 1u;  // list every candidate
+    if ((long long)A * C > kCap && nz >= kAllRank) {
+      unsigned lo = kmin;       // count(max >= kmin) = nz >= rank
+      unsigned hi = kmax + 1u;  // count = 0
+      while (hi - lo > 1u) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < kSelThreads / 32; ++r) cnt += v[r] >= mid;
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (cnt >= kAllRank) {
+          lo = mid;
+          if (cnt <= kAllRank + 3) break;  // any threshold in this band will do
+        } else {
+          hi = mid;
+        }
+      }
+      T = lo;
+      if (lo == kmin && nz <= kAllRank + 3) T = 1u;  // every thread maximum is in the band: list every candidate
+    }
+    if (T == 0x80000000u) T = 0x7FFFFFFFu;  // +0.0 -> -0.0: keeps "s >= t_lo" and "key >= T" the same set
+    if (lane == 0) s_T = T;
   }
-  if (T == 0x80000000u) T = 0x7FFFFFFFu;  // +0.0 -> -0.0: keeps "s >= t_lo" and "key >= T" the same set
+  __syncthreads();
+  const unsigned T = s_T;
   // listed  <=>  s > score_thr and key(s) >= T  <=>  s >= t_lo   (one compare per score)
   const float tf = (T <= 1u) ? -INFINITY : key_to_score(T);
   const float t_lo = (tf > score_thr) ? tf : nextafterf(score_thr, INFINITY);
-  // ---- one streaming pass ----
+  // ---- one streaming pass; hits (~1 % of the scores) are only marked, then appended in a compact loop ----
   u64* lst = lists + (size_t)b * kCap;
-  int* cnt_listed = &ctr[3];
   if (VEC4) {
-    constexpr int kBatch = 4;  // independent 128-bit streaming loads in flight per thread
+    constexpr int kBatch = 8;  // independent 128-bit streaming loads in flight per thread
     for (int a0 = tid; a0 < A; a0 += kSelThreads * kBatch) {
       float4 sb[kBatch];
 #pragma unroll
@@ -725,19 +712,21 @@ __global__ void __launch_bounds__(kSelThreads)
         sb[u] = (a < A) ? __ldcs(reinterpret_cast<const float4*>(img) + a)
                         : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
+      unsigned hits = 0u;  // bit 4*u + c
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const float m = fmaxf(fmaxf(sb[u].x, sb[u].y), fmaxf(sb[u].z, sb[u].w));
-        if (m >= t_lo) {  // rare (~1 % of the scores are listed)
-          const int a = a0 + u * kSelThreads;
-          const float sv[4] = {sb[u].x, sb[u].y, sb[u].z, sb[u].w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (sv[c] >= t_lo) {
-              const int pos = atomicAdd(cnt_listed, 1);
-              if (pos < kCap) lst[pos] = make_comp_all(score_to_key(sv[c]), c, a);
-            }
-        }
+        hits |= (sb[u].x >= t_lo ? 1u : 0u) << (4 * u);
+        hits |= (sb[u].y >= t_lo ? 2u : 0u) << (4 * u);
+        hits |= (sb[u].z >= t_lo ? 4u : 0u) << (4 * u);
+        hits |= (sb[u].w >= t_lo ? 8u : 0u) << (4 * u);
+      }
+      while (hits != 0u) {  // the score is re-read (L1/L2 hit) instead of indexing the register batch dynamically
+        const int bit = __ffs(hits) - 1;
+        hits &= hits - 1u;
+        const int a = a0 + (bit >> 2) * kSelThreads, c = bit & 3;
+        const float s = __ldg(img + (size_t)a * 4 + c);
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < kCap) lst[pos] = make_comp_all(score_to_key(s), c, a);
       }
     }
   } else {
@@ -746,20 +735,21 @@ __global__ void __launch_bounds__(kSelThreads)
       const float s = __ldcs(img + e);
       if (s >= t_lo) {
         const int a = e / C;
-        const int pos = atomicAdd(cnt_listed, 1);
+        const int pos = atomicAdd(&s_cnt, 1);
         if (pos < kCap) lst[pos] = make_comp_all(score_to_key(s), e - a * C, a);
       }
     }
   }
   __syncthreads();
   if (tid == 0) {
-    info[(size_t)b * kInfo + 0] = ctr[3];
+    info[(size_t)b * kInfo + 0] = s_cnt;
     info[(size_t)b * kInfo + 1] = (int)T;
   }
 }
 
 // ------------------------------------------------------------------------------------------ 2m. merged fast path
-__global__ void __launch_bounds__(kFastThreads, 6)
+template <int MAXSEL, int MINB>  // MAXSEL >= K; MINB resident CTAs per SM (7 * 148 >= 1024: one wave at batch 1024)
+__global__ void __launch_bounds__(kFastThreads, MINB)
     ssdx_nms_fast_all_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
                              const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                              const int K, const float iou_thr, const float score_thr, float* __restrict__ out,
@@ -767,10 +757,10 @@ __global__ void __launch_bounds__(kFastThreads, 6)
                              int* __restrict__ iflags) {
   __shared__ u64 s_list[kCap];
   __shared__ u64 s_tmp[kCap];  // second exchange buffer of the sort; the candidate arrays below alias it
-  __shared__ float4 s_sbox[kFastMaxSel];
-  __shared__ float s_sarea[kFastMaxSel];
-  __shared__ u64 s_pick[kFastMaxSel];
-  __shared__ unsigned char s_scls[kFastMaxSel];
+  __shared__ float4 s_sbox[MAXSEL];
+  __shared__ float s_sarea[MAXSEL];
+  __shared__ u64 s_pick[MAXSEL];
+  __shared__ unsigned char s_scls[MAXSEL];
   __shared__ u64 s_row[kBlk];  // per candidate of the block: earlier candidates (j < i) that suppress it
   __shared__ int s_sup[kBlk];
   __shared__ int s_nsel, s_n;
@@ -1393,25 +1383,24 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
                                    (int)merge_smem));
 
   // ---- merged pipeline: one list / sort / greedy pass per image ----
-  const size_t sel_all_smem = (size_t)NS * C * 4 + 64;
   const bool merged = !force_generic && !force_perclass && max_per_class >= max_total && C <= 256 &&
-                      A <= (1 << 24) && max_total <= kFastMaxSel && sel_all_smem <= 64 * 1024;
+                      A <= (1 << 24) && max_total <= kFastMaxSel;
   if (merged) {
-    if (vec4) {
-      SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sel_all_smem));
-      ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, sel_all_smem, s>>>(scores, A, C, score_threshold, lists,
-                                                                                info, flags, iflags);
-    } else {
-      SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sel_all_smem));
-      ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, sel_all_smem, s>>>(scores, A, C, score_threshold, lists,
-                                                                                 info, flags, iflags);
-    }
+    if (vec4)
+      ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, A, C, score_threshold, lists, info, flags,
+                                                                     iflags);
+    else
+      ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, A, C, score_threshold, lists, info,
+                                                                      flags, iflags);
     SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
-    ssdx_nms_fast_all_kernel<<<batch, kFastThreads, 0, s>>>(bx, scores, lists, info, A, C, max_total, iou_threshold,
-                                                            score_threshold, out, out_valid, out_anchor_idx, flags,
-                                                            iflags);
+    if (max_total <= 256)
+      ssdx_nms_fast_all_kernel<256, SSDX_FAST_MINB><<<batch, kFastThreads, 0, s>>>(
+          bx, scores, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx,
+          flags, iflags);
+    else
+      ssdx_nms_fast_all_kernel<kFastMaxSel, 6><<<batch, kFastThreads, 0, s>>>(
+          bx, scores, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx,
+          flags, iflags);
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_all_kernel");
     // handed-over images only (both kernels return at once when the worklists are empty)
     const int sms = ssdx_sm_count(device);

@@ -17,7 +17,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, kre = sys.argv[1], sys.argv[2]
-lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(
+lib = os.path.abspath(sys.argv[3]) if len(sys.argv) > 3 else os.path.join(
     ROOT, "multi-task-learning-object-detection-semantic-segmentation_b200", "lib", "libssdx.so")
 min_pct = float(sys.argv[4]) if len(sys.argv) > 4 else 0.7
 
@@ -38,11 +38,11 @@ subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 lines = None
 for cub in glob.glob(os.path.join(tmp, "*.cubin")):
     dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
-    cur, infunc, seq = None, False, []
+    cur, infunc, seq, cands = None, False, [], []
     for ln in dis.splitlines():
         if ln.startswith("//---") and ".text." in ln:
             if infunc and seq:
-                break
+                cands.append(seq)
             infunc = func in ln
             seq = []
         elif infunc:
@@ -51,8 +51,13 @@ for cub in glob.glob(os.path.join(tmp, "*.cubin")):
                 cur = int(m.group(1))
             elif re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
                 seq.append((cur, ln.split("*/", 1)[1].strip().rstrip(";").strip()))
-    if infunc and seq and abs(len(seq) - len(sass)) <= 2:
-        lines = seq
+    if infunc and seq:
+        cands.append(seq)
+    for seq in cands:  # template instantiations share the name: take the one with the same instruction count
+        if abs(len(seq) - len(sass)) <= 2:
+            lines = seq
+            break
+    if lines is not None:
         break
 if lines is None:
     raise SystemExit(f"could not align SASS of {func} (ncu has {len(sass)} instructions)")
