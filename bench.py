@@ -279,6 +279,7 @@ def gpu_arm(args, rank, world, local_rank):
     sp = stream.cuda_stream
 
     def step_device(events=None):
+        nonlocal sp
         i = 0
         if events is not None:
             events[i].record(stream); i += 1
@@ -297,7 +298,9 @@ def gpu_arm(args, rank, world, local_rank):
         if events is not None:
             events[i].record(stream)
 
-    kernels_per_step = (2 if "encode" in stages else 0) + 1 + 2  # + one memset node in encode
+    # kernels of one step: fused encode (1) + decode (1) + NMS merged pipeline (select_all, fast_all and the two
+    # worklist-gated fallback kernels, which exit at once when nothing was handed over)
+    kernels_per_step = (1 if "encode" in stages else 0) + 1 + 4
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -309,18 +312,41 @@ def gpu_arm(args, rank, world, local_rank):
     # ---------------- device-resident timing ----------------
     for _ in range(max(args.warmup, 3)):
         step_device()
-    n_ev = len(stages) + 1
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    torch.cuda.synchronize(dev)
+    # One step = one CUDA graph launch (the C ABI is stream-ordered and allocation-free, so it captures as is):
+    # no host-side launch gaps between the kernels of a step.  --no-graph times the eager launches instead.
+    graph = None
+    if not args.no_graph:
+        cap_stream = torch.cuda.Stream(dev)
+        cap_stream.wait_stream(stream)
+        graph = torch.cuda.CUDAGraph()
+        outer_sp = sp
+        with torch.cuda.graph(graph, stream=cap_stream):
+            sp = torch.cuda.current_stream(dev).cuda_stream
+            step_device()
+        sp = outer_sp
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize(dev)
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
     t_start.record(stream)
     for k in range(args.steps):
-        step_device(evs[k])
+        if graph is not None:
+            graph.replay()
+        else:
+            step_device()
     t_end.record(stream)
     barrier()
     total_ms = t_start.elapsed_time(t_end)
-    stage_ms = {s: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
+    # per-stage durations (roofline): the same K steps again, eager, with an event after every stage
+    n_ev = len(stages) + 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        step_device(evs[k])
+    barrier()
+    stage_ms = {s: float(np.median([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
                 for i, s in enumerate(stages)}
 
     # ---------------- end-to-end through the public API with host buffers ----------------
@@ -390,8 +416,8 @@ def gpu_arm(args, rank, world, local_rank):
         achieved = dom_bytes / (stage_ms[dom] / 1e3) / 1e9
         stage_roof = {s: {"ms": stage_ms[s], "gbs": BYTES_PER_IMAGE[s] * B / (stage_ms[s] / 1e3) / 1e9,
                           "frac": BYTES_PER_IMAGE[s] * B / (stage_ms[s] / 1e3) / 1e9 / peak} for s in stages}
-        kernels = {"encode": "ssdx_encode_match_kernel + ssdx_encode_emit_kernel", "decode": "ssdx_decode_kernel",
-                   "nms": "ssdx_nms_class_kernel + ssdx_nms_merge_kernel"}
+        kernels = {"encode": "ssdx_encode_fused_kernel", "decode": "ssdx_decode_kernel",
+                   "nms": "ssdx_nms_select_all_kernel + ssdx_nms_fast_all_kernel"}
         line = {
             "metric": "images/sec encode+decode+NMS", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -401,6 +427,7 @@ def gpu_arm(args, rank, world, local_rank):
                        "score_thr": 0.01, "iou_thr": 0.45, "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "no flush: each step streams %.0f MB (> 126 MB L2)" % (
                            sum(BYTES_PER_IMAGE[s] for s in stages) * B / 1e6),
+                       "launch": "eager" if graph is None else "one CUDA graph per step",
                        "oracle_check": check},
             "roofline": {"bound": "hbm", "kernel": kernels[dom], "stage": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -437,6 +464,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="roundtrip_b1024", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -451,7 +479,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload",
-               args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+               args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
+                   ["--no-graph"] if args.no_graph else [])
         raise SystemExit(subprocess.call(cmd))
     gpu_arm(args, rank, world, local_rank)
 
