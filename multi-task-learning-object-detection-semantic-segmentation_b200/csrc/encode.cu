@@ -483,6 +483,23 @@ __device__ __forceinline__ int resolve_match(int a, int g2, int s1max, const u64
   return s1max;
 }
 
+// Seeds of the GT-side bound for the tiled driver: one warp per (image, GT box), grid (ceil(Gmax / warps), B).
+__global__ void __launch_bounds__(kTiledThreads)
+    ssdx_encode_seed_kernel(const float4* __restrict__ m_box, const float* __restrict__ m_area,
+                            const int* __restrict__ m_idx, const float4* __restrict__ t_bbox,
+                            const float2* __restrict__ t_area, const int n_tiles,
+                            const float4* __restrict__ gt_xyxy, const int* __restrict__ gt_count, const int Gmax,
+                            u64* __restrict__ gt_best) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (kTiledThreads / 32) + (threadIdx.x >> 5);
+  int G = gt_count[b];
+  G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
+  if (g >= G) return;
+  const float4 gb = __ldg(gt_xyxy + (size_t)b * Gmax + g);
+  seed_gt_best(m_box, m_area, m_idx, t_bbox, t_area, n_tiles, gb, gt_area(gb), gt_best + (size_t)b * Gmax + g, lane);
+}
+
 // grid (ceil(n_tiles / kTiledTilesPerCta), B).  anchor_g2 is pre-set to -1; only anchors above the threshold write.
 __global__ void __launch_bounds__(kTiledThreads)
     ssdx_encode_match_kernel(const float4* __restrict__ m_box, const float* __restrict__ m_area,
@@ -677,6 +694,11 @@ extern "C" int ssdx_encode(const ssdx_anchors* anchors, const float* gt_xyxy, co
   int* anchor_g2 = (int*)((char*)workspace + best_bytes);
   SSDX_CUDA(cudaMemsetAsync(gt_best, 0, (size_t)batch * gm * sizeof(u64), s));
   SSDX_CUDA(cudaMemsetAsync(anchor_g2, 0xFF, (size_t)batch * A * sizeof(int), s));  // -1: below the threshold
+  dim3 g0((gm + kTiledThreads / 32 - 1) / (kTiledThreads / 32), batch);
+  ssdx_encode_seed_kernel<<<g0, kTiledThreads, 0, s>>>(anchors->m_box, anchors->m_area, anchors->m_idx, anchors->t_bbox,
+                                                       anchors->t_area, anchors->n_tiles, (const float4*)gt_xyxy,
+                                                       gt_count, gm, gt_best);
+  SSDX_LAUNCH_CHECK("ssdx_encode_seed_kernel");
   dim3 g1((anchors->n_tiles + kTiledTilesPerCta - 1) / kTiledTilesPerCta, batch);
   ssdx_encode_match_kernel<<<g1, kTiledThreads, 0, s>>>(anchors->m_box, anchors->m_area, anchors->m_idx,
                                                         anchors->t_bbox, anchors->t_area, anchors->n_tiles,

@@ -1,0 +1,128 @@
+"""GPU box: device-timed numbers for the BASELINE.json configs that are not the bench line (CUDA events, C ABI,
+inputs resident in HBM, 10 back-to-back launches per sample, best and median of 15 samples).
+
+  config 1  decode + per-class NMS, batch 64 (random logits/offsets, thr 0.01, IoU 0.45, top-200)
+  config 3  dense stress encode: 100k anchors x 256 GT boxes per image, batch 256
+  config 4  eval: detections vs GT with per-class TP/FP counting, batch 4096
+
+Prints one JSON line per config (saved under profiles/ by the caller).  Results are checked against the C oracle on
+the first images."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "multi-task-learning-object-detection-semantic-segmentation_b200")
+sys.path.insert(0, ROOT); sys.path.insert(0, PKG)
+import numpy as np, torch
+import ssdseglib
+from ssdseglib import _ssdx as sx
+from oracle import ssd_oracle as orc
+from oracle import c_oracle
+
+c_oracle.build()
+PEAK = 6542.7
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+STD = (0.1, 0.1, 0.2, 0.2)
+std = sx.std_array(STD)
+dev = 0
+sp = torch.cuda.current_stream().cuda_stream
+f32 = dict(dtype=torch.float32, device="cuda:0")
+
+
+def timeit(fn, inner=10, reps=15):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3 / inner)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def emit(name, images, us_med, us_best, bytes_per_image, check, extra=None):
+    line = {"config": name, "images": images, "us_per_launch_median": round(us_med, 1), "us_per_launch_best": round(us_best, 1),
+            "images_per_s": images / (us_med * 1e-6), "algorithmic_GBps": images * bytes_per_image / (us_med * 1e-6) / 1e9,
+            "frac_of_measured_hbm_peak": images * bytes_per_image / (us_med * 1e-6) / 1e9 / PEAK, "oracle_check": check}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ config 1
+def config1():
+    B, A, C, K = 64, 9600, 4, 200
+    anchors = orc.anchors_generate(**orc.STD_ANCHOR_CFG)
+    cent = np.stack(orc.corners_to_centroids(*[anchors[:, i] for i in range(4)]), 1).astype(np.float32)
+    off, scores = orc.synth_predictions(np.random.default_rng(1994), B, A, C)
+    coder = ssdseglib.datacoder.DataEncoderDecoder(C, (480, 640), anchors[:, 0], anchors[:, 1], anchors[:, 2], anchors[:, 3])
+    d_off, d_sc = torch.from_numpy(off).cuda(), torch.from_numpy(scores).cuda()
+    o_boxes, o_det = torch.empty((B, A, 4), **f32), torch.empty((B, K, 6), **f32)
+    ws = torch.empty(max(sx.lib.ssdx_nms_workspace_bytes(B, A, C, K, K), 256), dtype=torch.uint8, device="cuda:0")
+    h = coder._anchors.handle
+
+    def fn():
+        sx.check(sx.lib.ssdx_decode(h, d_off.data_ptr(), B, std, 0, o_boxes.data_ptr(), sp))
+        sx.check(sx.lib.ssdx_nms(o_boxes.data_ptr(), d_sc.data_ptr(), B, A, C, K, K, 0.45, 0.01, o_det.data_ptr(), None,
+                                 None, ws.data_ptr(), ws.numel(), dev, sp))
+    med, best = timeit(fn)
+    ref, _, _ = c_oracle.combined_nms(o_boxes[:2].cpu().numpy(), scores[:2], K, K, 0.45, 0.01)
+    ok = np.array_equal(ref, o_det[:2].cpu().numpy())
+    emit("1: decode + NMS, batch 64", B, med, best, 32 * A + 16 * A + 4 * A * C + 24 * K, "pass" if ok else "FAIL")
+
+
+# ------------------------------------------------------------------------------------------------ config 3
+def config3():
+    B, G, C = 256, 256, 4
+    anchors = orc.anchors_generate(**orc.STRESS_ANCHOR_CFG)
+    A = anchors.shape[0]
+    labels, boxes, counts = orc.synth_gt(np.random.default_rng(1996), B, G, image_hw=(1000, 1280))
+    coder = ssdseglib.datacoder.DataEncoderDecoder(C, (1000, 1280), anchors[:, 0], anchors[:, 1], anchors[:, 2], anchors[:, 3])
+    gb, gl, gc = torch.from_numpy(boxes).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(counts).cuda()
+    o_l, o_o = torch.empty((B, A, C), **f32), torch.empty((B, A, 4), **f32)
+    ws = torch.empty(max(sx.lib.ssdx_encode_workspace_bytes(A, B, G), 256), dtype=torch.uint8, device="cuda:0")
+    h = coder._anchors.handle
+
+    def fn():
+        sx.check(sx.lib.ssdx_encode(h, gb.data_ptr(), gl.data_ptr(), gc.data_ptr(), B, G, C, 0.5, std, o_l.data_ptr(),
+                                    o_o.data_ptr(), None, ws.data_ptr(), ws.numel(), sp))
+    med, best = timeit(fn, inner=3, reps=8)
+    rl, ro, _ = c_oracle.encode_batch(anchors, labels[:2], boxes[:2], counts[:2], C, 0.5, STD)
+    ok = np.array_equal(rl, o_l[:2].cpu().numpy()) and np.allclose(ro, o_o[:2].cpu().numpy(), rtol=1e-5, atol=1e-6)
+    emit("3: dense stress encode, 100k anchors x 256 GT, batch 256", B, med, best, 20 * G + 4 * A * (C + 4),
+         "pass" if ok else "FAIL", {"pairs_per_s": B * A * G / (med * 1e-6)})
+
+
+# ------------------------------------------------------------------------------------------------ config 4
+def config4():
+    B, K, G, C = 4096, 200, 16, 4
+    rng = np.random.default_rng(1997)
+    labels, boxes, counts = orc.synth_gt(rng, B, G)
+    # detections: GT boxes jittered + random boxes, labels 0..3 (0 = background rows)
+    pl = rng.integers(0, C, size=(B, K)).astype(np.int32)
+    src = rng.integers(0, G, size=(B, K))
+    pb = np.take_along_axis(boxes, src[..., None].repeat(4, -1), axis=1) + rng.normal(0, 8, size=(B, K, 4)).astype(np.float32)
+    pb = pb.astype(np.float32)
+    d = [torch.from_numpy(x).cuda() for x in (pl, pb, boxes, labels, counts)]
+    tp = torch.empty((B, K), dtype=torch.uint8, device="cuda:0")
+    cnt = torch.zeros((C, 3), dtype=torch.int64, device="cuda:0")
+
+    def fn():
+        sx.check(sx.lib.ssdx_eval_tp(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(),
+                                     B, K, G, C, 0, 0.5, tp.data_ptr(), cnt.data_ptr(), dev, sp))
+    med, best = timeit(fn)
+    ref = np.stack([orc.eval_tp_flags(pl[i], pb[i], labels[i], boxes[i], 0.5, 0) for i in range(4)])
+    ok = np.array_equal(ref, tp[:4].cpu().numpy())
+    emit("4: eval TP/FP + per-class counts, batch 4096", B, med, best, 24 * K + 20 * G + K, "pass" if ok else "FAIL")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["1", "3", "4"]
+    for w in which:
+        {"1": config1, "3": config3, "4": config4}[w]()
