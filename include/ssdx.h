@@ -123,6 +123,17 @@ SSDX_API int ssdx_iou_pred_vs_true(const int32_t* pred_label, const float* pred_
 SSDX_API int ssdx_parse_gt_csv(const char* text, size_t text_len, int crlf_only, float flip_width, int32_t* labels_host,
                       float* boxes_xyxy_host, int32_t capacity, int32_t* count);
 
+/* Batched form of the ingest (host, `threads` worker threads; <= 0 = all hardware threads): one file per image
+ * (datacoder.py:194 tf.io.read_file per element of the tf.data pipeline; evaluators.py:109-121 open() per image).
+ * paths (n_files) host C strings; flip (n_files) host bytes or NULL: files with a non-zero byte get the horizontal
+ * flip with flip_width (datacoder.py:337-343 draws one coin per image).  Outputs are host arrays, padded with
+ * zeros: labels (n_files, gmax) i32, boxes (n_files, gmax, 4) f32, counts (n_files) i32.  If a file holds more than
+ * gmax records the call returns SSDX_ERR_WORKSPACE with counts holding the true numbers (retry with a larger gmax;
+ * gmax = 0 with NULL arrays only counts). */
+SSDX_API int ssdx_read_gt_csv_batch(const char* const* paths, int32_t n_files, int crlf_only, const uint8_t* flip,
+                                    float flip_width, int32_t gmax, int32_t* labels_host, float* boxes_xyxy_host,
+                                    int32_t* counts_host, int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

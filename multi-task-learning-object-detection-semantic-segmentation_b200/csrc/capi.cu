@@ -6,6 +6,9 @@
 #include <math.h>
 
 #include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -279,6 +282,91 @@ int ssdx_parse_gt_csv(const char* text, size_t text_len, int crlf_only, float fl
   *count = n;
   if (n > capacity) {
     ssdx_set_error("ssdx_parse_gt_csv: %d records but capacity is %d", n, capacity);
+    return SSDX_ERR_WORKSPACE;
+  }
+  return SSDX_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Batched GT ingest (host, multithreaded): the step right before encode / eval.
+// One file per image (datacoder.py:194 tf.io.read_file, evaluators.py:111 open()), parsed by
+// ssdx_parse_gt_csv into padded arrays labels (N, gmax), boxes (N, gmax, 4), counts (N).
+// ---------------------------------------------------------------------------------------------
+int ssdx_read_gt_csv_batch(const char* const* paths, int32_t n_files, int crlf_only, const uint8_t* flip,
+                           float flip_width, int32_t gmax, int32_t* labels_host, float* boxes_xyxy_host,
+                           int32_t* counts_host, int32_t threads) {
+  SSDX_CHECK_ARG(n_files >= 0 && gmax >= 0, "ssdx_read_gt_csv_batch: n_files and gmax must be >= 0");
+  SSDX_CHECK_ARG(n_files == 0 || (paths != nullptr && counts_host != nullptr),
+                 "ssdx_read_gt_csv_batch: paths / counts_host is NULL");
+  SSDX_CHECK_ARG(gmax == 0 || (labels_host != nullptr && boxes_xyxy_host != nullptr),
+                 "ssdx_read_gt_csv_batch: output arrays missing");
+  if (n_files == 0) return SSDX_OK;
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, (int)n_files));
+  std::atomic<int32_t> next(0);
+  std::atomic<int> first_error(0);  // 0 none, else status of the first failure
+  std::string error_text;
+  std::atomic_flag error_lock = ATOMIC_FLAG_INIT;
+  std::atomic<int> overflow(0);
+  auto work = [&]() {
+    std::vector<char> buf;
+    for (;;) {
+      const int32_t i = next.fetch_add(1);
+      if (i >= n_files || first_error.load() != 0) return;
+      int32_t* lab = gmax ? labels_host + (size_t)i * gmax : nullptr;
+      float* box = gmax ? boxes_xyxy_host + (size_t)i * gmax * 4 : nullptr;
+      if (gmax) {
+        memset(lab, 0, (size_t)gmax * sizeof(int32_t));
+        memset(box, 0, (size_t)gmax * 4 * sizeof(float));
+      }
+      counts_host[i] = 0;
+      int st = SSDX_OK;
+      std::string msg;
+      FILE* f = paths[i] ? fopen(paths[i], "rb") : nullptr;
+      if (f == nullptr) {
+        st = SSDX_ERR_INVALID;
+        msg = std::string("ssdx_read_gt_csv_batch: cannot open '") + (paths[i] ? paths[i] : "(null)") + "'";
+      } else {
+        fseek(f, 0, SEEK_END);
+        const long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        buf.resize(sz > 0 ? (size_t)sz : 0);
+        const size_t got = sz > 0 ? fread(buf.data(), 1, (size_t)sz, f) : 0;
+        fclose(f);
+        int32_t n = 0;
+        st = ssdx_parse_gt_csv(buf.data(), got, crlf_only, (flip && flip[i]) ? flip_width : 0.0f, lab, box, gmax, &n);
+        counts_host[i] = n;
+        if (st == SSDX_ERR_WORKSPACE) {  // more records than gmax: counts hold the true number, caller retries
+          overflow.store(1);
+          st = SSDX_OK;
+        } else if (st != SSDX_OK) {
+          msg = std::string(ssdx_last_error()) + " (file '" + paths[i] + "')";
+        }
+      }
+      if (st != SSDX_OK) {
+        while (error_lock.test_and_set()) {}
+        if (first_error.load() == 0) {
+          error_text = msg;
+          first_error.store(st);
+        }
+        error_lock.clear();
+        return;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  if (first_error.load() != 0) {
+    ssdx_set_error("%s", error_text.c_str());
+    return first_error.load();
+  }
+  if (overflow.load()) {
+    int32_t need = 0;
+    for (int32_t i = 0; i < n_files; ++i) need = std::max(need, counts_host[i]);
+    ssdx_set_error("ssdx_read_gt_csv_batch: a file holds %d records but gmax is %d", need, gmax);
     return SSDX_ERR_WORKSPACE;
   }
   return SSDX_OK;

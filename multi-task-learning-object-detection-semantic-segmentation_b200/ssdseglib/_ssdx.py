@@ -49,6 +49,8 @@ SIGNATURES = {
     "ssdx_iou_pred_vs_true": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
     "ssdx_parse_gt_csv": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_float, c_i32_p, c_float_p, C.c_int32,
                                     c_i32_p]),
+    "ssdx_read_gt_csv_batch": (C.c_int, [C.POINTER(C.c_char_p), C.c_int32, C.c_int, C.POINTER(C.c_uint8), C.c_float,
+                                         C.c_int32, c_i32_p, c_float_p, c_i32_p, C.c_int32]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)
@@ -305,3 +307,32 @@ def parse_gt_csv(text: bytes, crlf_only: bool, flip_width: float = 0.0, capacity
                                labels.ctypes.data_as(c_i32_p), boxes.ctypes.data_as(c_float_p), cap, C.byref(n))
     check(st)
     return labels[: n.value].copy(), boxes[: n.value].copy()
+
+
+def read_gt_csv_batch(paths, crlf_only: bool, flips=None, flip_width: float = 0.0, gmax: int = 32, threads: int = 0):
+    """Multithreaded host-side ingest of one CSV file per image (C++ worker threads, the GIL is released).
+    Returns padded (labels (N, G) int32, boxes (N, G, 4) float32, counts (N,) int32) with G = max(count, 1);
+    retried once with the exact size if a file holds more than `gmax` records."""
+    n = len(paths)
+    enc = [p if isinstance(p, bytes) else str(p).encode() for p in paths]
+    arr = (C.c_char_p * max(n, 1))(*enc)
+    flip_arr = None
+    if flips is not None:
+        fl = np.ascontiguousarray(np.asarray(flips).astype(np.uint8))
+        if fl.shape != (n,):
+            raise ValueError("flips must have one entry per path")
+        flip_arr = fl.ctypes.data_as(C.POINTER(C.c_uint8))
+    counts = np.zeros(max(n, 1), np.int32)
+    g = max(int(gmax), 1)
+    for _ in range(2):
+        labels = np.empty((max(n, 1), g), np.int32)
+        boxes = np.empty((max(n, 1), g, 4), np.float32)
+        st = lib.ssdx_read_gt_csv_batch(arr, n, 1 if crlf_only else 0, flip_arr, float(flip_width), g,
+                                        labels.ctypes.data_as(c_i32_p), boxes.ctypes.data_as(c_float_p),
+                                        counts.ctypes.data_as(c_i32_p), int(threads))
+        if st != SSDX_ERR_WORKSPACE:
+            break
+        g = int(counts[:n].max())
+    check(st)
+    gfit = max(int(counts[:n].max()) if n else 0, 1)
+    return labels[:n, :gfit].copy(), boxes[:n, :gfit].copy(), counts[:n].copy()

@@ -105,6 +105,14 @@ class DataEncoderDecoder:
         return _ssdx.parse_gt_csv(text, crlf_only=True,
                                   flip_width=float(self.image_width) if augment_with_horizontal_flip else 0.0)
 
+    def read_labels_boxes_batch(self, path_files_labels_boxes, augment_with_horizontal_flip=None, threads: int = 0):
+        """Batched GT ingest (new entry point next to `read_labels_boxes`): one file per image, read and parsed by C++
+        worker threads.  `augment_with_horizontal_flip`: None, or one bool per file (the coin of datacoder.py:337).
+        Returns padded (labels (N, G) int32, boxes (N, G, 4) float32, counts (N,) int32) ready for `encode_batch`."""
+        return _ssdx.read_gt_csv_batch(list(path_files_labels_boxes), crlf_only=True,
+                                       flips=augment_with_horizontal_flip, flip_width=float(self.image_width),
+                                       threads=threads)
+
     def encode_batch(self, gt_boxes, gt_labels, gt_counts=None, return_match: bool = False):
         """Batched encode (new entry point).
 

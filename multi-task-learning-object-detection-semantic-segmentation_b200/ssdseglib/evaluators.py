@@ -30,23 +30,11 @@ def _iou_boxes_pred_vs_true(labels_pred, boxes_pred, labels_true, boxes_true) ->
     return _ssdx.from_device(_ssdx.iou_pred_vs_true(lp, bp, lt, bt), "numpy")
 
 
-def read_ground_truth(path_files_labels_boxes: Sequence[str]):
+def read_ground_truth(path_files_labels_boxes: Sequence[str], threads: int = 0):
     """Read the `label,xmin,ymin,xmax,ymax` CSV files of a dataset (evaluators.py:109-125) into padded
-    arrays: labels (N, Gmax) int32, boxes (N, Gmax, 4) float32, counts (N,) int32."""
-    per_file = []
-    for path in path_files_labels_boxes:
-        with open(path, "rb") as f:
-            per_file.append(_ssdx.parse_gt_csv(f.read(), crlf_only=False))
-    gmax = max([1] + [l.shape[0] for l, _ in per_file])
-    n = len(per_file)
-    labels = np.zeros((n, gmax), np.int32)
-    boxes = np.zeros((n, gmax, 4), np.float32)
-    counts = np.zeros(n, np.int32)
-    for i, (l, b) in enumerate(per_file):
-        counts[i] = l.shape[0]
-        labels[i, : l.shape[0]] = l
-        boxes[i, : l.shape[0]] = b
-    return labels, boxes, counts
+    arrays: labels (N, Gmax) int32, boxes (N, Gmax, 4) float32, counts (N,) int32.  The files are read and parsed
+    by C++ worker threads (`ssdx_read_gt_csv_batch`); any newline convention is accepted, as csv.reader does."""
+    return _ssdx.read_gt_csv_batch(list(path_files_labels_boxes), crlf_only=False, threads=threads)
 
 
 def true_positives_and_counts(labels_pred_batch, boxes_pred_batch, gt_labels, gt_boxes, gt_counts,

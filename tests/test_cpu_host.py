@@ -136,6 +136,45 @@ def test_csv_parser_matches_oracle(ssdseglib):
         p("1,1,2,3,4\n2,5,6,7,8\n", True)  # datacoder.py:195 splits on CRLF only -> one malformed record
 
 
+def test_batch_csv_reader_matches_per_file_parser(ssdseglib, tmp_path):
+    """ssdx_read_gt_csv_batch (C++ worker threads) against the oracle's parser, file by file: ragged counts, an empty
+    file, both newline conventions, per-file flips, capacity retry, and the error path."""
+    rng = np.random.default_rng(5)
+    paths, texts, flips = [], [], []
+    for i in range(37):
+        n = int(rng.integers(0, 9)) if i != 11 else 41          # one file larger than the default capacity
+        labels = rng.integers(0, 4, n)
+        boxes = rng.uniform(0, 600, (n, 4)).astype(np.float32)
+        rows = [f"{int(l)},{float(b[0])!r},{float(b[1])!r},{float(b[2])!r},{float(b[3])!r}" for l, b in zip(labels, boxes)]
+        text = "\r\n".join(rows) + ("\r\n" if n and i % 2 else "")
+        p = tmp_path / f"gt_{i}.csv"
+        p.write_bytes(text.encode())
+        paths.append(str(p)); texts.append(text); flips.append(bool(i % 3 == 0))
+    sx = ssdseglib._ssdx
+    for threads in (1, 4, 0):
+        L, Bx, Cn = sx.read_gt_csv_batch(paths, crlf_only=True, flips=flips, flip_width=640.0, gmax=8, threads=threads)
+        assert L.dtype == np.int32 and Bx.dtype == np.float32 and Cn.dtype == np.int32
+        assert L.shape == (37, 41) and Bx.shape == (37, 41, 4)
+        for i, text in enumerate(texts):
+            rl, rb = orc.parse_gt_csv_text(text) if text.strip() else (np.zeros(0, np.int32), np.zeros((0, 4), np.float32))
+            if flips[i]:
+                rb = orc.flip_boxes_horizontal(rb, 640) if len(rb) else rb
+            assert Cn[i] == len(rl)
+            assert np.array_equal(L[i, :Cn[i]], rl) and np.array_equal(Bx[i, :Cn[i]], rb)
+            assert not L[i, Cn[i]:].any() and not Bx[i, Cn[i]:].any()          # zero padding
+    # the evaluator front-end (csv.reader conventions: "\n" or "\r\n") and the datacoder front-end agree on these files
+    L2, B2, C2 = ssdseglib.evaluators.read_ground_truth(paths)
+    L3, B3, C3 = sx.read_gt_csv_batch(paths, crlf_only=True)
+    assert np.array_equal(C2, C3) and np.array_equal(L2, L3) and np.array_equal(B2, B3)
+    with pytest.raises(ValueError, match="cannot open"):
+        sx.read_gt_csv_batch(paths + [str(tmp_path / "missing.csv")], crlf_only=True)
+    bad = tmp_path / "bad.csv"
+    bad.write_bytes(b"1,2,3\r\n")
+    with pytest.raises(ValueError, match="bad.csv"):
+        sx.read_gt_csv_batch([str(bad)], crlf_only=True)
+    assert sx.read_gt_csv_batch([], crlf_only=True)[2].shape == (0,)
+
+
 def test_datacoder_validation_before_device(ssdseglib):
     D = ssdseglib.datacoder.DataEncoderDecoder
     a = np.zeros(4, np.float32)
