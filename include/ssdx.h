@@ -101,6 +101,27 @@ SSDX_API int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t batc
              int32_t* out_valid, int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
              ssdx_stream stream);
 
+/* Same, with every score multiplied by class_scale[c] (device, C floats; NULL = 1) as it is read: the product
+ * layers.SegmentationSuppression feeds to the NMS layer (layers.py:209, models.py:402-414) without materialising the
+ * suppressed (B,A,C) tensor.  One IEEE multiply per score, so results equal NMS over the multiplied tensor. */
+SSDX_API int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, const float* class_scale, int32_t batch,
+                             int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
+                             float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
+                             int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
+                             ssdx_stream stream);
+
+/* ---- segmentation suppression: layers.py:189-212 (SegmentationSuppression.call), SURVEY 8(f) row 2 ----
+ * seg_probs (num_pixels, Cm) f32 = the (B,H,W,Cm) segmentation output flattened over batch and space.
+ * out_presence (depth) f32: 1.0f iff some pixel of the WHOLE batch has argmax == c (ties -> lowest index), else 0.0f
+ * (argmax -> one_hot(depth) -> reduce_sum over (0,1,2) -> clip to [0,1]; the reference hard-codes depth = 4).
+ * workspace: 256 bytes, 256-byte aligned. */
+SSDX_API int ssdx_seg_class_presence(const float* seg_probs, int64_t num_pixels, int32_t cm, int32_t depth,
+                                     float* out_presence, void* workspace, size_t workspace_bytes, int device,
+                                     ssdx_stream stream);
+/* out[r][c] = scores[r][c] * class_scale[c] (layers.py:209 tf.math.multiply with broadcasting); rows = B*A. */
+SSDX_API int ssdx_scale_scores(const float* scores, int64_t rows, int32_t num_classes, const float* class_scale,
+                               float* out, int device, ssdx_stream stream);
+
 /* ---- detection eval: evaluators.py:6-63 (_iou_boxes_pred_vs_true) + :106-157 (TP flags, GT counts) ----
  * pred_label (B,K) i32, pred_xyxy (B,K,4) f32; gt_* as in encode; labels are class indices in [0,C)
  * out_tp (B,K) u8: 1 iff label != background and max_g IoU*[label match] >= iou_threshold (fp32 compare)

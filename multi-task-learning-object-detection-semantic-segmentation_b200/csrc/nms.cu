@@ -89,6 +89,19 @@ __device__ __forceinline__ u64 make_comp_all(unsigned key, int cls, int idx) {
 __device__ __forceinline__ int comp_all_cls(u64 c) { return (int)(0xFFu - (unsigned)((c >> 24) & 0xFFull)); }
 __device__ __forceinline__ int comp_all_idx(u64 c) { return (int)(0xFFFFFFu - (unsigned)(c & 0xFFFFFFull)); }
 
+// Optional per-class factor applied to every score as it is read (layers.SegmentationSuppression, layers.py:209:
+// probabilities * is_class_segmented): one IEEE multiply, so the products equal the reference's; x * 1.0f == x.
+__device__ __forceinline__ float class_factor(const float* __restrict__ cscale, int c) {
+  return cscale ? __ldg(cscale + c) : 1.0f;
+}
+__device__ __forceinline__ float4 class_factor4(const float* __restrict__ cscale) {
+  return cscale ? make_float4(__ldg(cscale), __ldg(cscale + 1), __ldg(cscale + 2), __ldg(cscale + 3))
+                : make_float4(1.f, 1.f, 1.f, 1.f);
+}
+__device__ __forceinline__ float4 mul4(const float4 a, const float4 b) {
+  return make_float4(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), __fmul_rn(a.w, b.w));
+}
+
 // box normalised as TF does: (y0, x0, y1, x1) with y0<=y1, x0<=x1
 __device__ __forceinline__ float4 normalise_box(const float4 b) {
   return make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
@@ -242,8 +255,9 @@ __device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n,
 // ------------------------------------------------------------------------------------------ 1. select
 template <bool VEC4>
 __global__ void __launch_bounds__(kSelThreads)
-    ssdx_nms_select_kernel(const float* __restrict__ scores, const int A, const int C, const float score_thr,
-                           u64* __restrict__ lists, int* __restrict__ info, int* __restrict__ flags) {
+    ssdx_nms_select_kernel(const float* __restrict__ scores, const float* __restrict__ cscale, const int A,
+                           const int C, const float score_thr, u64* __restrict__ lists, int* __restrict__ info,
+                           int* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * kSelGroup;
@@ -266,14 +280,14 @@ __global__ void __launch_bounds__(kSelThreads)
     int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
     a = a < A ? a : A - 1;
     if (VEC4) {
-      const float4 s = __ldg(reinterpret_cast<const float4*>(img) + a);
+      const float4 s = mul4(__ldg(reinterpret_cast<const float4*>(img) + a), class_factor4(cscale));
       skeys[0 * NS + k] = (s.x > score_thr) ? score_to_key(s.x) : 0u;
       skeys[1 * NS + k] = (s.y > score_thr) ? score_to_key(s.y) : 0u;
       skeys[2 * NS + k] = (s.z > score_thr) ? score_to_key(s.z) : 0u;
       skeys[3 * NS + k] = (s.w > score_thr) ? score_to_key(s.w) : 0u;
     } else {
       for (int c = 0; c < cg; ++c) {
-        const float s = __ldg(img + (size_t)a * C + c0 + c);
+        const float s = __fmul_rn(__ldg(img + (size_t)a * C + c0 + c), class_factor(cscale, c0 + c));
         skeys[c * NS + k] = (s > score_thr) ? score_to_key(s) : 0u;
       }
     }
@@ -321,13 +335,15 @@ __global__ void __launch_bounds__(kSelThreads)
 #pragma unroll
     for (int c = 0; c < 4; ++c) tt[c] = (tk[c] <= 1u) ? -INFINITY : key_to_score(tk[c]);
     int n_cand[4] = {0, 0, 0, 0};
+    const float4 cf4 = class_factor4(cscale);
     constexpr int kBatch = 4;  // independent 128-bit streaming loads in flight per thread
     for (int a0 = tid; a0 < A; a0 += kSelThreads * kBatch) {
       float4 sb[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int a = a0 + u * kSelThreads;
-        sb[u] = (a < A) ? __ldcs(reinterpret_cast<const float4*>(img) + a) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        sb[u] = (a < A) ? mul4(__ldcs(reinterpret_cast<const float4*>(img) + a), cf4)
+                        : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
@@ -353,9 +369,10 @@ __global__ void __launch_bounds__(kSelThreads)
   } else {
     for (int c = 0; c < cg; ++c) {
       const float t = (tk[c] <= 1u) ? -INFINITY : key_to_score(tk[c]);
+      const float cf = class_factor(cscale, c0 + c);
       int n_cand = 0;
       for (int a = tid; a < A; a += kSelThreads) {
-        const float s = __ldg(img + (size_t)a * C + c0 + c);
+        const float s = __fmul_rn(__ldg(img + (size_t)a * C + c0 + c), cf);
         if (s > score_thr) {
           ++n_cand;
           if (s >= t) {
@@ -381,7 +398,7 @@ __global__ void __launch_bounds__(kSelThreads)
 // ------------------------------------------------------------------------------------------ 2. fast path
 __global__ void __launch_bounds__(kFastThreads, 6)
     ssdx_nms_fast_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
-                         const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
+                         const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                          const int limit, const float iou_thr, const float score_thr, u64* __restrict__ picks,
                          int* __restrict__ pick_cnt, int* __restrict__ flags) {
   __shared__ u64 s_list[kCap];
@@ -406,6 +423,7 @@ __global__ void __launch_bounds__(kFastThreads, 6)
   }
   const float4* img_boxes = boxes + (size_t)b * A;
   const float* img_scores = scores + (size_t)b * A * C + c;
+  const float cf = class_factor(cscale, c);
   u64* my_picks = picks + seg * limit;
   const u64* lst = lists + seg * kCap;
   PHASE_T0();
@@ -570,7 +588,7 @@ __global__ void __launch_bounds__(kFastThreads, 6)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int a = a0 + u * kFastThreads;
-          sv[u] = (a < A) ? __ldg(img_scores + (size_t)a * C) : -INFINITY;
+          sv[u] = (a < A) ? __fmul_rn(__ldg(img_scores + (size_t)a * C), cf) : -INFINITY;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -619,9 +637,9 @@ __global__ void __launch_bounds__(kFastThreads, 6)
 // info per image: [0] listed candidates (may exceed kCap), [1] threshold key (every candidate with key >= it is listed)
 template <bool VEC4>
 __global__ void __launch_bounds__(kSelThreads)
-    ssdx_nms_select_all_kernel(const float* __restrict__ scores, const int A, const int C, const float score_thr,
-                               u64* __restrict__ lists, int* __restrict__ info, int* __restrict__ flags,
-                               int* __restrict__ iflags) {
+    ssdx_nms_select_all_kernel(const float* __restrict__ scores, const float* __restrict__ cscale, const int A,
+                               const int C, const float score_thr, u64* __restrict__ lists, int* __restrict__ info,
+                               int* __restrict__ flags, int* __restrict__ iflags) {
   __shared__ unsigned s_max[kSelThreads];  // per-thread maximum of the sampled keys
   __shared__ unsigned s_T;
   __shared__ int s_cnt;
@@ -642,12 +660,12 @@ __global__ void __launch_bounds__(kSelThreads)
       int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
       a = a < A ? a : A - 1;
       if (VEC4) {
-        const float4 s = __ldg(reinterpret_cast<const float4*>(img) + a);
+        const float4 s = mul4(__ldg(reinterpret_cast<const float4*>(img) + a), class_factor4(cscale));
         const float m = fmaxf(fmaxf(s.x, s.y), fmaxf(s.z, s.w));
         if (m > score_thr) kmax = max(kmax, score_to_key(m));
       } else {
         for (int c = 0; c < C; ++c) {
-          const float s = __ldg(img + (size_t)a * C + c);
+          const float s = __fmul_rn(__ldg(img + (size_t)a * C + c), class_factor(cscale, c));
           if (s > score_thr) kmax = max(kmax, score_to_key(s));
         }
       }
@@ -704,12 +722,13 @@ __global__ void __launch_bounds__(kSelThreads)
   u64* lst = lists + (size_t)b * kCap;
   if (VEC4) {
     constexpr int kBatch = 8;  // independent 128-bit streaming loads in flight per thread
+    const float4 cf4 = class_factor4(cscale);
     for (int a0 = tid; a0 < A; a0 += kSelThreads * kBatch) {
       float4 sb[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int a = a0 + u * kSelThreads;
-        sb[u] = (a < A) ? __ldcs(reinterpret_cast<const float4*>(img) + a)
+        sb[u] = (a < A) ? mul4(__ldcs(reinterpret_cast<const float4*>(img) + a), cf4)
                         : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
       unsigned hits = 0u;  // bit 4*u + c
@@ -724,7 +743,7 @@ __global__ void __launch_bounds__(kSelThreads)
         const int bit = __ffs(hits) - 1;
         hits &= hits - 1u;
         const int a = a0 + (bit >> 2) * kSelThreads, c = bit & 3;
-        const float s = __ldg(img + (size_t)a * 4 + c);
+        const float s = __fmul_rn(__ldg(img + (size_t)a * 4 + c), class_factor(cscale, c));
         const int pos = atomicAdd(&s_cnt, 1);
         if (pos < kCap) lst[pos] = make_comp_all(score_to_key(s), c, a);
       }
@@ -732,7 +751,7 @@ __global__ void __launch_bounds__(kSelThreads)
   } else {
     const int total = A * C;  // flat coalesced walk
     for (int e = tid; e < total; e += kSelThreads) {
-      const float s = __ldcs(img + e);
+      const float s = cscale ? __fmul_rn(__ldcs(img + e), __ldg(cscale + e % C)) : __ldcs(img + e);
       if (s >= t_lo) {
         const int a = e / C;
         const int pos = atomicAdd(&s_cnt, 1);
@@ -751,7 +770,7 @@ __global__ void __launch_bounds__(kSelThreads)
 template <int MAXSEL, int MINB>  // MAXSEL >= K; MINB resident CTAs per SM (7 * 148 >= 1024: one wave at batch 1024)
 __global__ void __launch_bounds__(kFastThreads, MINB)
     ssdx_nms_fast_all_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
-                             const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
+                             const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                              const int K, const float iou_thr, const float score_thr, float* __restrict__ out,
                              int* __restrict__ out_valid, int* __restrict__ out_idx, int* __restrict__ flags,
                              int* __restrict__ iflags) {
@@ -943,7 +962,8 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int e = e0 + u * kFastThreads;
-          sv[u] = (e < total) ? __ldg(img_scores + e) : -INFINITY;
+          sv[u] = (e < total) ? (cscale ? __fmul_rn(__ldg(img_scores + e), __ldg(cscale + e % C)) : __ldg(img_scores + e))
+                              : -INFINITY;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -1033,8 +1053,8 @@ __host__ __device__ inline size_t gen_smem_bytes(int A, int limit) {
 }
 
 __global__ void __launch_bounds__(kGenThreads)
-    ssdx_nms_generic_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const int A,
-                            const int C, const int limit, const float iou_thr, const float score_thr,
+    ssdx_nms_generic_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                            const float* __restrict__ cscale, const int A, const int C, const int limit, const float iou_thr, const float score_thr,
                             u64* __restrict__ picks, int* __restrict__ pick_cnt, const int* __restrict__ flags,
                             const int num_segments) {
   // persistent CTAs over the worklist of segments the fast path handed over (flags[0] = count, then ids);
@@ -1062,6 +1082,7 @@ __global__ void __launch_bounds__(kGenThreads)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* img_boxes = boxes + (size_t)b * A;
   const float* img_scores = scores + (size_t)b * A * C + c;
+  const float cf = class_factor(cscale, c);
   u64* my_picks = picks + ((size_t)b * C + c) * limit;
 
   if (tid < 8) sm.ctr[tid] = (tid == 6) ? -1 : 0;  // ctr[6] = min key (unsigned), ctr[7] = max key
@@ -1072,7 +1093,7 @@ __global__ void __launch_bounds__(kGenThreads)
     int n = 0;
     unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
     for (int i = tid; i < A; i += kGenThreads) {
-      const float s = __ldg(img_scores + (size_t)i * C);
+      const float s = __fmul_rn(__ldg(img_scores + (size_t)i * C), cf);
       unsigned k = 0u;
       if (s > score_thr) {
         k = score_to_key(s);
@@ -1333,6 +1354,17 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
                         int32_t num_classes, int32_t max_per_class, int32_t max_total, float iou_threshold,
                         float score_threshold, float* out, int32_t* out_valid, int32_t* out_anchor_idx,
                         void* workspace, size_t workspace_bytes, int device, ssdx_stream stream) {
+  return ssdx_nms_scaled(boxes_yxyx, scores, nullptr, batch, num_anchors, num_classes, max_per_class, max_total,
+                         iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes,
+                         device, stream);
+}
+
+extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, const float* class_scale, int32_t batch,
+                               int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
+                               float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
+                               int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
+                               ssdx_stream stream) {
+  const float* cscale = class_scale;
   SSDX_CHECK_ARG(boxes_yxyx != nullptr && scores != nullptr && out != nullptr, "ssdx_nms: NULL pointer argument");
   SSDX_CHECK_ARG(batch >= 0 && num_anchors > 0 && num_classes > 0, "ssdx_nms: bad shape (B=%d, A=%d, C=%d)", batch,
                  num_anchors, num_classes);
@@ -1387,25 +1419,25 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
                       A <= (1 << 24) && max_total <= kFastMaxSel;
   if (merged) {
     if (vec4)
-      ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, A, C, score_threshold, lists, info, flags,
+      ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, lists, info, flags,
                                                                      iflags);
     else
-      ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, A, C, score_threshold, lists, info,
+      ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, lists, info,
                                                                       flags, iflags);
     SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
     if (max_total <= 256)
       ssdx_nms_fast_all_kernel<256, SSDX_FAST_MINB><<<batch, kFastThreads, 0, s>>>(
-          bx, scores, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx,
-          flags, iflags);
+          bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid,
+          out_anchor_idx, flags, iflags);
     else
       ssdx_nms_fast_all_kernel<kFastMaxSel, 6><<<batch, kFastThreads, 0, s>>>(
-          bx, scores, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx,
-          flags, iflags);
+          bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid,
+          out_anchor_idx, flags, iflags);
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_all_kernel");
     // handed-over images only (both kernels return at once when the worklists are empty)
     const int sms = ssdx_sm_count(device);
     ssdx_nms_generic_kernel<<<min(num_segments, 2 * sms), kGenThreads, gen_smem, s>>>(
-        bx, scores, A, C, limit, iou_threshold, score_threshold, picks, pick_cnt, flags, num_segments);
+        bx, scores, cscale, A, C, limit, iou_threshold, score_threshold, picks, pick_cnt, flags, num_segments);
     SSDX_LAUNCH_CHECK("ssdx_nms_generic_kernel");
     ssdx_nms_merge_kernel<<<min(batch, 2 * sms), kMergeThreads, stage ? merge_smem : 0, s>>>(
         bx, picks, pick_cnt, A, C, limit, max_total, stage, out, out_valid, out_anchor_idx, iflags, batch);
@@ -1422,22 +1454,22 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
     if (vec4) {
       SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sel_smem));
-      ssdx_nms_select_kernel<true><<<gsel, kSelThreads, sel_smem, s>>>(scores, A, C, score_threshold, lists, info, flags);
+      ssdx_nms_select_kernel<true><<<gsel, kSelThreads, sel_smem, s>>>(scores, cscale, A, C, score_threshold, lists, info, flags);
     } else {
       SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sel_smem));
-      ssdx_nms_select_kernel<false><<<gsel, kSelThreads, sel_smem, s>>>(scores, A, C, score_threshold, lists, info, flags);
+      ssdx_nms_select_kernel<false><<<gsel, kSelThreads, sel_smem, s>>>(scores, cscale, A, C, score_threshold, lists, info, flags);
     }
     SSDX_LAUNCH_CHECK("ssdx_nms_select_kernel");
     // 2. fast path
     dim3 gseg(C, batch);
-    ssdx_nms_fast_kernel<<<gseg, kFastThreads, 0, s>>>(bx, scores, lists, info, A, C, limit, iou_threshold,
+    ssdx_nms_fast_kernel<<<gseg, kFastThreads, 0, s>>>(bx, scores, cscale, lists, info, A, C, limit, iou_threshold,
                                                        score_threshold, picks, pick_cnt, flags);
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_kernel");
   }
   // 3. generic path (flag-gated; handles every segment when the fast path is not applicable)
   const int gen_grid = use_fast ? min(num_segments, 2 * ssdx_sm_count(device)) : num_segments;
-  ssdx_nms_generic_kernel<<<gen_grid, kGenThreads, gen_smem, s>>>(bx, scores, A, C, limit, iou_threshold,
+  ssdx_nms_generic_kernel<<<gen_grid, kGenThreads, gen_smem, s>>>(bx, scores, cscale, A, C, limit, iou_threshold,
                                                                   score_threshold, picks, pick_cnt,
                                                                   use_fast ? flags : nullptr, num_segments);
   SSDX_LAUNCH_CHECK("ssdx_nms_generic_kernel");

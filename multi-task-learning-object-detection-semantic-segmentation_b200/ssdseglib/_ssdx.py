@@ -44,6 +44,10 @@ SIGNATURES = {
     "ssdx_nms_workspace_bytes": (C.c_size_t, [C.c_int32] * 5),
     "ssdx_nms": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
                            _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "ssdx_nms_scaled": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                  C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "ssdx_seg_class_presence": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "ssdx_scale_scores": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int, _vp]),
     "ssdx_eval_tp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, _vp, _vp, C.c_int, _vp]),
     "ssdx_iou_pred_vs_true": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
@@ -257,7 +261,7 @@ def decode(anchors: Anchors, offsets, std, mode: int):
 
 
 def nms(boxes_yxyx, scores, max_per_class: int, max_total: int, iou_threshold: float, score_threshold: float,
-        want_aux: bool = False):
+        want_aux: bool = False, class_scale=None):
     B, A, Cn = (int(v) for v in scores.shape)
     dev = boxes_yxyx.device.index
     out = empty((B, max_total, 6), np.float32, dev)
@@ -265,10 +269,30 @@ def nms(boxes_yxyx, scores, max_per_class: int, max_total: int, iou_threshold: f
     aidx = empty((B, max_total), np.int32, dev) if want_aux else None
     nbytes = lib.ssdx_nms_workspace_bytes(B, A, Cn, max_per_class, max_total)
     ws = workspace(nbytes, dev)
-    check(lib.ssdx_nms(ptr(boxes_yxyx), ptr(scores), B, A, Cn, int(max_per_class), int(max_total),
-                       float(iou_threshold), float(score_threshold), ptr(out), ptr(valid), ptr(aidx), ptr(ws),
-                       ws.numel(), dev, stream_ptr(dev)))
+    check(lib.ssdx_nms_scaled(ptr(boxes_yxyx), ptr(scores), ptr(class_scale), B, A, Cn, int(max_per_class),
+                              int(max_total), float(iou_threshold), float(score_threshold), ptr(out), ptr(valid),
+                              ptr(aidx), ptr(ws), ws.numel(), dev, stream_ptr(dev)))
     return out, valid, aidx
+
+
+def seg_class_presence(seg_probs, depth: int = 4):
+    """seg_probs: CUDA float32 tensor (..., Cm).  Returns a CUDA float32 tensor (depth,) of 0/1."""
+    dev = seg_probs.device.index
+    cm = int(seg_probs.shape[-1])
+    out = empty((depth,), np.float32, dev)
+    ws = workspace(256, dev)
+    check(lib.ssdx_seg_class_presence(ptr(seg_probs), int(seg_probs.numel() // cm), cm, int(depth), ptr(out), ptr(ws),
+                                      ws.numel(), dev, stream_ptr(dev)))
+    return out
+
+
+def scale_scores(scores, class_scale):
+    dev = scores.device.index
+    Cn = int(scores.shape[-1])
+    out = empty(tuple(scores.shape), np.float32, dev)
+    check(lib.ssdx_scale_scores(ptr(scores), int(scores.numel() // Cn), Cn, ptr(class_scale), ptr(out), dev,
+                                stream_ptr(dev)))
+    return out
 
 
 def eval_tp(pred_label, pred_xyxy, gt_xyxy, gt_label, gt_count, num_classes: int, background_label: int,

@@ -90,19 +90,26 @@ class NonMaximumSuppression(_Layer):
         self.labels_probability_threshold = labels_probability_threshold
         self.suppress_background_boxes = suppress_background_boxes
 
-    def call(self, boxes_corners_coordinates, labels_probabilities, return_aux: bool = False):
+    def call(self, boxes_corners_coordinates, labels_probabilities, return_aux: bool = False, class_scale=None):
         """boxes (batch, total boxes, 4) as (ymin, xmin, ymax, xmax), probabilities (batch, total boxes, classes)
         -> (batch, max boxes per sample, 6) rows [label, probability, xmin, ymin, xmax, ymax], zero padded.
         With `suppress_background_boxes` the rows with label > 0 are returned flattened over the batch, as
         the reference does (layers.py:127-168).  `return_aux=True` also returns (valid (batch,), source anchor
-        index (batch, max boxes per sample))."""
+        index (batch, max boxes per sample)).  `class_scale` (classes,): per-class factor applied to the
+        probabilities as they are read, e.g. `SegmentationSuppression.class_presence(mask)`: same result as calling
+        the layer on `SegmentationSuppression()(mask, probabilities)` without materialising that tensor."""
         boxes, kind = _ssdx.to_device(boxes_corners_coordinates, np.float32, None, "nms_boxes")
         scores, _ = _ssdx.to_device(labels_probabilities, np.float32, boxes.device.index, "nms_scores")
         if boxes.dim() != 3 or boxes.shape[2] != 4 or scores.dim() != 3 or scores.shape[:2] != boxes.shape[:2]:
             raise ValueError("expected boxes (batch, boxes, 4) and probabilities (batch, boxes, classes)")
+        if class_scale is not None:
+            class_scale, _ = _ssdx.to_device(class_scale, np.float32, boxes.device.index, "nms_scale")
+            if tuple(class_scale.shape) != (int(scores.shape[2]),):
+                raise ValueError("class_scale must have one entry per class")
         out, valid, aidx = _ssdx.nms(boxes, scores, self.max_number_of_boxes_per_class,
                                      self.max_number_of_boxes_per_sample, self.boxes_iou_threshold,
-                                     self.labels_probability_threshold, want_aux=return_aux)
+                                     self.labels_probability_threshold, want_aux=return_aux,
+                                     class_scale=class_scale)
         if self.suppress_background_boxes:
             out = out[out[..., 0] > 0.0]  # tf.boolean_mask over (batch, boxes): drops the batch axis
         res = _ssdx.from_device(out, kind)
@@ -118,3 +125,36 @@ class NonMaximumSuppression(_Layer):
             'labels_probability_threshold': self.labels_probability_threshold,
             'suppress_background_boxes': self.suppress_background_boxes,
         }
+
+
+class SegmentationSuppression(_Layer):
+    """Process the object detection outputs with the semantic segmentation output: a class that the segmentation
+    did not detect anywhere in the batch is ignored by the object detection (layers.py:179-212)."""
+
+    DEPTH = 4  # tf.one_hot(..., depth=4) is hard-coded in the reference (layers.py:204)
+
+    def __init__(self, **kwargs) -> None:
+        super().__init__(**kwargs)
+
+    @classmethod
+    def class_presence(cls, segmentation_mask):
+        """(batch, height, width, classes) probabilities -> (4,) float32 of 0/1: 1 iff some pixel of the whole batch
+        has that class as its arg-max (layers.py:203-207).  Feed it to `NonMaximumSuppression.call(class_scale=...)`
+        to fuse the suppression into the NMS score filter."""
+        m, kind = _ssdx.to_device(segmentation_mask, np.float32, None, "seg_mask")
+        if m.dim() < 2:
+            raise ValueError("expected a segmentation mask of shape (batch, height, width, classes)")
+        return _ssdx.from_device(_ssdx.seg_class_presence(m, cls.DEPTH), kind)
+
+    def call(self, segmentation_mask, labels_probabilities):
+        """-> labels_probabilities * is_class_segmented, same shape as labels_probabilities (layers.py:189-212)."""
+        m, _ = _ssdx.to_device(segmentation_mask, np.float32, None, "seg_mask")
+        p, kind = _ssdx.to_device(labels_probabilities, np.float32, m.device.index, "seg_probs")
+        if int(p.shape[-1]) != self.DEPTH:
+            raise ValueError("labels_probabilities must have 4 classes on its last axis (one_hot depth of the "
+                             "reference, layers.py:204)")
+        presence = _ssdx.seg_class_presence(m, self.DEPTH)
+        return _ssdx.from_device(_ssdx.scale_scores(p, presence), kind)
+
+    def get_config(self):
+        return {}

@@ -393,6 +393,24 @@ def combined_nms(boxes_yxyx, scores, max_per_class, max_total, iou_thr, score_th
 
 
 # --------------------------------------------------------------------------
+# segmentation suppression (layers.py:189-212)
+# --------------------------------------------------------------------------
+def seg_class_presence(segmentation_mask: np.ndarray, depth: int = 4) -> np.ndarray:
+    """layers.py:203-207: argmax over the class axis (lowest index on ties) ->
+    one_hot(depth) -> sum over (batch, height, width) -> clip to [0, 1]."""
+    cls = np.argmax(np.asarray(segmentation_mask, F32), axis=-1).reshape(-1)
+    present = np.zeros(depth, F32)
+    seen = np.unique(cls)
+    present[seen[seen < depth]] = F32(1.0)  # one_hot of an index >= depth is an all-zero row
+    return present
+
+
+def segmentation_suppression(segmentation_mask: np.ndarray, labels_probabilities: np.ndarray) -> np.ndarray:
+    """layers.py:209: probabilities * is_class_segmented (broadcast over the last axis)."""
+    return (np.asarray(labels_probabilities, F32) * seg_class_presence(segmentation_mask, 4)).astype(F32)
+
+
+# --------------------------------------------------------------------------
 # a17-a18: detection evaluation (evaluators.py:6-187)  [P7]
 # --------------------------------------------------------------------------
 def iou_pred_vs_true(labels_pred, boxes_pred, labels_true, boxes_true) -> np.ndarray:

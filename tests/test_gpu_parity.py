@@ -338,6 +338,46 @@ def test_nms_rejects_bad_iou_threshold(lib, golden):
         lib.layers.NonMaximumSuppression(10, 10, 1.5, 0.1, False)(g["decoded_yxyx"], g["scores"])
 
 
+# ------------------------------------------------------------------------------------------- segmentation suppression
+def test_segmentation_suppression_golden(lib, golden):
+    g = golden("seg")
+    layer = lib.layers.SegmentationSuppression()
+    for case in "abcd":
+        pres = lib.layers.SegmentationSuppression.class_presence(g[case + "_mask"])
+        assert pres.dtype == np.float32 and np.array_equal(pres, orc.seg_class_presence(g[case + "_mask"]))
+        out = layer(g[case + "_mask"], g[case + "_probs"])
+        assert out.shape == g[case + "_probs"].shape and np.array_equal(out, g[case + "_suppressed"])
+
+
+@pytest.mark.parametrize("cm,shape", [(4, (3, 120, 160)), (4, (1, 7, 5)), (3, (2, 33, 17)), (6, (2, 40, 24))])
+def test_segmentation_presence_shapes_and_rare_classes(lib, cm, shape):
+    """A class that wins a single pixel of the whole batch is present; classes >= 4 fall outside one_hot(depth=4)."""
+    rng = np.random.default_rng(cm * 100 + shape[1])
+    mask = rng.uniform(0.0, 0.5, size=shape + (cm,)).astype(np.float32)
+    mask[..., 0] += 1.0                       # background wins everywhere ...
+    mask[-1, shape[1] // 2, shape[2] // 3, min(2, cm - 1)] = 5.0   # ... except one pixel
+    if cm > 4:
+        mask[0, 0, 0, 5] = 9.0                # index 5: dropped by one_hot(depth=4)
+    pres = lib.layers.SegmentationSuppression.class_presence(mask)
+    assert np.array_equal(pres, orc.seg_class_presence(mask))
+    assert pres[0] == 1 and pres[min(2, cm - 1)] == 1 and pres.sum() == 2
+
+
+def test_nms_class_scale_equals_nms_of_suppressed_scores(lib, golden):
+    """The fused path (scores multiplied as they are read) against the NMS of the materialised product, on the merged
+    pipeline (200/200), the per-class pipeline (4/10) and with a non-0/1 scale."""
+    g = golden("layers")
+    yxyx, scores = g["decoded_yxyx"], g["scores"]
+    for scale in ([1, 0, 1, 1], [0, 1, 0, 1], [1, 1, 1, 1], [0.5, 0.25, 2.0, 1.0]):
+        sc = np.asarray(scale, np.float32)
+        sup = (scores * sc).astype(np.float32)
+        for mpc, mtot, iou, thr in ((200, 200, 0.45, 0.01), (4, 10, 0.025, 0.2)):
+            layer = lib.layers.NonMaximumSuppression(mpc, mtot, iou, thr, False)
+            fused, v1, a1 = layer.call(yxyx, scores, return_aux=True, class_scale=sc)
+            ref, v2, a2 = orc.combined_nms(yxyx, sup, mpc, mtot, iou, thr)
+            assert np.array_equal(a1, a2) and np.array_equal(v1, v2) and np.array_equal(fused, ref)
+
+
 # ------------------------------------------------------------------------------------------- eval
 def test_eval_golden(lib, golden, tmp_path):
     g = golden("eval")

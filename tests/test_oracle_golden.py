@@ -161,3 +161,13 @@ def test_csv_front_end():
     assert l.shape == (0,) and b.shape == (0, 4)
     f = orc.flip_boxes_horizontal(np.array([[10, 5, 50, 60]], np.float32), 640)
     assert f.tolist() == [[590, 5, 630, 60]]
+
+
+def test_segmentation_suppression_matches_reference_source(golden):
+    """the oracle against layers.SegmentationSuppression executed from the reference's file."""
+    g = golden("seg")
+    for case, expect in (("a", [1, 1, 1, 1]), ("b", [1, 1, 0, 1]), ("c", [1, 0, 0, 0]), ("d", [1, 0, 0, 1])):
+        pres = orc.seg_class_presence(g[case + "_mask"])
+        assert pres.tolist() == expect
+        assert np.array_equal(orc.segmentation_suppression(g[case + "_mask"], g[case + "_probs"]),
+                              g[case + "_suppressed"])
