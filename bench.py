@@ -356,18 +356,41 @@ def gpu_arm(args, rank, world, local_rank):
                 for i, s in enumerate(stages)}
 
     # ---------------- end-to-end through the public API with host buffers ----------------
+    # The batch is fed in chunks: chunk i + 1 crosses PCIe while chunk i is computed (two streams; every call below is
+    # the public API).  Per step all of the step's inputs are copied from pinned host memory and all of its
+    # detections are read back.
+    n_chunks = max(1, min(args.e2e_chunks, B))
+    bounds = [(B * i // n_chunks, B * (i + 1) // n_chunks) for i in range(n_chunks)]
+    copy_stream = torch.cuda.Stream(dev)
+    h_det = torch.empty((B, K_STD, 6), dtype=torch.float32).pin_memory()
+
     def step_e2e():
-        gb = h_boxes.to(f"cuda:{dev}", non_blocking=True)
-        gl = h_labels.to(f"cuda:{dev}", non_blocking=True)
-        gc = h_counts.to(f"cuda:{dev}", non_blocking=True)
-        sc = h_scores.to(f"cuda:{dev}", non_blocking=True)
-        if "encode" in stages:
-            _, off = coder.encode_batch(gb, gl, gc)
-        else:
-            off = h_pred_off.to(f"cuda:{dev}", non_blocking=True)
-        yx = dec_layer(off)
-        det = nms_layer(yx, sc)
-        return det.cpu()  # device -> host read of the step's result (synchronises)
+        staged = []
+        copy_stream.wait_stream(stream)
+        with torch.cuda.stream(copy_stream):
+            for lo, hi in bounds:
+                gb = h_boxes[lo:hi].to(f"cuda:{dev}", non_blocking=True)
+                gl = h_labels[lo:hi].to(f"cuda:{dev}", non_blocking=True)
+                gc = h_counts[lo:hi].to(f"cuda:{dev}", non_blocking=True)
+                sc = h_scores[lo:hi].to(f"cuda:{dev}", non_blocking=True)
+                po = None if "encode" in stages else h_pred_off[lo:hi].to(f"cuda:{dev}", non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                staged.append((gb, gl, gc, sc, po, ev))
+        for (lo, hi), (gb, gl, gc, sc, po, ev) in zip(bounds, staged):
+            stream.wait_event(ev)
+            for t in (gb, gl, gc, sc, po):
+                if t is not None:
+                    t.record_stream(stream)
+            if "encode" in stages:
+                _, off = coder.encode_batch(gb, gl, gc)
+            else:
+                off = po
+            yx = dec_layer(off)
+            det = nms_layer(yx, sc)
+            h_det[lo:hi].copy_(det, non_blocking=True)  # device -> host read of the chunk's result
+        stream.synchronize()
+        return h_det
 
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(2):
@@ -451,7 +474,8 @@ def gpu_arm(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "ssdseglib.datacoder.DataEncoderDecoder.encode_batch -> layers.DecodeBoxesCentroidsOffsets"
-                           " -> layers.NonMaximumSuppression (inputs from pinned host memory, detections to host)"},
+                           " -> layers.NonMaximumSuppression (inputs from pinned host memory, detections to pinned host"
+                           f" memory, {n_chunks} chunks per step on two streams)"},
             "gpu_launches": kernels_per_step * args.steps,
             "clocks": sampler.summary(),
         }
@@ -478,6 +502,7 @@ def main():
     ap.add_argument("--workload", default="roundtrip_b1024", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph per step")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks per step of the end-to-end leg (copy/compute overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -493,7 +518,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload",
                args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
-                   ["--no-graph"] if args.no_graph else [])
+                   ["--no-graph"] if args.no_graph else []) + ["--e2e-chunks", str(args.e2e_chunks)]
         raise SystemExit(subprocess.call(cmd))
     gpu_arm(args, rank, world, local_rank)
 

@@ -190,16 +190,17 @@ __device__ __forceinline__ void match_tile(AnchorTile& t, const float4 tb, const
 // Seed of the GT-side bound: one warp evaluates, for GT box g, the tile that looks most promising (largest
 // bound (ii), then nearest centre) and publishes the best real pair it finds.  Any real pair is a valid lower bound
 // of max_a iou[a,g]; a good one lets tests (ii) and (iii) cull from the first tile on.
+// (t_bbox / t_area: shared memory in the fused driver, global in the tiled one: generic loads, no __restrict__)
 __device__ __forceinline__ void seed_gt_best(const float4* __restrict__ m_box, const float* __restrict__ m_area,
-                                             const int* __restrict__ m_idx, const float4* __restrict__ t_bbox,
-                                             const float2* __restrict__ t_area, const int n_tiles, const float4 gb,
+                                             const int* __restrict__ m_idx, const float4* t_bbox,
+                                             const float2* t_area, const int n_tiles, const float4 gb,
                                              const float ga, u64* s_best_g, const int lane) {
   float best_score = -1.0f;
   int best_tile = 0;
   const float gcx = 0.5f * (gb.x + gb.z), gcy = 0.5f * (gb.y + gb.w);
   for (int tile = lane; tile < n_tiles; tile += 32) {
-    const float4 tb = __ldg(t_bbox + tile);
-    const float2 ta = __ldg(t_area + tile);
+    const float4 tb = t_bbox[tile];
+    const float2 ta = t_area[tile];
     const float tw = fminf(tb.z, gb.z) - fmaxf(tb.x, gb.x) + 1.0f;
     const float th = fminf(tb.w, gb.w) - fmaxf(tb.y, gb.y) + 1.0f;
     if (tw > 0.0f && th > 0.0f) {
@@ -279,6 +280,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int A, int G, int C) {
   n += g * 16 + g * 8 + g * 4 + g * 4 + g * 4;                                       // box, best, area, lab, s1a
   n = (n + 15) / 16 * 16;
   n += (size_t)kPosCap * 4 + 16;                                                     // pos, ctrl
+  n += (size_t)((A + kSsdxTile - 1) / kSsdxTile) * 24 + 16;                          // tile boxes + area ranges
   n += (size_t)((A + 7) / 8 * 8) * 2;                                                // table
   return n + 16;
 }
@@ -312,6 +314,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1024 / kFusedThreads)
   int* s_s1a;
   int* s_pos;
   int* s_ctrl;
+  float4* s_tbox;
+  float2* s_tarea;
   short* s_tab;
   {
     unsigned char* p = smem_raw;
@@ -325,6 +329,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1024 / kFusedThreads)
     p = smem_raw + ((size_t)(p - smem_raw) + 15) / 16 * 16;
     s_pos = (int*)p;      p += (size_t)kPosCap * 4;
     s_ctrl = (int*)p;     p += 16;
+    s_tbox = (float4*)p;  p += (size_t)n_tiles * 16;
+    s_tarea = (float2*)p; p += ((size_t)n_tiles * 8 + 15) / 16 * 16;
     s_tab = (short*)p;
   }
 
@@ -344,6 +350,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1024 / kFusedThreads)
     s_best[g] = 0ull;
   }
   for (int i = tid; i < A8 / 8; i += kFusedThreads) reinterpret_cast<int4*>(s_tab)[i] = make_int4(-1, -1, -1, -1);
+  for (int t = tid; t < n_tiles; t += kFusedThreads) {  // tile table: read by every seed warp and every tile visit
+    s_tbox[t] = __ldg(t_bbox + t);
+    s_tarea[t] = __ldg(t_area + t);
+  }
   if (tid == 0) {
     s_ctrl[0] = kWarps;  // next tile to hand out (the first kWarps tiles are taken statically)
     s_ctrl[1] = 0;       // number of positives
@@ -381,14 +391,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1024 / kFusedThreads)
     const float thr_eff = fmaxf(iou_thr, 0.0f);
 #ifndef SSDX_EXP_SKIP_SEED
     for (int g = warp; g < G; g += kWarps)
-      seed_gt_best(m_box, m_area, m_idx, t_bbox, t_area, n_tiles, s_box[g], s_area[g], s_best + g, lane);
+      seed_gt_best(m_box, m_area, m_idx, s_tbox, s_tarea, n_tiles, s_box[g], s_area[g], s_best + g, lane);
 #endif
     PHASE_ADD(17);  // seed (no barrier: the other warps' seeds arrive through s_best whenever they are ready)
     int tile = warp;
     while (tile < n_tiles) {
       AnchorTile t;
       load_tile(t, m_box, m_area, m_idx, tile, lane);
-      match_tile(t, __ldg(t_bbox + tile), __ldg(t_area + tile), s_box, s_area, s_best, G, 0, thr_eff, lane);
+      match_tile(t, s_tbox[tile], s_tarea[tile], s_box, s_area, s_best, G, 0, thr_eff, lane);
 #pragma unroll
       for (int u = 0; u < kApt; ++u)
         if (t.idx[u] >= 0 && t.best_v[u] > iou_thr) s_tab[t.idx[u]] = (short)t.best_g[u];
