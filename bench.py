@@ -284,9 +284,19 @@ def gpu_arm(args, rank, world, local_rank):
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
-    def step_device(events=None):
+    side = torch.cuda.Stream(dev)
+
+    def step_device(events=None, overlap=False):
+        """One step through the C ABI.  overlap=True: the NMS candidate selection (reads only the scores) runs on a
+        second stream while encode and decode run on the first one, as the two input branches of the reference's NMS
+        layer allow (models.py:402-414); ssdx_nms_select + ssdx_nms_finish == ssdx_nms bit for bit."""
         nonlocal sp
         i = 0
+        cur = torch.cuda.current_stream(dev)
+        if overlap:
+            side.wait_stream(cur)
+            sx.check(sx.lib.ssdx_nms_select(d_scores.data_ptr(), None, B, A_STD, C_STD, K_STD, K_STD, 0.01,
+                                            ws_nms.data_ptr(), ws_nms.numel(), dev, side.cuda_stream))
         if events is not None:
             events[i].record(stream); i += 1
         if "encode" in stages:
@@ -299,8 +309,15 @@ def gpu_arm(args, rank, world, local_rank):
         sx.check(sx.lib.ssdx_decode(dec_layer._anchors.handle, src.data_ptr(), B, std, 0, o_boxes.data_ptr(), sp))
         if events is not None:
             events[i].record(stream); i += 1
-        sx.check(sx.lib.ssdx_nms(o_boxes.data_ptr(), d_scores.data_ptr(), B, A_STD, C_STD, K_STD, K_STD, 0.45, 0.01,
-                                 o_det.data_ptr(), o_valid.data_ptr(), None, ws_nms.data_ptr(), ws_nms.numel(), dev, sp))
+        if overlap:
+            cur.wait_stream(side)
+            sx.check(sx.lib.ssdx_nms_finish(o_boxes.data_ptr(), d_scores.data_ptr(), None, B, A_STD, C_STD, K_STD, K_STD,
+                                            0.45, 0.01, o_det.data_ptr(), o_valid.data_ptr(), None, ws_nms.data_ptr(),
+                                            ws_nms.numel(), dev, sp))
+        else:
+            sx.check(sx.lib.ssdx_nms(o_boxes.data_ptr(), d_scores.data_ptr(), B, A_STD, C_STD, K_STD, K_STD, 0.45, 0.01,
+                                     o_det.data_ptr(), o_valid.data_ptr(), None, ws_nms.data_ptr(), ws_nms.numel(),
+                                     dev, sp))
         if events is not None:
             events[i].record(stream)
 
@@ -329,7 +346,7 @@ def gpu_arm(args, rank, world, local_rank):
         outer_sp = sp
         with torch.cuda.graph(graph, stream=cap_stream):
             sp = torch.cuda.current_stream(dev).cuda_stream
-            step_device()
+            step_device(overlap=not args.no_overlap)
         sp = outer_sp
         for _ in range(3):
             graph.replay()
@@ -342,7 +359,7 @@ def gpu_arm(args, rank, world, local_rank):
         if graph is not None:
             graph.replay()
         else:
-            step_device()
+            step_device(overlap=not args.no_overlap)
     t_end.record(stream)
     barrier()
     total_ms = t_start.elapsed_time(t_end)
@@ -465,7 +482,9 @@ def gpu_arm(args, rank, world, local_rank):
                        "score_thr": 0.01, "iou_thr": 0.45, "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "no flush: each step streams %.0f MB (> 126 MB L2)" % (
                            sum(BYTES_PER_IMAGE[s] for s in stages) * B / 1e6),
-                       "launch": "eager" if graph is None else "one CUDA graph per step",
+                       "launch": ("eager" if graph is None else "one CUDA graph per step") + (
+                           "" if args.no_overlap else "; NMS candidate selection (ssdx_nms_select) on a second stream, "
+                           "concurrent with encode/decode, joined before ssdx_nms_finish"),
                        "oracle_check": check},
             "roofline": {"bound": "hbm", "kernel": kernels[dom], "stage": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -502,6 +521,7 @@ def main():
     ap.add_argument("--workload", default="roundtrip_b1024", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph per step")
+    ap.add_argument("--no-overlap", action="store_true", help="single stream: ssdx_nms instead of select || encode/decode")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks per step of the end-to-end leg (copy/compute overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -518,7 +538,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload",
                args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
-                   ["--no-graph"] if args.no_graph else []) + ["--e2e-chunks", str(args.e2e_chunks)]
+                   ["--no-graph"] if args.no_graph else []) + (["--no-overlap"] if args.no_overlap else []) + [
+                   "--e2e-chunks", str(args.e2e_chunks)]
         raise SystemExit(subprocess.call(cmd))
     gpu_arm(args, rank, world, local_rank)
 

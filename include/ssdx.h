@@ -110,6 +110,21 @@ SSDX_API int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, const
                              int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
                              ssdx_stream stream);
 
+/* The same NMS in two stream-ordered phases on one workspace.  ssdx_nms_select reads only the scores (candidate lists
+ * into the workspace); ssdx_nms_finish needs the boxes and must see the same scores, class_scale, shape, caps,
+ * score_threshold and workspace.  In the reference's inference graph the two inputs of the NMS layer are independent
+ * branches (models.py:402-414: output-labels -> [SegmentationSuppression], output-boxes -> Decode), so phase 1 may
+ * run on another stream while the boxes are still being decoded; the caller orders the two calls (events).
+ * select + finish == ssdx_nms_scaled, bit for bit. */
+SSDX_API int ssdx_nms_select(const float* scores, const float* class_scale, int32_t batch, int32_t num_anchors,
+                             int32_t num_classes, int32_t max_per_class, int32_t max_total, float score_threshold,
+                             void* workspace, size_t workspace_bytes, int device, ssdx_stream stream);
+SSDX_API int ssdx_nms_finish(const float* boxes_yxyx, const float* scores, const float* class_scale, int32_t batch,
+                             int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
+                             float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
+                             int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
+                             ssdx_stream stream);
+
 /* ---- segmentation suppression: layers.py:189-212 (SegmentationSuppression.call), SURVEY 8(f) row 2 ----
  * seg_probs (num_pixels, Cm) f32 = the (B,H,W,Cm) segmentation output flattened over batch and space.
  * out_presence (depth) f32: 1.0f iff some pixel of the WHOLE batch has argmax == c (ties -> lowest index), else 0.0f

@@ -1359,18 +1359,23 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
                          device, stream);
 }
 
-extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, const float* class_scale, int32_t batch,
-                               int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
-                               float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
-                               int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
-                               ssdx_stream stream) {
+// phases: 1 = candidate selection (reads only the scores), 2 = everything that needs the boxes.  ssdx_nms runs both;
+// ssdx_nms_select / ssdx_nms_finish expose them separately so that a caller can run phase 1 on another stream while
+// the boxes are still being decoded (in the reference's inference graph the two inputs of the NMS layer are
+// independent branches, models.py:402-414).
+static int nms_run(const int phases, const float* boxes_yxyx, const float* scores, const float* class_scale,
+                   int32_t batch, int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
+                   float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
+                   int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device, ssdx_stream stream) {
   const float* cscale = class_scale;
-  SSDX_CHECK_ARG(boxes_yxyx != nullptr && scores != nullptr && out != nullptr, "ssdx_nms: NULL pointer argument");
+  const bool ph1 = (phases & 1) != 0, ph2 = (phases & 2) != 0;
+  SSDX_CHECK_ARG(scores != nullptr && (!ph2 || (boxes_yxyx != nullptr && out != nullptr)),
+                 "ssdx_nms: NULL pointer argument");
   SSDX_CHECK_ARG(batch >= 0 && num_anchors > 0 && num_classes > 0, "ssdx_nms: bad shape (B=%d, A=%d, C=%d)", batch,
                  num_anchors, num_classes);
   SSDX_CHECK_ARG(max_per_class > 0 && max_total > 0, "ssdx_nms: max_per_class and max_total must be > 0");
   SSDX_CHECK_ARG(iou_threshold >= 0.0f && iou_threshold <= 1.0f, "iou_threshold must be in [0, 1]");
-  SSDX_CHECK_ARG(((uintptr_t)boxes_yxyx & 15) == 0, "ssdx_nms: boxes must be 16-byte aligned");
+  SSDX_CHECK_ARG(!ph2 || ((uintptr_t)boxes_yxyx & 15) == 0, "ssdx_nms: boxes must be 16-byte aligned");
   SSDX_CHECK_ARG(batch <= 65535 && num_classes <= 65535 && (long long)batch * num_classes < (1ll << 30),
                  "ssdx_nms: batch and classes must be <= 65535 per call");
   if (batch == 0) return SSDX_OK;
@@ -1418,13 +1423,16 @@ extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, con
   const bool merged = !force_generic && !force_perclass && max_per_class >= max_total && C <= 256 &&
                       A <= (1 << 24) && max_total <= kFastMaxSel;
   if (merged) {
-    if (vec4)
-      ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, lists, info, flags,
-                                                                     iflags);
-    else
-      ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, lists, info,
-                                                                      flags, iflags);
-    SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
+    if (ph1) {
+      if (vec4)
+        ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, lists,
+                                                                       info, flags, iflags);
+      else
+        ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, lists,
+                                                                        info, flags, iflags);
+      SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
+    }
+    if (!ph2) return SSDX_OK;
     if (max_total <= 256)
       ssdx_nms_fast_all_kernel<256, SSDX_FAST_MINB><<<batch, kFastThreads, 0, s>>>(
           bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid,
@@ -1449,7 +1457,7 @@ extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, con
   // 1. select
   const size_t sel_smem = (size_t)(C < kSelGroup ? C : kSelGroup) * NS * 4 + kSelGroup * 12 + 16;
   const bool use_fast = sel_smem <= 200 * 1024 && !force_generic;
-  if (use_fast) {
+  if (use_fast && ph1) {
     dim3 gsel((C + kSelGroup - 1) / kSelGroup, batch);
     if (vec4) {
       SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1461,6 +1469,9 @@ extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, con
       ssdx_nms_select_kernel<false><<<gsel, kSelThreads, sel_smem, s>>>(scores, cscale, A, C, score_threshold, lists, info, flags);
     }
     SSDX_LAUNCH_CHECK("ssdx_nms_select_kernel");
+  }
+  if (!ph2) return SSDX_OK;
+  if (use_fast) {
     // 2. fast path
     dim3 gseg(C, batch);
     ssdx_nms_fast_kernel<<<gseg, kFastThreads, 0, s>>>(bx, scores, cscale, lists, info, A, C, limit, iou_threshold,
@@ -1479,4 +1490,31 @@ extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, con
                                                                              out_anchor_idx, nullptr, batch);
   SSDX_LAUNCH_CHECK("ssdx_nms_merge_kernel");
   return SSDX_OK;
+}
+
+extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, const float* class_scale, int32_t batch,
+                               int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
+                               float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
+                               int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
+                               ssdx_stream stream) {
+  return nms_run(3, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
+                 iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes, device,
+                 stream);
+}
+
+extern "C" int ssdx_nms_select(const float* scores, const float* class_scale, int32_t batch, int32_t num_anchors,
+                               int32_t num_classes, int32_t max_per_class, int32_t max_total, float score_threshold,
+                               void* workspace, size_t workspace_bytes, int device, ssdx_stream stream) {
+  return nms_run(1, nullptr, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total, 0.5f,
+                 score_threshold, nullptr, nullptr, nullptr, workspace, workspace_bytes, device, stream);
+}
+
+extern "C" int ssdx_nms_finish(const float* boxes_yxyx, const float* scores, const float* class_scale, int32_t batch,
+                               int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
+                               float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
+                               int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
+                               ssdx_stream stream) {
+  return nms_run(2, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
+                 iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes, device,
+                 stream);
 }

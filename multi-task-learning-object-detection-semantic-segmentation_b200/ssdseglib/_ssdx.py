@@ -46,6 +46,10 @@ SIGNATURES = {
                            _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
     "ssdx_nms_scaled": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                   C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "ssdx_nms_select": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _vp,
+                                  C.c_size_t, C.c_int, _vp]),
+    "ssdx_nms_finish": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                  C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
     "ssdx_seg_class_presence": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.c_size_t, C.c_int, _vp]),
     "ssdx_scale_scores": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int, _vp]),
     "ssdx_eval_tp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -272,6 +276,47 @@ def nms(boxes_yxyx, scores, max_per_class: int, max_total: int, iou_threshold: f
     check(lib.ssdx_nms_scaled(ptr(boxes_yxyx), ptr(scores), ptr(class_scale), B, A, Cn, int(max_per_class),
                               int(max_total), float(iou_threshold), float(score_threshold), ptr(out), ptr(valid),
                               ptr(aidx), ptr(ws), ws.numel(), dev, stream_ptr(dev)))
+    return out, valid, aidx
+
+
+class NmsSelection:
+    """Phase 1 of the NMS (candidate lists in a private workspace), to be finished with `nms_finish`."""
+
+    def __init__(self, scores, class_scale, max_per_class, max_total, score_threshold, ws, event):
+        self.scores, self.class_scale, self.ws, self.event = scores, class_scale, ws, event
+        self.max_per_class, self.max_total, self.score_threshold = max_per_class, max_total, score_threshold
+
+
+def nms_select(scores, max_per_class: int, max_total: int, score_threshold: float, class_scale=None) -> NmsSelection:
+    """Runs on the CURRENT stream (which may differ from the stream `nms_finish` is called on); the returned object
+    carries the event phase 2 waits for."""
+    torch = _torch()
+    B, A, Cn = (int(v) for v in scores.shape)
+    dev = scores.device.index
+    ws = torch.empty(int(lib.ssdx_nms_workspace_bytes(B, A, Cn, max_per_class, max_total)), dtype=torch.uint8,
+                     device=f"cuda:{dev}")
+    check(lib.ssdx_nms_select(ptr(scores), ptr(class_scale), B, A, Cn, int(max_per_class), int(max_total),
+                              float(score_threshold), ptr(ws), ws.numel(), dev, stream_ptr(dev)))
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    return NmsSelection(scores, class_scale, int(max_per_class), int(max_total), float(score_threshold), ws, ev)
+
+
+def nms_finish(sel: NmsSelection, boxes_yxyx, iou_threshold: float, want_aux: bool = False):
+    torch = _torch()
+    B, A, Cn = (int(v) for v in sel.scores.shape)
+    dev = boxes_yxyx.device.index
+    cur = torch.cuda.current_stream(dev)
+    cur.wait_event(sel.event)
+    for t in (sel.scores, sel.class_scale, sel.ws):
+        if t is not None:
+            t.record_stream(cur)
+    out = empty((B, sel.max_total, 6), np.float32, dev)
+    valid = empty((B,), np.int32, dev) if want_aux else None
+    aidx = empty((B, sel.max_total), np.int32, dev) if want_aux else None
+    check(lib.ssdx_nms_finish(ptr(boxes_yxyx), ptr(sel.scores), ptr(sel.class_scale), B, A, Cn, sel.max_per_class,
+                              sel.max_total, float(iou_threshold), sel.score_threshold, ptr(out), ptr(valid),
+                              ptr(aidx), ptr(sel.ws), sel.ws.numel(), dev, stream_ptr(dev)))
     return out, valid, aidx
 
 

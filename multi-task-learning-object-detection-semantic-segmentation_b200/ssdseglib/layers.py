@@ -117,6 +117,33 @@ class NonMaximumSuppression(_Layer):
             return res, _ssdx.from_device(valid, kind), _ssdx.from_device(aidx, kind)
         return res
 
+    def select(self, labels_probabilities, class_scale=None):
+        """Phase 1 of `call` (new entry point): everything that depends only on the probabilities, on the current
+        CUDA stream.  In the reference's inference graph the probabilities and the decoded boxes reach this layer
+        through independent branches (models.py:402-414), so this can run on a side stream while the boxes are
+        still being decoded.  Returns an opaque selection for `finish`."""
+        scores, _ = _ssdx.to_device(labels_probabilities, np.float32, None, "nms_scores")
+        if scores.dim() != 3:
+            raise ValueError("expected probabilities (batch, boxes, classes)")
+        if class_scale is not None:
+            class_scale, _ = _ssdx.to_device(class_scale, np.float32, scores.device.index, "nms_scale")
+        return _ssdx.nms_select(scores, self.max_number_of_boxes_per_class, self.max_number_of_boxes_per_sample,
+                                self.labels_probability_threshold, class_scale=class_scale)
+
+    def finish(self, selection, boxes_corners_coordinates, return_aux: bool = False):
+        """Phase 2 of `call`: waits (stream-ordered) for `selection`, then suppresses and packs.  Same result as
+        `call(boxes, probabilities)`."""
+        boxes, kind = _ssdx.to_device(boxes_corners_coordinates, np.float32, selection.scores.device.index, "nms_boxes")
+        if boxes.dim() != 3 or boxes.shape[2] != 4 or selection.scores.shape[:2] != boxes.shape[:2]:
+            raise ValueError("expected boxes (batch, boxes, 4) matching the selected probabilities")
+        out, valid, aidx = _ssdx.nms_finish(selection, boxes, self.boxes_iou_threshold, want_aux=return_aux)
+        if self.suppress_background_boxes:
+            out = out[out[..., 0] > 0.0]
+        res = _ssdx.from_device(out, kind)
+        if return_aux:
+            return res, _ssdx.from_device(valid, kind), _ssdx.from_device(aidx, kind)
+        return res
+
     def get_config(self):
         return {
             'max_number_of_boxes_per_class': self.max_number_of_boxes_per_class,

@@ -321,6 +321,25 @@ def test_nms_merged_runs_dry_and_refills(lib):
     assert (out[..., 1] > 0).sum(axis=1).max() <= 4 * 40 + 40  # ~ one survivor per (cluster, class)
 
 
+def test_nms_two_phase_on_a_side_stream(lib, golden):
+    """select (scores only, on a side stream) + finish == call, on the merged and on the per-class pipeline."""
+    import torch
+
+    g = golden("layers")
+    boxes = torch.from_numpy(g["decoded_yxyx"]).cuda()
+    scores = torch.from_numpy(g["scores"]).cuda()
+    side = torch.cuda.Stream()
+    for mpc, mtot, iou, thr in ((200, 200, 0.45, 0.01), (4, 10, 0.025, 0.2)):
+        layer = lib.layers.NonMaximumSuppression(mpc, mtot, iou, thr, False)
+        ref, vref, aref = layer.call(boxes, scores, return_aux=True)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            sel = layer.select(scores)
+        out, valid, aidx = layer.finish(sel, boxes, return_aux=True)
+        assert torch.equal(out, ref) and torch.equal(valid, vref) and torch.equal(aidx, aref)
+    assert np.array_equal(ref.cpu().numpy().shape, (2, 10, 6))
+
+
 def test_nms_torch_in_torch_out(lib, golden):
     import torch
 
