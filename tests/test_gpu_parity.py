@@ -357,6 +357,37 @@ def test_nms_rejects_bad_iou_threshold(lib, golden):
         lib.layers.NonMaximumSuppression(10, 10, 1.5, 0.1, False)(g["decoded_yxyx"], g["scores"])
 
 
+# ------------------------------------------------------------------------------------------- full bench size
+def test_round_trip_at_bench_size_against_c_oracle(lib, coder, std_anchors, golden):
+    """BASELINE's full configuration (batch 1024, A = 9600, G = 16, C = 4, thr .01, IoU .45, top-200): every image of
+    encode -> decode -> NMS against the C/OpenMP port of the oracle (itself checked against the NumPy oracle in
+    tests/test_c_oracle.py).  Matched indices, labels, keep-sets and detection rows bit-exact; offsets/boxes 1e-5."""
+    import os
+
+    from oracle import c_oracle
+
+    NT = os.cpu_count() or 1
+    B = 1024
+    rng = np.random.default_rng(1995)
+    labels, boxes, counts = orc.synth_gt(rng, B, 16)
+    counts[::97] = rng.integers(0, 16, size=counts[::97].shape)           # a few ragged / empty images
+    L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = c_oracle.encode_batch(std_anchors, labels, boxes, counts, 4, 0.5, STD, nthreads=NT)
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+    cent = golden("anchors")["std_centroids"]
+    layer = lib.layers.DecodeBoxesCentroidsOffsets(cent[:, 0], cent[:, 1], cent[:, 2], cent[:, 3], *STD)
+    yxyx = layer(O)
+    assert_coords_close(yxyx, c_oracle.decode_batch(cent, O, STD, 0, nthreads=NT), cent[None, :, 2:])
+    noise = rng.normal(0, 1, size=L.shape).astype(np.float32)
+    scores = (np.float32(0.9) * L + np.float32(0.1) * orc.softmax_f32(noise)).astype(np.float32)
+    nms = lib.layers.NonMaximumSuppression(200, 200, 0.45, 0.01, False)
+    det, valid, aidx = nms.call(yxyx, scores, return_aux=True)
+    det_r, valid_r, aidx_r = c_oracle.combined_nms(yxyx, scores, 200, 200, 0.45, 0.01, nthreads=NT)
+    assert np.array_equal(aidx, aidx_r) and np.array_equal(valid, valid_r) and np.array_equal(det, det_r)
+    assert np.all(np.diff(det[..., 1], axis=1) <= 0)                      # rows sorted by score
+
+
 # ------------------------------------------------------------------------------------------- segmentation suppression
 def test_segmentation_suppression_golden(lib, golden):
     g = golden("seg")
