@@ -611,15 +611,24 @@ __global__ void __launch_bounds__(kEmitThreads)
 
   int match = -1;
   if (a < A) match = resolve_match(a, anchor_g2[(size_t)b * A + a], s_s1max[tid], best);
-  float4 off = make_float4(0.f, 0.f, 0.f, 0.f);
   int lab = 0;  // background row = one_hot(0)
-  if (match >= 0) {
-    lab = __ldg(gt_label + (size_t)b * Gmax + match);
-    off = pair_offsets(__ldg(gt_xyxy + (size_t)b * Gmax + match), __ldg(anc_cent + a), sx, sy, sw, sh);
-  }
+  if (match >= 0) lab = __ldg(gt_label + (size_t)b * Gmax + match);
+  // offsets: background rows are written at once; the positives (log + six IEEE divisions each) are compacted and
+  // encoded densely by the first warps instead of diverging every warp of the CTA
+  __shared__ int s_pos[kEmitThreads];
+  __shared__ int s_npos;
+  if (tid == 0) s_npos = 0;
+  __syncthreads();
   if (a < A) {
-    st_stream_f4(out_offsets + (size_t)b * A + a, off);
+    if (match >= 0) s_pos[atomicAdd(&s_npos, 1)] = (tid << 16) | match;  // match <= 32766
+    else st_stream_f4(out_offsets + (size_t)b * A + a, make_float4(0.f, 0.f, 0.f, 0.f));
     if (out_match) out_match[(size_t)b * A + a] = match;
+  }
+  __syncthreads();
+  if (tid < s_npos) {
+    const int pa = a_base + (s_pos[tid] >> 16), pm = s_pos[tid] & 0xFFFF;
+    st_stream_f4(out_offsets + (size_t)b * A + pa,
+                 pair_offsets(__ldg(gt_xyxy + (size_t)b * Gmax + pm), __ldg(anc_cent + pa), sx, sy, sw, sh));
   }
   const int n_here = min(kEmitThreads, A - a_base);
   if (C == 4) {
