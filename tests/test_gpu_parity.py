@@ -242,7 +242,9 @@ def test_nms_config1_batch(lib, golden):
 
 
 @pytest.mark.parametrize("mpc,mtot,iou,thr", [(4, 10, 0.025, 0.725), (50, 20, 0.3, 0.3), (300, 1000, 0.6, 0.05),
-                                              (1, 1, 0.0, 0.0), (200, 200, 1.0, 0.01)])
+                                              (1, 1, 0.0, 0.0), (200, 200, 1.0, 0.01),
+                                              (500, 300, 0.5, 0.05),     # merged pipeline, 256 < max_total <= 512
+                                              (600, 600, 0.5, 0.05)])    # more than 512 boxes per class: generic kernel
 def test_nms_parameter_grid(lib, golden, mpc, mtot, iou, thr):
     a = golden("anchors")["std_centroids"]
     off, scores = orc.synth_predictions(np.random.default_rng(mpc), 3, 9600, 4)
