@@ -285,41 +285,71 @@ def gpu_arm(args, rank, world, local_rank):
     sp = stream.cuda_stream
 
     side = torch.cuda.Stream(dev)
+    # --pipeline P: the batch is cut into P contiguous sub-batches that run encode -> decode -> NMS on alternating
+    # streams, so that the memory-bound kernels of one sub-batch (decode, NMS select) overlap the compute-bound ones
+    # of the other (encode match, NMS sort + suppression).  Same calls, same work, same outputs; P = 1 is one stream.
+    n_pipe = max(1, min(args.pipeline, B))
+    pipe_bounds = [(B * i // n_pipe, B * (i + 1) // n_pipe) for i in range(n_pipe)]
+    ws_enc_p = [ws_enc] + [torch.empty_like(ws_enc) for _ in range(n_pipe - 1)]
+    ws_nms_p = [ws_nms] + [torch.empty_like(ws_nms) for _ in range(n_pipe - 1)]
+    n_streams = max(1, min(args.pipeline_streams, n_pipe))
+    pipe_streams = [None, side] + [torch.cuda.Stream(dev) for _ in range(max(0, n_streams - 2))]  # None = step stream
+    pipe_streams = pipe_streams[:n_streams]
+
+    def run_range(lo, hi, s_ptr, ws_e, ws_n, events=None, ev_stream=None, overlap_side=None):
+        n = hi - lo
+        i = 0
+        if overlap_side is not None:
+            overlap_side.wait_stream(ev_stream)
+            sx.check(sx.lib.ssdx_nms_select(d_scores[lo:hi].data_ptr(), None, n, A_STD, C_STD, K_STD, K_STD, 0.01,
+                                            ws_n.data_ptr(), ws_n.numel(), dev, overlap_side.cuda_stream))
+        if events is not None:
+            events[i].record(ev_stream); i += 1
+        if "encode" in stages:
+            sx.check(sx.lib.ssdx_encode(handle, d_boxes[lo:hi].data_ptr(), d_labels[lo:hi].data_ptr(),
+                                        d_counts[lo:hi].data_ptr(), n, G_STD, C_STD, 0.5, std,
+                                        o_labels[lo:hi].data_ptr(), o_offsets[lo:hi].data_ptr(), None, ws_e.data_ptr(),
+                                        ws_e.numel(), s_ptr))
+            if events is not None:
+                events[i].record(ev_stream); i += 1
+        src = o_offsets if "encode" in stages else d_pred_off
+        sx.check(sx.lib.ssdx_decode(dec_layer._anchors.handle, src[lo:hi].data_ptr(), n, std, 0,
+                                    o_boxes[lo:hi].data_ptr(), s_ptr))
+        if events is not None:
+            events[i].record(ev_stream); i += 1
+        if overlap_side is not None:
+            ev_stream.wait_stream(overlap_side)
+            sx.check(sx.lib.ssdx_nms_finish(o_boxes[lo:hi].data_ptr(), d_scores[lo:hi].data_ptr(), None, n, A_STD, C_STD,
+                                            K_STD, K_STD, 0.45, 0.01, o_det[lo:hi].data_ptr(), o_valid[lo:hi].data_ptr(),
+                                            None, ws_n.data_ptr(), ws_n.numel(), dev, s_ptr))
+        else:
+            sx.check(sx.lib.ssdx_nms(o_boxes[lo:hi].data_ptr(), d_scores[lo:hi].data_ptr(), n, A_STD, C_STD, K_STD, K_STD,
+                                     0.45, 0.01, o_det[lo:hi].data_ptr(), o_valid[lo:hi].data_ptr(), None,
+                                     ws_n.data_ptr(), ws_n.numel(), dev, s_ptr))
+        if events is not None:
+            events[i].record(ev_stream)
 
     def step_device(events=None, overlap=False):
-        """One step through the C ABI.  overlap=True: the NMS candidate selection (reads only the scores) runs on a
-        second stream while encode and decode run on the first one, as the two input branches of the reference's NMS
-        layer allow (models.py:402-414); ssdx_nms_select + ssdx_nms_finish == ssdx_nms bit for bit."""
+        """One step through the C ABI.  events: single stream, one event after every stage (roofline pass).
+        overlap: the pipelined form described above (P sub-batches on two streams); with P = 1 the NMS candidate
+        selection (reads only the scores) runs on the second stream while encode and decode run on the first one,
+        as the two input branches of the reference's NMS layer allow (models.py:402-414)."""
         nonlocal sp
-        i = 0
         cur = torch.cuda.current_stream(dev)
-        if overlap:
-            side.wait_stream(cur)
-            sx.check(sx.lib.ssdx_nms_select(d_scores.data_ptr(), None, B, A_STD, C_STD, K_STD, K_STD, 0.01,
-                                            ws_nms.data_ptr(), ws_nms.numel(), dev, side.cuda_stream))
-        if events is not None:
-            events[i].record(stream); i += 1
-        if "encode" in stages:
-            sx.check(sx.lib.ssdx_encode(handle, d_boxes.data_ptr(), d_labels.data_ptr(), d_counts.data_ptr(), B, G_STD,
-                                        C_STD, 0.5, std, o_labels.data_ptr(), o_offsets.data_ptr(), None,
-                                        ws_enc.data_ptr(), ws_enc.numel(), sp))
-            if events is not None:
-                events[i].record(stream); i += 1
-        src = o_offsets if "encode" in stages else d_pred_off
-        sx.check(sx.lib.ssdx_decode(dec_layer._anchors.handle, src.data_ptr(), B, std, 0, o_boxes.data_ptr(), sp))
-        if events is not None:
-            events[i].record(stream); i += 1
-        if overlap:
-            cur.wait_stream(side)
-            sx.check(sx.lib.ssdx_nms_finish(o_boxes.data_ptr(), d_scores.data_ptr(), None, B, A_STD, C_STD, K_STD, K_STD,
-                                            0.45, 0.01, o_det.data_ptr(), o_valid.data_ptr(), None, ws_nms.data_ptr(),
-                                            ws_nms.numel(), dev, sp))
-        else:
-            sx.check(sx.lib.ssdx_nms(o_boxes.data_ptr(), d_scores.data_ptr(), B, A_STD, C_STD, K_STD, K_STD, 0.45, 0.01,
-                                     o_det.data_ptr(), o_valid.data_ptr(), None, ws_nms.data_ptr(), ws_nms.numel(),
-                                     dev, sp))
-        if events is not None:
-            events[i].record(stream)
+        if events is not None or not overlap:
+            run_range(0, B, sp, ws_enc, ws_nms, events, stream if events is not None else cur)
+            return
+        if n_pipe == 1:
+            run_range(0, B, sp, ws_enc, ws_nms, None, cur, overlap_side=side)
+            return
+        for st in pipe_streams[1:]:
+            st.wait_stream(cur)
+        for p, (lo, hi) in enumerate(pipe_bounds):
+            st = pipe_streams[p % len(pipe_streams)]
+            run_range(lo, hi, sp if st is None else st.cuda_stream, ws_enc_p[p], ws_nms_p[p], None,
+                      cur if st is None else st)
+        for st in pipe_streams[1:]:
+            cur.wait_stream(st)
 
     # kernels of one step: fused encode (1) + decode (1) + NMS merged pipeline (select_all, fast_all and the two
     # worklist-gated fallback kernels, which exit at once when nothing was handed over)
@@ -483,8 +513,10 @@ def gpu_arm(args, rank, world, local_rank):
                        "l2": "no flush: each step streams %.0f MB (> 126 MB L2)" % (
                            sum(BYTES_PER_IMAGE[s] for s in stages) * B / 1e6),
                        "launch": ("eager" if graph is None else "one CUDA graph per step") + (
-                           "" if args.no_overlap else "; NMS candidate selection (ssdx_nms_select) on a second stream, "
-                           "concurrent with encode/decode, joined before ssdx_nms_finish"),
+                           "" if args.no_overlap else (
+                               "; NMS candidate selection (ssdx_nms_select) on a second stream, concurrent with "
+                               "encode/decode, joined before ssdx_nms_finish" if n_pipe == 1 else
+                               f"; {n_pipe} sub-batches of {B // n_pipe} images pipelined on {n_streams} streams")),
                        "oracle_check": check},
             "roofline": {"bound": "hbm", "kernel": kernels[dom], "stage": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -522,6 +554,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: ssdx_nms instead of select || encode/decode")
+    ap.add_argument("--pipeline", type=int, default=2, help="sub-batches per step pipelined on two streams (1 = off)")
+    ap.add_argument("--pipeline-streams", type=int, default=2)
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks per step of the end-to-end leg (copy/compute overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -539,7 +573,8 @@ def main():
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload",
                args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
                    ["--no-graph"] if args.no_graph else []) + (["--no-overlap"] if args.no_overlap else []) + [
-                   "--e2e-chunks", str(args.e2e_chunks)]
+                   "--e2e-chunks", str(args.e2e_chunks), "--pipeline", str(args.pipeline),
+                   "--pipeline-streams", str(args.pipeline_streams)]
         raise SystemExit(subprocess.call(cmd))
     gpu_arm(args, rank, world, local_rank)
 
