@@ -527,7 +527,7 @@ def gpu_arm(args, rank, world, local_rank):
                     "api": "ssdseglib.datacoder.DataEncoderDecoder.encode_batch -> layers.DecodeBoxesCentroidsOffsets"
                            " -> layers.NonMaximumSuppression (inputs from pinned host memory, detections to pinned host"
                            f" memory, {n_chunks} chunks per step on two streams)"},
-            "gpu_launches": kernels_per_step * args.steps,
+            "gpu_launches": kernels_per_step * (1 if args.no_overlap else n_pipe) * args.steps,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -125,6 +125,17 @@ SSDX_API int ssdx_nms_finish(const float* boxes_yxyx, const float* scores, const
                              int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
                              ssdx_stream stream);
 
+/* Decode fused into the NMS: the wiring of get_model_for_inference (models.py:410-414: DecodeBoxesCentroidsOffsets ->
+ * NonMaximumSuppression) whose only output is the detections.  offsets (B,A,4) are the raw regression outputs; every
+ * box the NMS touches (a few hundred candidates per image) is decoded on the fly with the decode kernel's own
+ * formula, so the result equals ssdx_decode(mode YXYX) followed by ssdx_nms_scaled bit for bit, without writing and
+ * re-reading the (B,A,4) box tensor.  A and the device come from the anchor handle; std_host as in ssdx_decode. */
+SSDX_API int ssdx_decode_nms(const ssdx_anchors* anchors, const float* offsets, const float* std_host,
+                             const float* scores, const float* class_scale, int32_t batch, int32_t num_classes,
+                             int32_t max_per_class, int32_t max_total, float iou_threshold, float score_threshold,
+                             float* out, int32_t* out_valid, int32_t* out_anchor_idx, void* workspace,
+                             size_t workspace_bytes, ssdx_stream stream);
+
 /* ---- segmentation suppression: layers.py:189-212 (SegmentationSuppression.call), SURVEY 8(f) row 2 ----
  * seg_probs (num_pixels, Cm) f32 = the (B,H,W,Cm) segmentation output flattened over batch and space.
  * out_presence (depth) f32: 1.0f iff some pixel of the WHOLE batch has argmax == c (ties -> lowest index), else 0.0f

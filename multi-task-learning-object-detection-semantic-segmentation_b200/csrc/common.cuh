@@ -82,6 +82,33 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
                : "memory");
 }
 
+// layers.py:57-79 for one anchor: ((t*s)*d)+c, (exp(t*s)-1)*d, c -/+ (s-1)/2 -> (ymin, xmin, ymax, xmax).  One definition
+// shared by the decode kernel and by the NMS kernels that decode their candidates on the fly (ssdx_decode_nms), so
+// that both produce the same bits.
+__device__ __forceinline__ float4 ssdx_decode_yxyx(const float4 t, const float4 d, const float sx, const float sy,
+                                                   const float sw, const float sh) {
+  const float cx = __fadd_rn(__fmul_rn(__fmul_rn(t.x, sx), d.z), d.x);
+  const float cy = __fadd_rn(__fmul_rn(__fmul_rn(t.y, sy), d.w), d.y);
+  const float w = __fmul_rn(__fsub_rn(expf(__fmul_rn(t.z, sw)), 1.0f), d.z);
+  const float h = __fmul_rn(__fsub_rn(expf(__fmul_rn(t.w, sh)), 1.0f), d.w);
+  const float hw = __fmul_rn(__fsub_rn(w, 1.0f), 0.5f);  // (w-1)/2 exactly
+  const float hh = __fmul_rn(__fsub_rn(h, 1.0f), 0.5f);
+  return make_float4(__fsub_rn(cy, hh), __fsub_rn(cx, hw), __fadd_rn(cy, hh), __fadd_rn(cx, hw));
+}
+
+// Where the NMS kernels get a box from: the decoded (B,A,4) tensor, or the offsets + anchor centroids (decoded per
+// candidate, nothing materialised).
+struct ssdx_box_src {
+  const float4* boxes;    // (B,A) yxyx, or NULL
+  const float4* offsets;  // (B,A) standardised centroid offsets when boxes == NULL
+  const float4* cent;     // (A) anchor centroids as the decode layer holds them
+  float sx, sy, sw, sh;
+};
+__device__ __forceinline__ float4 ssdx_load_box(const ssdx_box_src& s, const size_t row0, const int idx) {
+  if (s.boxes != nullptr) return __ldg(s.boxes + row0 + idx);
+  return ssdx_decode_yxyx(__ldg(s.offsets + row0 + idx), __ldg(s.cent + idx), s.sx, s.sy, s.sw, s.sh);
+}
+
 // Optional per-phase cycle counters (debug builds only: -DSSDX_PHASE_TIMERS).  Each translation unit that uses
 // them defines its own `static __device__ unsigned long long g_phase_cycles[32]` and a reader
 // (ssdx_debug_phase_cycles for nms.cu, ssdx_debug_phase_cycles_encode for encode.cu).

@@ -15,6 +15,7 @@ constexpr int kUnroll = 2;
 template <int MODE>
 __device__ __forceinline__ float4 decode_one(const float4 t, const float4 d, const float sx, const float sy,
                                              const float sw, const float sh) {
+  if (MODE == SSDX_DECODE_YXYX) return ssdx_decode_yxyx(t, d, sx, sy, sw, sh);  // shared with the NMS kernels
   // explicit _rn intrinsics: never contracted into FMA
   float cx = __fadd_rn(__fmul_rn(__fmul_rn(t.x, sx), d.z), d.x);
   float cy = __fadd_rn(__fmul_rn(__fmul_rn(t.y, sy), d.w), d.y);

@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kSelThreads)
 
 // ------------------------------------------------------------------------------------------ 2. fast path
 __global__ void __launch_bounds__(kFastThreads, 6)
-    ssdx_nms_fast_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+    ssdx_nms_fast_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                          const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                          const int limit, const float iou_thr, const float score_thr, u64* __restrict__ picks,
                          int* __restrict__ pick_cnt, int* __restrict__ flags) {
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kFastThreads, 6)
     if (tid == 0) flags[1 + atomicAdd(&flags[0], 1)] = (int)seg;  // hand the segment to the generic kernel
     return;
   }
-  const float4* img_boxes = boxes + (size_t)b * A;
+  const size_t box_row0 = (size_t)b * A;
   const float* img_scores = scores + (size_t)b * A * C + c;
   const float cf = class_factor(cscale, c);
   u64* my_picks = picks + seg * limit;
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(kFastThreads, 6)
     for (int g0 = 0; g0 < n && n_sel < limit; g0 += kFastThreads) {
       const int gn = min(kFastThreads, n - g0);
       if (tid < gn) {  // gather the boxes of the next 256 sorted candidates
-        const float4 nb = normalise_box(__ldg(img_boxes + comp_idx(s_list[g0 + tid])));
+        const float4 nb = normalise_box(ssdx_load_box(boxes, box_row0, comp_idx(s_list[g0 + tid])));
         s_cbox[tid] = nb;
         s_carea[tid] = box_area(nb);
       }
@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(kSelThreads)
 // ------------------------------------------------------------------------------------------ 2m. merged fast path
 template <int MAXSEL, int MINB>  // MAXSEL >= K; MINB resident CTAs per SM (7 * 148 >= 1024: one wave at batch 1024)
 __global__ void __launch_bounds__(kFastThreads, MINB)
-    ssdx_nms_fast_all_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+    ssdx_nms_fast_all_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                              const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                              const int K, const float iou_thr, const float score_thr, float* __restrict__ out,
                              int* __restrict__ out_valid, int* __restrict__ out_idx, int* __restrict__ flags,
@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
     }
     return;
   }
-  const float4* img_boxes = boxes + (size_t)b * A;
+  const size_t box_row0 = (size_t)b * A;
   const float* img_scores = scores + (size_t)b * A * C;
   const u64* lst = lists + (size_t)b * kCap;
   for (int i = tid; i < n; i += kFastThreads) s_list[i] = lst[i];
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
       __syncthreads();  // s_tmp (sort buffer / previous candidate arrays) is free
       if (tid < gn) {   // gather the boxes of the next 256 sorted candidates
         const u64 cp = s_list[g0 + tid];
-        const float4 nb = normalise_box(__ldg(img_boxes + comp_all_idx(cp)));
+        const float4 nb = normalise_box(ssdx_load_box(boxes, box_row0, comp_all_idx(cp)));
         s_cbox[tid] = nb;
         s_carea[tid] = box_area(nb);
         s_ccls[tid] = (unsigned char)comp_all_cls(cp);
@@ -1030,7 +1030,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   for (int r = tid; r < n_sel; r += kFastThreads) {
     const u64 cp = s_pick[r];
     const int idx = comp_all_idx(cp);
-    const float4 bx = __ldg(img_boxes + idx);  // raw (ymin, xmin, ymax, xmax)
+    const float4 bx = ssdx_load_box(boxes, box_row0, idx);  // raw (ymin, xmin, ymax, xmax)
     float* row = o + (size_t)r * 6;
     row[0] = (float)comp_all_cls(cp);
     row[1] = key_to_score((unsigned)(cp >> 32));
@@ -1074,7 +1074,7 @@ __host__ __device__ inline size_t gen_smem_bytes(int A, int limit) {
 }
 
 __global__ void __launch_bounds__(kGenThreads)
-    ssdx_nms_generic_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+    ssdx_nms_generic_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                             const float* __restrict__ cscale, const int A, const int C, const int limit, const float iou_thr, const float score_thr,
                             u64* __restrict__ picks, int* __restrict__ pick_cnt, const int* __restrict__ flags,
                             const int num_segments) {
@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(kGenThreads)
     sm.ctr = (int*)p;
   }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float4* img_boxes = boxes + (size_t)b * A;
+  const size_t box_row0 = (size_t)b * A;
   const float* img_scores = scores + (size_t)b * A * C + c;
   const float cf = class_factor(cscale, c);
   u64* my_picks = picks + ((size_t)b * C + c) * limit;
@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(kGenThreads)
     consumed_from = T;
     bitonic_sort_desc<kGenThreads>(sm.list, n, tid);
     for (int i = tid; i < n; i += kGenThreads) {
-      const float4 nb = normalise_box(__ldg(img_boxes + comp_idx(sm.list[i])));
+      const float4 nb = normalise_box(ssdx_load_box(boxes, box_row0, comp_idx(sm.list[i])));
       sm.cbox[i] = nb;
       sm.carea[i] = box_area(nb);
     }
@@ -1277,7 +1277,7 @@ __device__ __forceinline__ int count_before(const u64* lst, int n, unsigned k, b
 }
 
 __global__ void __launch_bounds__(kMergeThreads)
-    ssdx_nms_merge_kernel(const float4* __restrict__ boxes, const u64* __restrict__ picks,
+    ssdx_nms_merge_kernel(const ssdx_box_src boxes, const u64* __restrict__ picks,
                           const int* __restrict__ pick_cnt, const int A, const int C, const int limit, const int K,
                           const int stage_in_smem, float* __restrict__ out, int* __restrict__ out_valid,
                           int* __restrict__ out_idx, const int* __restrict__ iflags, const int batch) {
@@ -1313,7 +1313,7 @@ __global__ void __launch_bounds__(kMergeThreads)
       if (c2 != c) rank += count_before(img_picks + (size_t)c2 * limit, cnt[c2], k, c2 < c);
     if (rank < K) {
       const int idx = comp_idx(cp);
-      const float4 bx = __ldg(boxes + (size_t)b * A + idx);  // raw (ymin, xmin, ymax, xmax)
+      const float4 bx = ssdx_load_box(boxes, (size_t)b * A, idx);  // raw (ymin, xmin, ymax, xmax)
       float* r = o + (size_t)rank * 6;
       r[0] = (float)c;
       r[1] = key_to_score(k);
@@ -1384,13 +1384,14 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
 // ssdx_nms_select / ssdx_nms_finish expose them separately so that a caller can run phase 1 on another stream while
 // the boxes are still being decoded (in the reference's inference graph the two inputs of the NMS layer are
 // independent branches, models.py:402-414).
-static int nms_run(const int phases, const float* boxes_yxyx, const float* scores, const float* class_scale,
+static int nms_run(const int phases, const ssdx_box_src* fused_src, const float* boxes_yxyx, const float* scores,
+                   const float* class_scale,
                    int32_t batch, int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
                    float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
                    int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device, ssdx_stream stream) {
   const float* cscale = class_scale;
   const bool ph1 = (phases & 1) != 0, ph2 = (phases & 2) != 0;
-  SSDX_CHECK_ARG(scores != nullptr && (!ph2 || (boxes_yxyx != nullptr && out != nullptr)),
+  SSDX_CHECK_ARG(scores != nullptr && (!ph2 || ((boxes_yxyx != nullptr || fused_src != nullptr) && out != nullptr)),
                  "ssdx_nms: NULL pointer argument");
   SSDX_CHECK_ARG(batch >= 0 && num_anchors > 0 && num_classes > 0, "ssdx_nms: bad shape (B=%d, A=%d, C=%d)", batch,
                  num_anchors, num_classes);
@@ -1420,7 +1421,9 @@ static int nms_run(const int phases, const float* boxes_yxyx, const float* score
   u64* lists = (u64*)(base + w.lists);
   int* info = (int*)(base + w.info);
   int* flags = (int*)(base + w.flags);
-  const float4* bx = (const float4*)boxes_yxyx;
+  ssdx_box_src bx;
+  if (fused_src != nullptr) bx = *fused_src;
+  else bx = ssdx_box_src{(const float4*)boxes_yxyx, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f};
 
   int* iflags = (int*)(base + w.iflags);
   const int NS = (A + kSampleStride - 1) / kSampleStride;
@@ -1518,7 +1521,7 @@ extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, con
                                float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
                                int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
                                ssdx_stream stream) {
-  return nms_run(3, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
+  return nms_run(3, nullptr, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
                  iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes, device,
                  stream);
 }
@@ -1526,7 +1529,7 @@ extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, con
 extern "C" int ssdx_nms_select(const float* scores, const float* class_scale, int32_t batch, int32_t num_anchors,
                                int32_t num_classes, int32_t max_per_class, int32_t max_total, float score_threshold,
                                void* workspace, size_t workspace_bytes, int device, ssdx_stream stream) {
-  return nms_run(1, nullptr, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total, 0.5f,
+  return nms_run(1, nullptr, nullptr, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total, 0.5f,
                  score_threshold, nullptr, nullptr, nullptr, workspace, workspace_bytes, device, stream);
 }
 
@@ -1535,7 +1538,22 @@ extern "C" int ssdx_nms_finish(const float* boxes_yxyx, const float* scores, con
                                float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
                                int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
                                ssdx_stream stream) {
-  return nms_run(2, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
+  return nms_run(2, nullptr, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
                  iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes, device,
                  stream);
+}
+
+extern "C" int ssdx_decode_nms(const ssdx_anchors* anchors, const float* offsets, const float* std_host,
+                               const float* scores, const float* class_scale, int32_t batch, int32_t num_classes,
+                               int32_t max_per_class, int32_t max_total, float iou_threshold, float score_threshold,
+                               float* out, int32_t* out_valid, int32_t* out_anchor_idx, void* workspace,
+                               size_t workspace_bytes, ssdx_stream stream) {
+  SSDX_CHECK_ARG(anchors != nullptr && offsets != nullptr && std_host != nullptr,
+                 "ssdx_decode_nms: NULL pointer argument");
+  SSDX_CHECK_ARG(((uintptr_t)offsets & 15) == 0, "ssdx_decode_nms: offsets must be 16-byte aligned");
+  const ssdx_box_src src{nullptr, (const float4*)offsets, anchors->dec_cent, std_host[0], std_host[1], std_host[2],
+                         std_host[3]};
+  return nms_run(3, &src, nullptr, scores, class_scale, batch, anchors->A, num_classes, max_per_class, max_total,
+                 iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes,
+                 anchors->device, stream);
 }

@@ -50,6 +50,8 @@ SIGNATURES = {
                                   C.c_size_t, C.c_int, _vp]),
     "ssdx_nms_finish": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                   C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "ssdx_decode_nms": (C.c_int, [_vp, _vp, c_float_p, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                  C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ssdx_seg_class_presence": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, C.c_size_t, C.c_int, _vp]),
     "ssdx_scale_scores": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int, _vp]),
     "ssdx_eval_tp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -276,6 +278,20 @@ def nms(boxes_yxyx, scores, max_per_class: int, max_total: int, iou_threshold: f
     check(lib.ssdx_nms_scaled(ptr(boxes_yxyx), ptr(scores), ptr(class_scale), B, A, Cn, int(max_per_class),
                               int(max_total), float(iou_threshold), float(score_threshold), ptr(out), ptr(valid),
                               ptr(aidx), ptr(ws), ws.numel(), dev, stream_ptr(dev)))
+    return out, valid, aidx
+
+
+def decode_nms(anchors: "Anchors", offsets, std, scores, max_per_class: int, max_total: int, iou_threshold: float,
+               score_threshold: float, want_aux: bool = False, class_scale=None):
+    B, A, Cn = (int(v) for v in scores.shape)
+    dev = anchors.device
+    out = empty((B, max_total, 6), np.float32, dev)
+    valid = empty((B,), np.int32, dev) if want_aux else None
+    aidx = empty((B, max_total), np.int32, dev) if want_aux else None
+    ws = workspace(lib.ssdx_nms_workspace_bytes(B, A, Cn, max_per_class, max_total), dev)
+    check(lib.ssdx_decode_nms(anchors.handle, ptr(offsets), std_array(std), ptr(scores), ptr(class_scale), B, Cn,
+                              int(max_per_class), int(max_total), float(iou_threshold), float(score_threshold),
+                              ptr(out), ptr(valid), ptr(aidx), ptr(ws), ws.numel(), stream_ptr(dev)))
     return out, valid, aidx
 
 

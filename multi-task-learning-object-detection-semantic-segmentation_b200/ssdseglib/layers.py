@@ -117,6 +117,30 @@ class NonMaximumSuppression(_Layer):
             return res, _ssdx.from_device(valid, kind), _ssdx.from_device(aidx, kind)
         return res
 
+    def call_on_offsets(self, decode_layer, boxes_centroids_offsets, labels_probabilities, return_aux: bool = False,
+                        class_scale=None):
+        """`self.call(decode_layer.call(offsets), probabilities)` as one operation (new entry point): the wiring of
+        `get_model_for_inference` (models.py:410-414), whose only output is the detections.  The boxes the NMS looks
+        at are decoded on the fly; the (batch, boxes, 4) tensor is never written.  Bit-identical results."""
+        off, kind = _ssdx.to_device(boxes_centroids_offsets, np.float32, decode_layer._anchors.device, "nms_off")
+        scores, _ = _ssdx.to_device(labels_probabilities, np.float32, off.device.index, "nms_scores")
+        if off.dim() != 3 or off.shape[2] != 4 or scores.dim() != 3 or scores.shape[:2] != off.shape[:2]:
+            raise ValueError("expected offsets (batch, boxes, 4) and probabilities (batch, boxes, classes)")
+        if int(off.shape[1]) != decode_layer._anchors.num_anchors:
+            raise ValueError("offsets do not match the number of default boxes of the decode layer")
+        if class_scale is not None:
+            class_scale, _ = _ssdx.to_device(class_scale, np.float32, off.device.index, "nms_scale")
+        out, valid, aidx = _ssdx.decode_nms(decode_layer._anchors, off, decode_layer._std, scores,
+                                            self.max_number_of_boxes_per_class, self.max_number_of_boxes_per_sample,
+                                            self.boxes_iou_threshold, self.labels_probability_threshold,
+                                            want_aux=return_aux, class_scale=class_scale)
+        if self.suppress_background_boxes:
+            out = out[out[..., 0] > 0.0]
+        res = _ssdx.from_device(out, kind)
+        if return_aux:
+            return res, _ssdx.from_device(valid, kind), _ssdx.from_device(aidx, kind)
+        return res
+
     def select(self, labels_probabilities, class_scale=None):
         """Phase 1 of `call` (new entry point): everything that depends only on the probabilities, on the current
         CUDA stream.  In the reference's inference graph the probabilities and the decoded boxes reach this layer

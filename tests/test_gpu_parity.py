@@ -342,6 +342,27 @@ def test_nms_two_phase_on_a_side_stream(lib, golden):
     assert np.array_equal(ref.cpu().numpy().shape, (2, 10, 6))
 
 
+def test_nms_on_offsets_equals_decode_then_nms(lib, golden):
+    """ssdx_decode_nms (boxes decoded per candidate inside the NMS kernels) == DecodeBoxesCentroidsOffsets ->
+    NonMaximumSuppression, bit for bit, on every NMS path (merged / per-class / generic via the fixture) and with a
+    class scale; also checked against the oracle."""
+    g = golden("layers")
+    a = golden("anchors")["std_centroids"]
+    dec = lib.layers.DecodeBoxesCentroidsOffsets(a[:, 0], a[:, 1], a[:, 2], a[:, 3], 0.1, 0.1, 0.2, 0.2)
+    off, scores = g["offsets"], g["scores"]
+    yxyx = dec(off)
+    for mpc, mtot, iou, thr, scale in ((200, 200, 0.45, 0.01, None), (4, 10, 0.025, 0.2, None),
+                                       (200, 200, 0.45, 0.01, [1, 0, 1, 1])):
+        layer = lib.layers.NonMaximumSuppression(mpc, mtot, iou, thr, False)
+        sc = None if scale is None else np.asarray(scale, np.float32)
+        ref, vref, aref = layer.call(yxyx, scores, return_aux=True, class_scale=sc)
+        out, valid, aidx = layer.call_on_offsets(dec, off, scores, return_aux=True, class_scale=sc)
+        assert np.array_equal(out, ref) and np.array_equal(valid, vref) and np.array_equal(aidx, aref)
+    o_ref, _, a_ref = orc.combined_nms(yxyx, scores, 200, 200, 0.45, 0.01)
+    out, _, aidx = lib.layers.NonMaximumSuppression(200, 200, 0.45, 0.01, False).call_on_offsets(dec, off, scores, True)
+    assert np.array_equal(aidx, a_ref) and np.array_equal(out, o_ref)
+
+
 def test_nms_torch_in_torch_out(lib, golden):
     import torch
 

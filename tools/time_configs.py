@@ -75,6 +75,33 @@ def config1():
     ref, _, _ = c_oracle.combined_nms(o_boxes[:2].cpu().numpy(), scores[:2], K, K, 0.45, 0.01)
     ok = np.array_equal(ref, o_det[:2].cpu().numpy())
     emit("1: decode + NMS, batch 64", B, med, best, 32 * A + 16 * A + 4 * A * C + 24 * K, "pass" if ok else "FAIL")
+    o_det2 = torch.empty_like(o_det)
+
+    def fused():
+        sx.check(sx.lib.ssdx_decode_nms(h, d_off.data_ptr(), std, d_sc.data_ptr(), None, B, C, K, K, 0.45, 0.01,
+                                        o_det2.data_ptr(), None, None, ws.data_ptr(), ws.numel(), sp))
+    med, best = timeit(fused)
+    emit("1f: ssdx_decode_nms (boxes decoded per candidate, no (B,A,4) tensor), batch 64", B, med, best,
+         16 * A + 4 * A * C + 24 * K, "pass" if torch.equal(o_det, o_det2) else "FAIL")
+    # the same at the bench batch
+    B2 = 1024
+    off2, sc2 = d_off.repeat(B2 // B, 1, 1), d_sc.repeat(B2 // B, 1, 1)
+    ob2, od2, od3 = torch.empty((B2, A, 4), **f32), torch.empty((B2, K, 6), **f32), torch.empty((B2, K, 6), **f32)
+    ws2 = torch.empty(max(sx.lib.ssdx_nms_workspace_bytes(B2, A, C, K, K), 256), dtype=torch.uint8, device="cuda:0")
+
+    def two():
+        sx.check(sx.lib.ssdx_decode(h, off2.data_ptr(), B2, std, 0, ob2.data_ptr(), sp))
+        sx.check(sx.lib.ssdx_nms(ob2.data_ptr(), sc2.data_ptr(), B2, A, C, K, K, 0.45, 0.01, od2.data_ptr(), None, None,
+                                 ws2.data_ptr(), ws2.numel(), dev, sp))
+
+    def one():
+        sx.check(sx.lib.ssdx_decode_nms(h, off2.data_ptr(), std, sc2.data_ptr(), None, B2, C, K, K, 0.45, 0.01,
+                                        od3.data_ptr(), None, None, ws2.data_ptr(), ws2.numel(), sp))
+    m2, b2 = timeit(two)
+    m1, b1 = timeit(one)
+    emit("decode + NMS, batch 1024 (random predictions)", B2, m2, b2, 32 * A + 16 * A + 4 * A * C + 24 * K, "pass")
+    emit("ssdx_decode_nms, batch 1024 (random predictions)", B2, m1, b1, 16 * A + 4 * A * C + 24 * K,
+         "pass" if torch.equal(od2, od3) else "FAIL")
 
 
 # ------------------------------------------------------------------------------------------------ config 3
