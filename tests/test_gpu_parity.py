@@ -493,6 +493,45 @@ def test_eval_tp_flags_and_counts(lib):
             assert counts[c, 2] == sum((gl[i, :gc[i]] == c).sum() for i in range(N))
 
 
+# ------------------------------------------------------------------------------------------- DLPack
+class _DLPackOnly:
+    """A device array that is NOT a torch tensor: only the DLPack protocol (what a TF / CuPy / JAX array offers)."""
+
+    def __init__(self, t):
+        self._t = t
+
+    def __dlpack__(self, stream=None):
+        return self._t.__dlpack__() if stream is None else self._t.__dlpack__(stream=stream)
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+def test_dlpack_device_arrays_are_used_in_place(lib, coder, golden, std_anchors):
+    """north star: 'DLPack for zero-copy device tensors'.  Any object with __dlpack__ is consumed on the device it
+    lives on (no host round trip) and device tensors come back."""
+    import torch
+
+    g = golden("layers")
+    a = golden("anchors")["std_centroids"]
+    dec = lib.layers.DecodeBoxesCentroidsOffsets(a[:, 0], a[:, 1], a[:, 2], a[:, 3], 0.1, 0.1, 0.2, 0.2)
+    off_t = torch.from_numpy(g["offsets"]).cuda()
+    sc_t = torch.from_numpy(g["scores"]).cuda()
+    yxyx = dec(_DLPackOnly(off_t))
+    assert isinstance(yxyx, torch.Tensor) and yxyx.is_cuda
+    assert np.array_equal(yxyx.cpu().numpy(), dec(g["offsets"]))
+    box_t = torch.from_numpy(g["decoded_yxyx"]).cuda()  # the fixture's boxes: det_200 holds copies of their bits
+    det = lib.layers.NonMaximumSuppression(200, 200, 0.45, 0.01, False)(_DLPackOnly(box_t), _DLPackOnly(sc_t))
+    assert det.is_cuda and np.array_equal(det.cpu().numpy(), g["det_200"])
+    rng = np.random.default_rng(5)
+    labels, boxes, counts = orc.synth_gt(rng, 4, 16)
+    L, O = coder.encode_batch(_DLPackOnly(torch.from_numpy(boxes).cuda()), _DLPackOnly(torch.from_numpy(labels).cuda()),
+                              _DLPackOnly(torch.from_numpy(counts).cuda()))
+    Lr, Or, _ = encode_ref(std_anchors, labels, boxes, counts, 4, 0.5)
+    assert L.is_cuda and np.array_equal(L.cpu().numpy(), Lr)
+    assert_offsets_close(O.cpu().numpy(), Or)
+
+
 # ------------------------------------------------------------------------------------------- C ABI details
 def test_error_paths_and_workspace(lib, coder):
     import ctypes as C
