@@ -493,6 +493,30 @@ def test_eval_tp_flags_and_counts(lib):
             assert counts[c, 2] == sum((gl[i, :gc[i]] == c).sum() for i in range(N))
 
 
+# ------------------------------------------------------------------------------------------- determinism
+def test_repeated_runs_are_bit_identical(lib, coder, std_anchors, golden):
+    """Races would show up as run-to-run differences: the fused encode patches positives over TMA bulk stores, the
+    NMS appends candidates with atomics in arbitrary order, the tiled encode publishes arg-max results across CTAs.
+    40 repetitions of each at the bench batch size must give the same bits."""
+    import torch
+
+    rng = np.random.default_rng(7)
+    labels, boxes, counts = orc.synth_gt(rng, 1024, 16)
+    gb, gl, gc = (torch.from_numpy(x).cuda() for x in (boxes, labels, counts))
+    L0, O0 = coder.encode_batch(gb, gl, gc)
+    scores = (0.9 * L0 + 0.1 * torch.softmax(torch.randn(L0.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(3)), -1))
+    a = golden("anchors")["std_centroids"]
+    dec = lib.layers.DecodeBoxesCentroidsOffsets(a[:, 0], a[:, 1], a[:, 2], a[:, 3], *STD)
+    nms = lib.layers.NonMaximumSuppression(200, 200, 0.45, 0.01, False)
+    yx0 = dec(O0)
+    D0 = nms(yx0, scores)
+    for _ in range(40):
+        L, O = coder.encode_batch(gb, gl, gc)
+        assert torch.equal(L, L0) and torch.equal(O, O0)
+        assert torch.equal(nms(dec(O), scores), D0)
+        assert torch.equal(nms.call_on_offsets(dec, O, scores), D0)
+
+
 # ------------------------------------------------------------------------------------------- DLPack
 class _DLPackOnly:
     """A device array that is NOT a torch tensor: only the DLPack protocol (what a TF / CuPy / JAX array offers)."""
