@@ -1445,7 +1445,7 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
 
   // ---- merged pipeline: one list / sort / greedy pass per image ----
   const bool merged = !force_generic && !force_perclass && max_per_class >= max_total && C <= 256 &&
-                      A <= (1 << 24) && max_total <= kFastMaxSel;
+                      A <= (1 << 24) && (long long)A * C < (1ll << 31) && max_total <= kFastMaxSel;
   if (merged) {
     if (ph1) {
       if (vec4)
