@@ -163,6 +163,14 @@ SSDX_API int ssdx_iou_pred_vs_true(const int32_t* pred_label, const float* pred_
                                    const float* gt_xyxy, int32_t num_pred, int32_t num_gt, float* out, int device,
                                    ssdx_stream stream);
 
+/* ---- training-time box metric: metrics.py:53-173 (jaccard_iou_bounding_boxes), SURVEY 8(f) row 3 ----
+ * y_true, y_pred (B,A,4) f32 standardised centroid offsets (y_true = encode output, background rows all zero);
+ * out (B) f32 = mean over the non-background anchors of IoU(decoded prediction, decoded target) with the reference's
+ * arithmetic (width/height clamped at 0, +1 pixel convention, epsilon 1e-7); NaN for an image without positives,
+ * as the reference (0 / 0).  Uses the decode-side centroids of the anchor handle; std_host as in ssdx_decode. */
+SSDX_API int ssdx_metric_iou_boxes(const ssdx_anchors* anchors, const float* y_true, const float* y_pred, int32_t batch,
+                                   const float* std_host, float* out, ssdx_stream stream);
+
 /* ---- GT ingest (host): datacoder.py:194-203, evaluators.py:111-121 ----
  * Parses `label,xmin,ymin,xmax,ymax` records from `text` (host).  crlf_only != 0 reproduces datacoder.py:195
  * (records split on "\r\n" only); 0 accepts "\n", "\r\n" (csv.reader).  flip_width > 0 applies the horizontal flip

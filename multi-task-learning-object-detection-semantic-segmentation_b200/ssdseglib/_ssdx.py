@@ -57,6 +57,7 @@ SIGNATURES = {
     "ssdx_eval_tp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, _vp, _vp, C.c_int, _vp]),
     "ssdx_iou_pred_vs_true": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
+    "ssdx_metric_iou_boxes": (C.c_int, [_vp, _vp, _vp, C.c_int32, c_float_p, _vp, _vp]),
     "ssdx_parse_gt_csv": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_float, c_i32_p, c_float_p, C.c_int32,
                                     c_i32_p]),
     "ssdx_read_gt_csv_batch": (C.c_int, [C.POINTER(C.c_char_p), C.c_int32, C.c_int, C.POINTER(C.c_uint8), C.c_float,
@@ -334,6 +335,14 @@ def nms_finish(sel: NmsSelection, boxes_yxyx, iou_threshold: float, want_aux: bo
                               sel.max_total, float(iou_threshold), sel.score_threshold, ptr(out), ptr(valid),
                               ptr(aidx), ptr(sel.ws), sel.ws.numel(), dev, stream_ptr(dev)))
     return out, valid, aidx
+
+
+def metric_iou_boxes(anchors: "Anchors", y_true, y_pred, std):
+    B = int(y_true.shape[0])
+    out = empty((B,), np.float32, anchors.device)
+    check(lib.ssdx_metric_iou_boxes(anchors.handle, ptr(y_true), ptr(y_pred), B, std_array(std), ptr(out),
+                                    stream_ptr(anchors.device)))
+    return out
 
 
 def seg_class_presence(seg_probs, depth: int = 4):

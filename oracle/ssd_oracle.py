@@ -411,6 +411,38 @@ def segmentation_suppression(segmentation_mask: np.ndarray, labels_probabilities
 
 
 # --------------------------------------------------------------------------
+# training-time box IoU metric (metrics.py:53-173)
+# --------------------------------------------------------------------------
+def metric_iou_boxes(y_true, y_pred, anchors_cxcywh, std=(0.1, 0.1, 0.2, 0.2)) -> np.ndarray:
+    """metrics.py:125-171 statement by statement: (batch,) mean IoU of the non-background anchors."""
+    y_true = np.asarray(y_true, F32)
+    y_pred = np.asarray(y_pred, F32)
+    a = np.asarray(anchors_cxcywh, F32)
+    sx, sy, sw, sh = (F32(s) for s in std)
+    nb = (np.sum(np.abs(y_true), axis=-1, dtype=F32) > 0).astype(F32)            # :138-139
+
+    def dec(t):                                                                   # :79-121
+        cx = (t[..., 0] * sx * a[:, 2] + a[:, 0]) * nb
+        cy = (t[..., 1] * sy * a[:, 3] + a[:, 1]) * nb
+        w = np.maximum(F32(0), (np.exp(t[..., 2] * sw) - F32(1)) * a[:, 2]) * nb
+        h = np.maximum(F32(0), (np.exp(t[..., 3] * sh) - F32(1)) * a[:, 3]) * nb
+        x0 = (cx - (w - F32(1)) / F32(2)) * nb
+        y0 = (cy - (h - F32(1)) / F32(2)) * nb
+        x1 = (cx + (w - F32(1)) / F32(2)) * nb
+        y1 = (cy + (h - F32(1)) / F32(2)) * nb
+        return x0, y0, x1, y1, w, h
+
+    px0, py0, px1, py1, pw, ph = dec(y_pred)
+    tx0, ty0, tx1, ty1, tw, th = dec(y_true)
+    wi = np.maximum(F32(0), np.minimum(tx1, px1) - np.maximum(tx0, px0) + F32(1)) * nb
+    hi = np.maximum(F32(0), np.minimum(ty1, py1) - np.maximum(ty0, py0) + F32(1)) * nb
+    ai, at, ap = wi * hi, tw * th, pw * ph
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = ai / (ap + at - ai + F32(1e-7))
+        return (np.sum(iou, axis=-1, dtype=F32) / np.sum(nb, axis=-1, dtype=F32)).astype(F32)
+
+
+# --------------------------------------------------------------------------
 # a17-a18: detection evaluation (evaluators.py:6-187)  [P7]
 # --------------------------------------------------------------------------
 def iou_pred_vs_true(labels_pred, boxes_pred, labels_true, boxes_true) -> np.ndarray:

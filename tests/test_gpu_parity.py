@@ -451,6 +451,30 @@ def test_nms_class_scale_equals_nms_of_suppressed_scores(lib, golden):
             assert np.array_equal(a1, a2) and np.array_equal(v1, v2) and np.array_equal(fused, ref)
 
 
+# ------------------------------------------------------------------------------------------- training-time box metric
+def test_box_iou_metric_golden_and_full_batch(lib, golden, std_anchors, coder):
+    """metrics.jaccard_iou_bounding_boxes: the fused kernel against the fixture made by the reference's own file, and
+    at batch 1024 against the oracle (fp32 sum order differs: 1e-5 relative, the north star's fp32 tolerance)."""
+    g = golden("metric")
+    cent = golden("anchors")["std_centroids"]
+    metric = lib.metrics.jaccard_iou_bounding_boxes(cent[:, 0], cent[:, 1], cent[:, 2], cent[:, 3], STD)
+    got = metric(g["y_true"], g["y_pred"])
+    assert got.shape == (6,) and got.dtype == np.float32
+    np.testing.assert_allclose(got, g["value"], rtol=RTOL)
+    rng = np.random.default_rng(8)
+    labels, boxes, counts = orc.synth_gt(rng, 1024, 16)
+    counts[5] = 0                                                        # no positives -> 0 / 0 = NaN, as the reference
+    _, y_true = coder.encode_batch(boxes, labels, counts)
+    y_pred = (y_true + rng.normal(0, 0.5, y_true.shape)).astype(np.float32)
+    got = metric(y_true, y_pred)
+    ref = orc.metric_iou_boxes(y_true, y_pred, cent, STD)
+    assert np.isnan(got[5]) and np.isnan(ref[5])
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=RTOL)
+    with pytest.raises(ValueError):
+        metric(y_true[:, :100], y_pred[:, :100])
+
+
 # ------------------------------------------------------------------------------------------- eval
 def test_eval_golden(lib, golden, tmp_path):
     g = golden("eval")

@@ -171,3 +171,12 @@ def test_segmentation_suppression_matches_reference_source(golden):
         assert pres.tolist() == expect
         assert np.array_equal(orc.segmentation_suppression(g[case + "_mask"], g[case + "_probs"]),
                               g[case + "_suppressed"])
+
+
+def test_box_iou_metric_matches_reference_source(golden, std_anchors):
+    """the oracle against metrics.jaccard_iou_bounding_boxes executed from the reference's file."""
+    g = golden("metric")
+    cent = np.stack(orc.corners_to_centroids(*[std_anchors[:, i] for i in range(4)]), 1).astype(np.float32)
+    got = orc.metric_iou_boxes(g["y_true"], g["y_pred"], cent, STD)
+    np.testing.assert_allclose(got, g["value"], rtol=1e-6)
+    assert abs(float(got[2]) - 1.0) < 1e-6      # perfect predictions

@@ -35,3 +35,17 @@ scores = torch.rand((1024, 9600, 4), generator=g, device="cuda"); out = torch.em
 us = timeit(lambda: sx.check(sx.lib.ssdx_scale_scores(scores.data_ptr(), 1024 * 9600, 4, pres.data_ptr(), out.data_ptr(), 0, sp)))
 print(json.dumps({"case": "materialised product (B,A,C) * presence, B=1024", "us": round(us, 1), "GBps": 2 * scores.numel() * 4 / us / 1e3,
                   "note": "the fused path (ssdx_nms_scaled) avoids this pass: 4 extra multiplies per float4 inside the NMS select"}))
+
+# ---- metrics.jaccard_iou_bounding_boxes at batch 1024 (two (B,A,4) streams in, (B,) out)
+import ssdseglib
+from oracle import ssd_oracle as orc
+anchors = orc.anchors_generate(**orc.STD_ANCHOR_CFG)
+coder = ssdseglib.datacoder.DataEncoderDecoder(4, (480, 640), anchors[:, 0], anchors[:, 1], anchors[:, 2], anchors[:, 3])
+labels, boxes, counts = orc.synth_gt(np.random.default_rng(3), 1024, 16)
+_, yt = coder.encode_batch(torch.from_numpy(boxes).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(counts).cuda())
+yp = yt + 0.5 * torch.randn(yt.shape, generator=g, device="cuda")
+outm = torch.empty(1024, device="cuda")
+stdm = sx.std_array((0.1, 0.1, 0.2, 0.2))
+us = timeit(lambda: sx.check(sx.lib.ssdx_metric_iou_boxes(coder._anchors.handle, yt.data_ptr(), yp.data_ptr(), 1024, stdm, outm.data_ptr(), sp)))
+nb = 2 * yt.numel() * 4
+print(json.dumps({"case": "metrics.jaccard_iou_bounding_boxes, B=1024", "us": round(us, 1), "GBps": nb / us / 1e3, "frac_of_measured_hbm_peak": nb / us / 1e3 / PEAK, "mean_iou": float(outm.nanmean())}))
