@@ -157,6 +157,19 @@ SSDX_API int ssdx_eval_tp(const int32_t* pred_label, const float* pred_xyxy, con
                  int32_t background_label, float iou_threshold, uint8_t* out_tp, int64_t* counts, int device,
                  ssdx_stream stream);
 
+/* ---- average precision: evaluators.py:159-187 (the tail of average_precision_object_detection), SURVEY 8(f) row 4 ----
+ * tp (N) u8, confidence (N) f32, label (N) i32 class indices: every prediction of the data set, flattened;
+ * counts (C,3) i64 as ssdx_eval_tp accumulates them ([c][2] = ground-truth boxes of class c).
+ * out_ap (C) f64: per class, predictions sorted by confidence descending, precision = cumsum(tp)/rank (f64),
+ * recall = cumsum(tp)/n_gt (f32), trapezoid in f64 without a (0,.) sentinel; 0 for the background class, for a class
+ * without ground truth and for a class without predictions.  N < 2^31.  Tie order among equal confidences is the
+ * input order (the reference's quicksort leaves it unspecified). */
+SSDX_API size_t ssdx_average_precision_workspace_bytes(int64_t num_predictions, int32_t num_classes);
+SSDX_API int ssdx_average_precision(const uint8_t* tp, const float* confidence, const int32_t* label,
+                                    int64_t num_predictions, int32_t num_classes, const int64_t* counts,
+                                    int32_t background_label, double* out_ap, void* workspace, size_t workspace_bytes,
+                                    int device, ssdx_stream stream);
+
 /* evaluators.py:6-63 as a matrix: out (P,G) f32 = IoU (+1 convention, +1e-7f in the denominator) * [labels equal].
  * G == 0 is the caller's business (the reference returns a (P,1) zero matrix, :27-28). */
 SSDX_API int ssdx_iou_pred_vs_true(const int32_t* pred_label, const float* pred_xyxy, const int32_t* gt_label,

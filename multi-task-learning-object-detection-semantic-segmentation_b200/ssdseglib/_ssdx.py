@@ -56,6 +56,9 @@ SIGNATURES = {
     "ssdx_scale_scores": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int, _vp]),
     "ssdx_eval_tp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, _vp, _vp, C.c_int, _vp]),
+    "ssdx_average_precision_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "ssdx_average_precision": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, _vp, C.c_size_t,
+                                         C.c_int, _vp]),
     "ssdx_iou_pred_vs_true": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
     "ssdx_metric_iou_boxes": (C.c_int, [_vp, _vp, _vp, C.c_int32, c_float_p, _vp, _vp]),
     "ssdx_parse_gt_csv": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_float, c_i32_p, c_float_p, C.c_int32,
@@ -378,6 +381,19 @@ def eval_tp(pred_label, pred_xyxy, gt_xyxy, gt_label, gt_count, num_classes: int
                            num_classes, int(background_label), float(iou_threshold), ptr(tp), ptr(counts), dev,
                            stream_ptr(dev)))
     return tp, counts
+
+
+def average_precision(tp, confidence, label, counts, num_classes: int, background_label: int):
+    """tp (N,) uint8, confidence (N,) float32, label (N,) int32 class indices, counts (C,3) int64: CUDA tensors.
+    Returns a CUDA float64 tensor (C,)."""
+    torch = _torch()
+    dev = tp.device.index
+    n = int(tp.numel())
+    out = torch.empty((num_classes,), dtype=torch.float64, device=f"cuda:{dev}")
+    ws = workspace(int(lib.ssdx_average_precision_workspace_bytes(n, num_classes)), dev)
+    check(lib.ssdx_average_precision(ptr(tp), ptr(confidence), ptr(label), n, int(num_classes), ptr(counts),
+                                     int(background_label), ptr(out), ptr(ws), ws.numel(), dev, stream_ptr(dev)))
+    return out
 
 
 def iou_pred_vs_true(pred_label, pred_xyxy, gt_label, gt_xyxy):

@@ -113,7 +113,19 @@ def average_precision_object_detection(
     lut = np.vectorize(lambda v: remap.get(int(v), len(codes)))
     lp_i = lut(lp).astype(np.int32) if lp.size else lp
     gl_i = lut(gl).astype(np.int32) if gl.size else gl
-    tp, counts = true_positives_and_counts(lp_i, bp, gl_i, gb, gc, iou_threshold, len(codes) + 1,
-                                           remap[label_code_background])
-    n_gt = {l: int(counts[remap[l], 2]) for l in foreground}
-    return average_precision_from_flags(tp[scored], conf[scored], lp[scored], n_gt, label_code_background)
+    # device: TP flags + per-class counts, then the precision/recall integration (sort, scan, trapezoid); only the
+    # per-class AP values come back to the host
+    torch = _ssdx.require_cuda()
+    num_idx = len(codes) + 1
+    bg_idx = remap[label_code_background]
+    lp_d, _ = _ssdx.to_device(lp_i, np.int32, None, "ap_lp")
+    dev = lp_d.device.index
+    bp_d, _ = _ssdx.to_device(bp, np.float32, dev, "ap_bp")
+    gl_d, _ = _ssdx.to_device(gl_i, np.int32, dev, "ap_gl")
+    gb_d, _ = _ssdx.to_device(gb, np.float32, dev, "ap_gb")
+    gc_d, _ = _ssdx.to_device(gc, np.int32, dev, "ap_gc")
+    conf_d, _ = _ssdx.to_device(conf, np.float32, dev, "ap_conf")
+    tp_d, counts_d = _ssdx.eval_tp(lp_d, bp_d, gb_d, gl_d, gc_d, num_idx, bg_idx, iou_threshold)
+    ap_d = _ssdx.average_precision(tp_d.reshape(-1), conf_d.reshape(-1), lp_d.reshape(-1), counts_d, num_idx, bg_idx)
+    ap = ap_d.cpu().numpy()
+    return {l: float(ap[remap[l]]) for l in foreground}

@@ -580,6 +580,36 @@ def test_dlpack_device_arrays_are_used_in_place(lib, coder, golden, std_anchors)
     assert_offsets_close(O.cpu().numpy(), Or)
 
 
+# ------------------------------------------------------------------------------------------- average precision
+def test_average_precision_on_device(lib):
+    """ssdx_average_precision (radix sort + scan + trapezoid on the GPU) against the reference's NumPy formula
+    (evaluators.py:159-187 as restated in average_precision_from_flags) on tie-free confidences, including a class
+    without predictions, a class without ground truth and segments longer than one scan chunk."""
+    import torch
+
+    rng = np.random.default_rng(17)
+    n, C, bg = 50_000, 6, 0
+    label = rng.integers(0, C, size=n).astype(np.int32)
+    label[label == 4] = 1                                   # class 4: no predictions
+    conf = rng.permutation(n).astype(np.float32) / np.float32(n)   # distinct
+    tp = (rng.uniform(size=n) < 0.3).astype(np.uint8)
+    tp[label == bg] = 0
+    n_gt = {1: 4000, 2: 700, 3: 0, 4: 50, 5: 123}                  # class 3: no ground truth
+    counts = np.zeros((C, 3), np.int64)
+    for c, v in n_gt.items():
+        counts[c, 2] = v
+    ref = lib.evaluators.average_precision_from_flags(tp[label != bg], conf[label != bg], label[label != bg], n_gt, bg)
+    sx = lib._ssdx
+    got = sx.average_precision(torch.from_numpy(tp).cuda(), torch.from_numpy(conf).cuda(), torch.from_numpy(label).cuda(),
+                               torch.from_numpy(counts).cuda(), C, bg).cpu().numpy()
+    assert got.dtype == np.float64 and got[bg] == 0.0 and got[3] == 0.0 and got[4] == 0.0
+    for c in (1, 2, 5):
+        assert abs(got[c] - ref[c]) <= 1e-12 * max(1.0, abs(ref[c])), (c, got[c], ref[c])
+    empty = sx.average_precision(torch.zeros(0, dtype=torch.uint8, device="cuda"), torch.zeros(0, device="cuda"),
+                                 torch.zeros(0, dtype=torch.int32, device="cuda"), torch.from_numpy(counts).cuda(), C, bg)
+    assert not empty.cpu().numpy().any()
+
+
 # ------------------------------------------------------------------------------------------- C ABI details
 def test_error_paths_and_workspace(lib, coder):
     import ctypes as C

@@ -147,6 +147,27 @@ def config4():
     ref = np.stack([orc.eval_tp_flags(pl[i], pb[i], labels[i], boxes[i], 0.5, 0) for i in range(4)])
     ok = np.array_equal(ref, tp[:4].cpu().numpy())
     emit("4: eval TP/FP + per-class counts, batch 4096", B, med, best, 24 * K + 20 * G + K, "pass" if ok else "FAIL")
+    # the AP tail on the device (sort by confidence, scan, trapezoid) over all 4096 x 200 predictions
+    conf = (torch.randperm(B * K, generator=torch.Generator("cuda").manual_seed(5), device="cuda:0").float()
+            / float(B * K)).reshape(B, K)  # distinct confidences: the tie order of the reference's quicksort is unspecified
+    cnt.zero_(); fn(); torch.cuda.synchronize()
+    ap = torch.empty(C, dtype=torch.float64, device="cuda:0")
+    wsb = int(sx.lib.ssdx_average_precision_workspace_bytes(B * K, C))
+    wsa = torch.empty(wsb, dtype=torch.uint8, device="cuda:0")
+
+    def fap():
+        sx.check(sx.lib.ssdx_average_precision(tp.data_ptr(), conf.data_ptr(), d[0].data_ptr(), B * K, C, cnt.data_ptr(), 0,
+                                               ap.data_ptr(), wsa.data_ptr(), wsb, dev, sp))
+    med, best = timeit(fap)
+    import time
+    t0 = time.perf_counter()
+    ref = ssdseglib.evaluators.average_precision_from_flags(
+        tp.cpu().numpy().reshape(-1), conf.cpu().numpy().reshape(-1), pl.reshape(-1),
+        {c: int(cnt[c, 2]) for c in range(1, C)}, 0)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    okap = all(abs(float(ap[c]) - ref[c]) < 1e-9 for c in range(1, C))
+    emit("4b: average precision tail on the device, 819,200 predictions", B, med, best, 9 * K, "pass" if okap else "FAIL",
+         {"host_numpy_ms_incl_d2h": round(host_ms, 1)})
 
 
 if __name__ == "__main__":
