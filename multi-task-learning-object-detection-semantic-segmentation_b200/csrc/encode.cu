@@ -48,6 +48,9 @@ constexpr int kApt = kSsdxApt;      // anchors per lane per tile
 #ifndef SSDX_ENC_THREADS
 #define SSDX_ENC_THREADS 256
 #endif
+#ifndef SSDX_ENC_MINB
+#define SSDX_ENC_MINB (1024 / SSDX_ENC_THREADS)  // resident CTAs per SM the register budget is sized for
+#endif
 #ifndef SSDX_ENC_BGROWS
 #define SSDX_ENC_BGROWS 512
 #endif
@@ -285,7 +288,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int A, int G, int C) {
   return n + 16;
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 1024 / kFusedThreads)
+__global__ void __launch_bounds__(kFusedThreads, SSDX_ENC_MINB)
     ssdx_encode_fused_kernel(const float4* __restrict__ m_box, const float* __restrict__ m_area,
                              const int* __restrict__ m_idx, const float4* __restrict__ t_bbox,
                              const float2* __restrict__ t_area, const int n_tiles,
