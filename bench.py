@@ -370,17 +370,23 @@ def gpu_arm(args, rank, world, local_rank):
     # no host-side launch gaps between the kernels of a step.  --no-graph times the eager launches instead.
     graph = None
     if not args.no_graph:
-        cap_stream = torch.cuda.Stream(dev)
-        cap_stream.wait_stream(stream)
-        graph = torch.cuda.CUDAGraph()
         outer_sp = sp
-        with torch.cuda.graph(graph, stream=cap_stream):
-            sp = torch.cuda.current_stream(dev).cuda_stream
-            step_device(overlap=not args.no_overlap)
-        sp = outer_sp
-        for _ in range(3):
-            graph.replay()
-        torch.cuda.synchronize(dev)
+        try:
+            cap_stream = torch.cuda.Stream(dev)
+            cap_stream.wait_stream(stream)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap_stream):
+                sp = torch.cuda.current_stream(dev).cuda_stream
+                step_device(overlap=not args.no_overlap)
+            sp = outer_sp
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+        except Exception as exc:  # capture is an optimisation of the launch path only: fall back to eager launches
+            sys.stderr.write(f"bench.py: CUDA graph capture failed ({exc}); timing eager launches\n")
+            sp = outer_sp
+            graph = None
+            torch.cuda.synchronize(dev)
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
