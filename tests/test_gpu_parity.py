@@ -125,6 +125,21 @@ def test_encode_other_class_counts(lib, std_anchors, C, thr):
     assert_offsets_close(O, Or)
 
 
+@pytest.mark.parametrize("A,C", [(9563, 4), (9563, 3), (1001, 5), (63, 4)])
+def test_encode_odd_anchor_counts(lib, std_anchors, A, C):
+    """Anchor counts that are not multiples of the tile / vector sizes (padding slots of the match order, partial
+    background blocks, label rows that cannot be bulk-stored because the image stride is not 16-byte aligned)."""
+    rng = np.random.default_rng(A + C)
+    anchors = std_anchors[rng.permutation(9600)[:A]]          # arbitrary order: the match order is built inside
+    labels, boxes, counts = orc.synth_gt(rng, 150, 12, n_fg=max(C - 1, 1))
+    counts[::7] = 0
+    c = lib.datacoder.DataEncoderDecoder(C, (480, 640), anchors[:, 0], anchors[:, 1], anchors[:, 2], anchors[:, 3])
+    L, O, M = c.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(anchors, labels, boxes, counts, C, 0.5)
+    assert L.shape == (150, A, C) and np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+
+
 def test_encode_stress_shape_small_batch(lib):
     """BASELINE config 3 shape (A = 100k, G = 256) at batch 2 against the oracle."""
     anchors = orc.anchors_generate(**orc.STRESS_ANCHOR_CFG)
