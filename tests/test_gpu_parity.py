@@ -138,6 +138,11 @@ def test_encode_odd_anchor_counts(lib, std_anchors, A, C):
     Lr, Or, Mr = encode_ref(anchors, labels, boxes, counts, C, 0.5)
     assert L.shape == (150, A, C) and np.array_equal(M, Mr) and np.array_equal(L, Lr)
     assert_offsets_close(O, Or)
+    # decode on the same odd shape: batched layer form and the masked single-image form
+    cent = np.stack(orc.corners_to_centroids(*[anchors[:, i] for i in range(4)]), 1).astype(np.float32)
+    layer = lib.layers.DecodeBoxesCentroidsOffsets(cent[:, 0], cent[:, 1], cent[:, 2], cent[:, 3], *STD)
+    assert_coords_close(layer(O), orc.decode_batched_yxyx(Or, cent, STD), cent[None, :, 2:])
+    assert_coords_close(c.decode_to_corners(O[3]), orc.decode_to_corners(Or[3], cent, STD), cent[:, 2:])
 
 
 def test_encode_stress_shape_small_batch(lib):
