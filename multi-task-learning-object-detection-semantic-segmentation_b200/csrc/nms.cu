@@ -246,7 +246,14 @@ __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64*
 // sort s_list[0..n) descending for the fast kernel (256 threads); uniform control flow
 __device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n,
                                           const int tid) {
-  if (n <= 512) {
+  if (n <= 256) {
+    u64 v[1];
+    v[0] = (tid < n) ? s_list[tid] : 0ull;
+    __syncthreads();
+    bitonic_sort_regs<1>(v, s_list, s_tmp, tid);
+    __syncthreads();
+    s_list[tid] = v[0];
+  } else if (n <= 512) {
     u64 v[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) v[r] = (r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
@@ -269,90 +276,95 @@ __device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n,
 }
 
 // ------------------------------------------------------------------------------------------ 1. select
+// info per (image, class): [0] listed candidates (may exceed kCap), [2] threshold key (every candidate with key >= it
+// is listed).  Same scheme as the merged select below, per class: threshold = the kTierRank-th largest of the
+// per-thread maxima of a 1/16 sample, then one streaming pass with one compare per score and marked hits.
 template <bool VEC4>
 __global__ void __launch_bounds__(kSelThreads)
     ssdx_nms_select_kernel(const float* __restrict__ scores, const float* __restrict__ cscale, const int A,
-                           const int C, const float score_thr, u64* __restrict__ lists, int* __restrict__ info,
-                           int* __restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                           const int C, const float score_thr, const int tier_rank, u64* __restrict__ lists,
+                           int* __restrict__ info, int* __restrict__ flags) {
+  __shared__ unsigned s_max[kSelGroup][kSelThreads];  // per class: per-thread maximum of the sampled keys
+  __shared__ unsigned s_T[kSelGroup];
+  __shared__ float s_tlo[kSelGroup];
+  __shared__ int s_cnt[kSelGroup];
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * kSelGroup;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) flags[0] = 0;  // worklist of the generic kernel
   const int cg = min(kSelGroup, C - c0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NS = (A + kSampleStride - 1) / kSampleStride;
-  unsigned* skeys = (unsigned*)smem_raw;          // [cg][NS] sample keys
-  unsigned* tk = skeys + (size_t)cg * NS;         // [kSelGroup] key of the tier-0 threshold per class
-  int* cnt = (int*)(tk + kSelGroup);              // [kSelGroup] listed candidates (tier 0)
-  int* tot = cnt + kSelGroup;                     // [kSelGroup] all candidates (score > thr)
   const float* img = scores + (size_t)b * A * C;
-
-  if (tid < kSelGroup) {
-    cnt[tid] = 0;
-    tot[tid] = 0;
-  }
+  if (tid < kSelGroup) s_cnt[tid] = 0;
+  for (int c = 0; c < cg; ++c) s_max[c][tid] = 0u;  // own column only: no barrier needed before the sample pass
   // ---- sample ----
   for (int k = tid; k < NS; k += kSelThreads) {
     int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
     a = a < A ? a : A - 1;
     if (VEC4) {
       const float4 s = mul4(__ldg(reinterpret_cast<const float4*>(img) + a), class_factor4(cscale));
-      skeys[0 * NS + k] = (s.x > score_thr) ? score_to_key(s.x) : 0u;
-      skeys[1 * NS + k] = (s.y > score_thr) ? score_to_key(s.y) : 0u;
-      skeys[2 * NS + k] = (s.z > score_thr) ? score_to_key(s.z) : 0u;
-      skeys[3 * NS + k] = (s.w > score_thr) ? score_to_key(s.w) : 0u;
+      const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (sv[c] > score_thr) s_max[c][tid] = max(s_max[c][tid], score_to_key(sv[c]));
     } else {
       for (int c = 0; c < cg; ++c) {
         const float s = __fmul_rn(__ldg(img + (size_t)a * C + c0 + c), class_factor(cscale, c0 + c));
-        skeys[c * NS + k] = (s > score_thr) ? score_to_key(s) : 0u;
+        if (s > score_thr) s_max[c][tid] = max(s_max[c][tid], score_to_key(s));
       }
     }
   }
   __syncthreads();
-  // ---- tier-0 threshold: one warp per class finds a key with kTierRank .. kTierRank+3 samples at or above it
+  // ---- threshold: one warp per class bisects the 256 maxima held in registers ----
   for (int c = warp; c < cg; c += kSelThreads / 32) {
-    const unsigned* keys = skeys + (size_t)c * NS;
-    int nv = 0;
-    unsigned kmax = 0u, kmin = 0xFFFFFFFFu;
-    for (int k = lane; k < NS; k += 32) {
-      const unsigned key = keys[k];
-      nv += key != 0u;
-      kmax = max(kmax, key);
-      kmin = min(kmin, key != 0u ? key : 0xFFFFFFFFu);
+    unsigned v[kSelThreads / 32];
+    int nz = 0;
+    unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+    for (int r = 0; r < kSelThreads / 32; ++r) {
+      v[r] = s_max[c][r * 32 + lane];
+      nz += v[r] != 0u;
+      kmax = max(kmax, v[r]);
+      kmin = min(kmin, v[r] != 0u ? v[r] : 0xFFFFFFFFu);
     }
-    nv = __reduce_add_sync(0xFFFFFFFFu, nv);
+    nz = __reduce_add_sync(0xFFFFFFFFu, nz);
     kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
     kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
-    unsigned lo = 1u;  // count(key >= 1) = nv: every candidate
-    if (A > kCap && nv >= kTierRank) {
-      lo = kmin;                  // count(key >= kmin) = nv >= rank
-      unsigned hi = kmax + 1u;    // count = 0
+    unsigned T = 1u;  // list every candidate
+    if (A > kCap && nz >= tier_rank) {
+      unsigned lo = kmin;       // count(max >= kmin) = nz >= rank
+      unsigned hi = kmax + 1u;  // count = 0
       while (hi - lo > 1u) {
         const unsigned mid = lo + ((hi - lo) >> 1);
-        int n = 0;
-        for (int k = lane; k < NS; k += 32) n += keys[k] >= mid;
-        n = __reduce_add_sync(0xFFFFFFFFu, n);
-        if (n >= kTierRank) {
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < kSelThreads / 32; ++r) cnt += v[r] >= mid;
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (cnt >= tier_rank) {
           lo = mid;
-          if (n <= kTierRank + 3) break;  // any threshold in this band will do
+          if (cnt <= tier_rank + 3) break;  // any threshold in this band will do
         } else {
           hi = mid;
         }
       }
-      if (lo == kmin && nv <= kTierRank + 3) lo = 1u;  // the whole sample is in the band: list every candidate
+      T = lo;
+      if (lo == kmin && nz <= tier_rank + 3) T = 1u;  // every thread maximum is in the band: list every candidate
     }
-    if (lane == 0) tk[c] = lo;
+    if (T == 0x80000000u) T = 0x7FFFFFFFu;  // +0.0 -> -0.0: keeps "s >= t_lo" and "key >= T" the same set
+    if (lane == 0) {
+      s_T[c] = T;
+      // listed  <=>  s > score_thr and key(s) >= T  <=>  s >= t_lo   (one compare per score)
+      const float tf = (T <= 1u) ? -INFINITY : key_to_score(T);
+      s_tlo[c] = (tf > score_thr) ? tf : nextafterf(score_thr, INFINITY);
+    }
   }
   __syncthreads();
-  // ---- full scan: append every candidate of tier 0 (score >= first threshold) ----
+  // ---- one streaming pass; hits are only marked, then appended in a compact loop ----
   u64* img_lists = lists + ((size_t)b * C + c0) * kCap;
   if (VEC4) {
-    float tt[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tt[c] = (tk[c] <= 1u) ? -INFINITY : key_to_score(tk[c]);
-    int n_cand[4] = {0, 0, 0, 0};
+    const float t0 = s_tlo[0], t1 = s_tlo[1], t2 = s_tlo[2], t3 = s_tlo[3];
     const float4 cf4 = class_factor4(cscale);
-    constexpr int kBatch = 4;  // independent 128-bit streaming loads in flight per thread
+    constexpr int kBatch = 8;  // independent 128-bit streaming loads in flight per thread
     for (int a0 = tid; a0 < A; a0 += kSelThreads * kBatch) {
       float4 sb[kBatch];
 #pragma unroll
@@ -361,52 +373,42 @@ __global__ void __launch_bounds__(kSelThreads)
         sb[u] = (a < A) ? mul4(__ldcs(reinterpret_cast<const float4*>(img) + a), cf4)
                         : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
+      unsigned hits = 0u;  // bit 4*u + c
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const int a = a0 + u * kSelThreads;
-        const float sv[4] = {sb[u].x, sb[u].y, sb[u].z, sb[u].w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (sv[c] > score_thr) {  // false for the -inf padding
-            ++n_cand[c];
-            if (sv[c] >= tt[c]) {
-              const int pos = atomicAdd(&cnt[c], 1);
-              if (pos < kCap) img_lists[(size_t)c * kCap + pos] = make_comp(score_to_key(sv[c]), a);
-            }
-          }
-        }
+        hits |= (sb[u].x >= t0 ? 1u : 0u) << (4 * u);
+        hits |= (sb[u].y >= t1 ? 2u : 0u) << (4 * u);
+        hits |= (sb[u].z >= t2 ? 4u : 0u) << (4 * u);
+        hits |= (sb[u].w >= t3 ? 8u : 0u) << (4 * u);
       }
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int n = __reduce_add_sync(0xFFFFFFFFu, n_cand[c]);
-      if (lane == 0 && n) atomicAdd(&tot[c], n);
+      while (hits != 0u) {  // the score is re-read (L1/L2 hit) instead of indexing the register batch dynamically
+        const int bit = __ffs(hits) - 1;
+        hits &= hits - 1u;
+        const int a = a0 + (bit >> 2) * kSelThreads, c = bit & 3;
+        const float s = __fmul_rn(__ldg(img + (size_t)a * 4 + c), class_factor(cscale, c));
+        const int pos = atomicAdd(&s_cnt[c], 1);
+        if (pos < kCap) img_lists[(size_t)c * kCap + pos] = make_comp(score_to_key(s), a);
+      }
     }
   } else {
     for (int c = 0; c < cg; ++c) {
-      const float t = (tk[c] <= 1u) ? -INFINITY : key_to_score(tk[c]);
+      const float t = s_tlo[c];
       const float cf = class_factor(cscale, c0 + c);
-      int n_cand = 0;
       for (int a = tid; a < A; a += kSelThreads) {
         const float s = __fmul_rn(__ldg(img + (size_t)a * C + c0 + c), cf);
-        if (s > score_thr) {
-          ++n_cand;
-          if (s >= t) {
-            const int pos = atomicAdd(&cnt[c], 1);
-            if (pos < kCap) img_lists[(size_t)c * kCap + pos] = make_comp(score_to_key(s), a);
-          }
+        if (s >= t) {
+          const int pos = atomicAdd(&s_cnt[c], 1);
+          if (pos < kCap) img_lists[(size_t)c * kCap + pos] = make_comp(score_to_key(s), a);
         }
       }
-      n_cand = __reduce_add_sync(0xFFFFFFFFu, n_cand);
-      if (lane == 0 && n_cand) atomicAdd(&tot[c], n_cand);
     }
   }
   __syncthreads();
   if (tid < cg) {
     int* dst = info + ((size_t)b * C + c0 + tid) * kInfo;
-    dst[0] = cnt[tid];
-    dst[1] = tot[tid];
-    dst[2] = (int)tk[tid];
+    dst[0] = s_cnt[tid];
+    dst[1] = 0;
+    dst[2] = (int)s_T[tid];
     dst[3] = 0;
   }
 }
@@ -432,7 +434,6 @@ __global__ void __launch_bounds__(kFastThreads, 6)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int* seg_info = info + seg * kInfo;
   int n = seg_info[0];
-  const int total = seg_info[1];
   if (n > kCap || limit > kFastMaxSel) {  // uniform
     if (tid == 0) flags[1 + atomicAdd(&flags[0], 1)] = (int)seg;  // hand the segment to the generic kernel
     return;
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kFastThreads, 6)
         n_sel = s_nsel;
       }
     }
-    if (n_sel >= limit || consumed >= total) break;
+    if (n_sel >= limit || key_hi <= 1u) break;  // done, or every candidate has been visited
     // ---- the tier ran dry and candidates remain: fetch the next key band [key_lo, key_hi) from the scores.
     //      The band width adapts to the density seen so far; an over-full band is narrowed and rescanned. ----
     bool got = false;
@@ -642,7 +643,7 @@ __global__ void __launch_bounds__(kFastThreads, 6)
     atomicAdd(&g_phase_cycles[9], (unsigned long long)scans);
     atomicAdd(&g_phase_cycles[10], (unsigned long long)consumed);
 #endif
-    const bool complete = !failed && ((n_sel >= limit) || (consumed >= total));
+    const bool complete = !failed;
     pick_cnt[seg] = n_sel;
     if (!complete) flags[1 + atomicAdd(&flags[0], 1)] = (int)seg;
   }
@@ -1426,7 +1427,6 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
   else bx = ssdx_box_src{(const float4*)boxes_yxyx, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f};
 
   int* iflags = (int*)(base + w.iflags);
-  const int NS = (A + kSampleStride - 1) / kSampleStride;
   const bool vec4 = (C == 4) && (((uintptr_t)scores & 15) == 0);
   // test hooks: "generic" = exact generic kernel alone, "perclass" = per-class fast pipeline even when the merged
   // one applies.  All paths give identical results.
@@ -1479,19 +1479,18 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
 
   // ---- per-class pipeline ----
   // 1. select
-  const size_t sel_smem = (size_t)(C < kSelGroup ? C : kSelGroup) * NS * 4 + kSelGroup * 12 + 16;
-  const bool use_fast = sel_smem <= 200 * 1024 && !force_generic;
+  const bool use_fast = !force_generic;
+  // first tier: ~16 * rank candidates.  (Sizing it to the per-class cap was measured and dropped: a tier that runs dry
+  // costs a rescan of the class's scores, 194 vs 120 us for max_per_class = 4 at batch 1024.)
+  const int tier_rank = kTierRank;
   if (use_fast && ph1) {
     dim3 gsel((C + kSelGroup - 1) / kSelGroup, batch);
-    if (vec4) {
-      SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sel_smem));
-      ssdx_nms_select_kernel<true><<<gsel, kSelThreads, sel_smem, s>>>(scores, cscale, A, C, score_threshold, lists, info, flags);
-    } else {
-      SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sel_smem));
-      ssdx_nms_select_kernel<false><<<gsel, kSelThreads, sel_smem, s>>>(scores, cscale, A, C, score_threshold, lists, info, flags);
-    }
+    if (vec4)
+      ssdx_nms_select_kernel<true><<<gsel, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, tier_rank,
+                                                                lists, info, flags);
+    else
+      ssdx_nms_select_kernel<false><<<gsel, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, tier_rank,
+                                                                 lists, info, flags);
     SSDX_LAUNCH_CHECK("ssdx_nms_select_kernel");
   }
   if (!ph2) return SSDX_OK;
