@@ -65,7 +65,10 @@ constexpr int kMergeThreads = 256;
 #ifndef SSDX_FAST_MINB
 #define SSDX_FAST_MINB 7
 #endif
-constexpr int kAllRank = 26;       // merged select: threshold at the 26th largest sample => ~416 +- 80 listed
+#ifndef SSDX_ALL_RANK
+#define SSDX_ALL_RANK 26
+#endif
+constexpr int kAllRank = SSDX_ALL_RANK;       // merged select: threshold at the 26th largest sample => ~416 +- 80 listed
 constexpr int kAllRefillTarget = 384;
 
 #ifdef SSDX_PHASE_TIMERS

@@ -180,3 +180,26 @@ def test_box_iou_metric_matches_reference_source(golden, std_anchors):
     got = orc.metric_iou_boxes(g["y_true"], g["y_pred"], cent, STD)
     np.testing.assert_allclose(got, g["value"], rtol=1e-6)
     assert abs(float(got[2]) - 1.0) < 1e-6      # perfect predictions
+
+
+def test_closed_form_equals_literal_property():
+    """Property test (hypothesis): on small integer grids, where exact IoU ties and duplicated winners are the rule,
+    the closed form of SURVEY P3 equals the literal concat -> unique -> sequential scatter for every threshold."""
+    from hypothesis import given, settings, strategies as st
+
+    box = st.tuples(st.integers(0, 12), st.integers(0, 12), st.integers(1, 8), st.integers(1, 8)).map(
+        lambda t: (t[0], t[1], t[0] + t[2] - 1, t[1] + t[3] - 1))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(box, min_size=1, max_size=24), st.lists(box, min_size=1, max_size=6),
+           st.sampled_from([0.0, 0.25, 0.5, 0.525, 0.9]))
+    def check(anchors, gts, thr):
+        a = np.asarray(anchors, np.float32)
+        g = np.asarray(gts, np.float32)
+        iou = orc.iou_matrix(a, g)
+        ref = np.full(len(a), -1, np.int32)
+        for ai, gi in orc.match_literal(iou, thr):
+            ref[ai] = gi
+        assert np.array_equal(ref, orc.match_closed_form(iou, thr))
+
+    check()
