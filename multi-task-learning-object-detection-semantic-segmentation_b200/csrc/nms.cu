@@ -334,7 +334,9 @@ __global__ void __launch_bounds__(kSelThreads)
     kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
     kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
     unsigned T = 1u;  // list every candidate
-    if (A > kCap && nz >= tier_rank) {
+    // a class is thresholded only when it is dense (>= kTierRank threads saw a candidate): a sparse class is listed
+    // whole, so that it never needs a refill scan; the rank of the threshold follows the per-class cap
+    if (A > kCap && nz >= kTierRank) {
       unsigned lo = kmin;       // count(max >= kmin) = nz >= rank
       unsigned hi = kmax + 1u;  // count = 0
       while (hi - lo > 1u) {
@@ -1483,9 +1485,10 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
   // ---- per-class pipeline ----
   // 1. select
   const bool use_fast = !force_generic;
-  // first tier: ~16 * rank candidates.  (Sizing it to the per-class cap was measured and dropped: a tier that runs dry
-  // costs a rescan of the class's scores, 194 vs 120 us for max_per_class = 4 at batch 1024.)
-  const int tier_rank = kTierRank;
+  // first tier of a dense class: ~16 * rank candidates, sized to the per-class cap (a tier that runs dry is refilled
+  // by the fast kernel at the price of a rescan, so keep a margin), never more than the default 320
+  int tier_rank = (3 * limit + 63) / 16;
+  tier_rank = tier_rank < 4 ? 4 : (tier_rank > kTierRank ? kTierRank : tier_rank);
   if (use_fast && ph1) {
     dim3 gsel((C + kSelGroup - 1) / kSelGroup, batch);
     if (vec4)
