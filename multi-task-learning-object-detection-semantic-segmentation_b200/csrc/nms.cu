@@ -660,8 +660,8 @@ __global__ void __launch_bounds__(kFastThreads, 6)
 template <bool VEC4>
 __global__ void __launch_bounds__(kSelThreads)
     ssdx_nms_select_all_kernel(const float* __restrict__ scores, const float* __restrict__ cscale, const int A,
-                               const int C, const float score_thr, u64* __restrict__ lists, int* __restrict__ info,
-                               int* __restrict__ flags, int* __restrict__ iflags) {
+                               const int C, const float score_thr, const int all_rank, u64* __restrict__ lists,
+                               int* __restrict__ info, int* __restrict__ flags, int* __restrict__ iflags) {
   __shared__ unsigned s_max[kSelThreads];  // per-thread maximum of the sampled keys
   __shared__ unsigned s_T;
   __shared__ int s_cnt;
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(kSelThreads)
     kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
     kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
     unsigned T = 1u;  // list every candidate
-    if ((long long)A * C > kCap && nz >= kAllRank) {
+    if ((long long)A * C > kCap && nz >= kAllRank) {  // dense enough to need a threshold at all
       unsigned lo = kmin;       // count(max >= kmin) = nz >= rank
       unsigned hi = kmax + 1u;  // count = 0
       while (hi - lo > 1u) {
@@ -722,15 +722,15 @@ __global__ void __launch_bounds__(kSelThreads)
 #pragma unroll
         for (int r = 0; r < kSelThreads / 32; ++r) cnt += v[r] >= mid;
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-        if (cnt >= kAllRank) {
+        if (cnt >= all_rank) {
           lo = mid;
-          if (cnt <= kAllRank + 3) break;  // any threshold in this band will do
+          if (cnt <= all_rank + 3) break;  // any threshold in this band will do
         } else {
           hi = mid;
         }
       }
       T = lo;
-      if (lo == kmin && nz <= kAllRank + 3) T = 1u;  // every thread maximum is in the band: list every candidate
+      if (lo == kmin && nz <= all_rank + 3) T = 1u;  // every thread maximum is in the band: list every candidate
     }
     if (T == 0x80000000u) T = 0x7FFFFFFFu;  // +0.0 -> -0.0: keeps "s >= t_lo" and "key >= T" the same set
     if (lane == 0) s_T = T;
@@ -1453,12 +1453,15 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
                       A <= (1 << 24) && (long long)A * C < (1ll << 31) && max_total <= kFastMaxSel;
   if (merged) {
     if (ph1) {
+      // first list sized to max_total (rank (3 K + 63) / 16 of the thread maxima, at most kAllRank = the K = 200 tuning)
+      int all_rank = (3 * max_total + 63) / 16;
+      all_rank = all_rank < 4 ? 4 : (all_rank > kAllRank ? kAllRank : all_rank);
       if (vec4)
-        ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, lists,
-                                                                       info, flags, iflags);
+        ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, all_rank,
+                                                                       lists, info, flags, iflags);
       else
-        ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, lists,
-                                                                        info, flags, iflags);
+        ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
+                                                                        all_rank, lists, info, flags, iflags);
       SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
     }
     if (!ph2) return SSDX_OK;
