@@ -351,9 +351,8 @@ def gpu_arm(args, rank, world, local_rank):
         for st in pipe_streams[1:]:
             cur.wait_stream(st)
 
-    # kernels of one step: fused encode (1) + decode (1) + NMS merged pipeline (select_all, fast_all and the two
-    # worklist-gated fallback kernels, which exit at once when nothing was handed over)
-    kernels_per_step = (1 if "encode" in stages else 0) + 1 + 4
+    # kernels of one step: fused encode (1) + decode (1) + NMS merged pipeline (select_all, fast_all)
+    kernels_per_step = (1 if "encode" in stages else 0) + 1 + 2
 
     def barrier():
         torch.cuda.synchronize(dev)

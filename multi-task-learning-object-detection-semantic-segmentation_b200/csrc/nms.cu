@@ -661,16 +661,12 @@ template <bool VEC4>
 __global__ void __launch_bounds__(kSelThreads)
     ssdx_nms_select_all_kernel(const float* __restrict__ scores, const float* __restrict__ cscale, const int A,
                                const int C, const float score_thr, const int all_rank, u64* __restrict__ lists,
-                               int* __restrict__ info, int* __restrict__ flags, int* __restrict__ iflags) {
+                               int* __restrict__ info) {
   __shared__ unsigned s_max[kSelThreads];  // per-thread maximum of the sampled keys
   __shared__ unsigned s_T;
   __shared__ int s_cnt;
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
-  if (b == 0 && tid == 0) {  // worklists of the fallback kernels
-    flags[0] = 0;
-    iflags[0] = 0;
-  }
   const int NS = (A + kSampleStride - 1) / kSampleStride;
   const float* img = scores + (size_t)b * A * C;
   if (tid == 0) s_cnt = 0;
@@ -794,8 +790,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
     ssdx_nms_fast_all_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                              const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                              const int K, const float iou_thr, const float score_thr, float* __restrict__ out,
-                             int* __restrict__ out_valid, int* __restrict__ out_idx, int* __restrict__ flags,
-                             int* __restrict__ iflags) {
+                             int* __restrict__ out_valid, int* __restrict__ out_idx) {
   __shared__ u64 s_list[kCap];
   __shared__ u64 s_tmp[kCap];  // second exchange buffer of the sort; the candidate arrays below alias it
   __shared__ float4 s_sbox[MAXSEL];
@@ -814,33 +809,36 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int n = info[(size_t)b * kInfo + 0];
-  if (n > kCap) {  // uniform: hand the image to the per-class generic kernel + merge
-    if (tid == 0) {
-      const int at = atomicAdd(&flags[0], C);
-      for (int c = 0; c < C; ++c) flags[1 + at + c] = b * C + c;
-      iflags[1 + atomicAdd(&iflags[0], 1)] = b;
-    }
-    return;
+  // Everything at or above comp_hi (composite order: score key, class, anchor) has been listed.  Candidates are
+  // fetched in composite bands [comp_lo, comp_hi), so even thousands of equal scores are split (by class and anchor)
+  // into lists of at most kCap entries: this kernel never hands an image over.
+  u64 comp_hi = (u64)(unsigned)info[(size_t)b * kInfo + 1] << 32;
+  u64 span = 0ull;
+  const bool overflow = n > kCap;  // uniform: the first list does not fit; start over with band refills
+  if (overflow) {
+    n = 0;
+    span = (0xFFFFFFFFFFFFFFFFull - comp_hi) >> 2;  // the overflowing list covered [comp_hi, max]: a quarter of it
+    comp_hi = 0xFFFFFFFFFFFFFFFFull;
   }
   const size_t box_row0 = (size_t)b * A;
   const float* img_scores = scores + (size_t)b * A * C;
   const u64* lst = lists + (size_t)b * kCap;
-  for (int i = tid; i < n; i += kFastThreads) s_list[i] = lst[i];
+  for (int i = tid; i < n; i += kFastThreads) s_list[i] = lst[i];  // (n = 0 after an overflow: refill right away)
   if (tid == 0) s_nsel = 0;
   __syncthreads();
 
-  int n_sel = 0, scans = 0;
-  bool failed = false;
-  unsigned key_hi = (unsigned)info[(size_t)b * kInfo + 1];  // every candidate with key >= key_hi has been listed
-  unsigned span = 0u;
+  int n_sel = 0;
   while (true) {
     // ---- sort the current tier (merged order) ----
     fast_sort(s_list, s_tmp, n, tid);
-    if (span == 0u) {  // key width that held the lower half of this tier -> width expected to hold the refill target
-      const unsigned k_mid = (n >= 2) ? (unsigned)(s_list[n >> 1] >> 32) : 0u;
-      const unsigned k_bot = (n >= 2) ? (unsigned)(s_list[n - 1] >> 32) : 0u;
-      const u64 w = (n >= 2) ? (u64)(k_mid - k_bot) * (2ull * kAllRefillTarget) / (u64)n : 0ull;
-      span = (w == 0ull) ? 1024u : (w > 0x7FFFFFFFull ? 0x7FFFFFFFu : (unsigned)w);
+    if (span == 0ull) {  // band that held the lower half of this tier -> width expected to hold the refill target
+      const u64 c_mid = (n >= 2) ? s_list[n >> 1] : 0ull;
+      const u64 c_bot = (n >= 2) ? s_list[n - 1] : 0ull;
+      const u64 half = c_mid - c_bot;  // (sorted descending)
+      const u64 per = (n >= 2) ? half / (u64)n : 0ull;
+      span = (per == 0ull) ? (1024ull << 32)
+                           : (per > (0x7FFFFFFFFFFFFFFFull / (2ull * kAllRefillTarget)) ? 0x7FFFFFFFFFFFFFFFull
+                                                                                         : per * (2ull * kAllRefillTarget));
     }
 
     for (int g0 = 0; g0 < n && n_sel < K; g0 += kFastThreads) {
@@ -971,18 +969,17 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
         n_sel = s_nsel;
       }
     }
-    if (n_sel >= K || key_hi <= 1u) break;  // done, or every candidate has been visited
-    // ---- the tier ran dry: fetch the next key band [key_lo, key_hi) of all classes from the scores ----
+    if (n_sel >= K || comp_hi <= (1ull << 32)) break;  // done, or every candidate has been visited
+    // ---- the tier ran dry: fetch the next composite band [comp_lo, comp_hi) of all classes from the scores.  The
+    //      band width adapts to the density seen; an over-full band is narrowed and rescanned (down to one composite,
+    //      i.e. one candidate, so this always makes progress). ----
     bool got = false;
-    while (!got && !failed) {
-      if (++scans > kMaxRefills) {
-        failed = true;
-        break;
-      }
-      const unsigned key_lo = (key_hi - 1u > span) ? key_hi - span : 1u;
+    while (!got) {
+      const u64 comp_lo = (comp_hi - (1ull << 32) > span) ? comp_hi - span : (1ull << 32);
       __syncthreads();
       if (tid == 0) s_n = 0;
       __syncthreads();
+      const unsigned key_lo = (unsigned)(comp_lo >> 32), key_hi32 = (unsigned)((comp_hi - 1ull) >> 32);
       const int total = A * C;
       for (int e0 = tid; e0 < total; e0 += kFastThreads * 8) {  // 8 independent loads in flight per thread
         float sv[8];
@@ -996,11 +993,14 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
         for (int u = 0; u < 8; ++u) {
           if (sv[u] > score_thr) {  // false for the -inf padding
             const unsigned key = score_to_key(sv[u]);
-            if (key >= key_lo && key < key_hi) {
+            if (key >= key_lo && key <= key_hi32) {  // cheap 32-bit pre-test, then the exact composite band
               const int e = e0 + u * kFastThreads;
               const int a = e / C;
-              const int pos = atomicAdd(&s_n, 1);
-              if (pos < kCap) s_list[pos] = make_comp_all(key, e - a * C, a);
+              const u64 cp = make_comp_all(key, e - a * C, a);
+              if (cp >= comp_lo && cp < comp_hi) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < kCap) s_list[pos] = cp;
+              }
             }
           }
         }
@@ -1008,29 +1008,19 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
       __syncthreads();
       const int n_new = s_n;
       if (n_new > kCap) {
-        if (span <= 1u) failed = true;  // more than kCap equal scores: cannot be split by a threshold
-        span = max(span >> 2, 1u);
+        span = (span >> 2) > 1ull ? (span >> 2) : 1ull;
       } else {
         n = n_new;
-        key_hi = key_lo;
-        if (n_new < kAllRefillTarget / 8) span = (span > 0x1FFFFFFFu) ? 0x7FFFFFFFu : span << 2;
-        else if (n_new < kAllRefillTarget / 2) span = (span > 0x3FFFFFFFu) ? 0x7FFFFFFFu : span << 1;
-        else if (n_new > kAllRefillTarget * 2) span = max(span >> 1, 1u);
-        got = n_new > 0 || key_lo <= 1u;
+        comp_hi = comp_lo;
+        if (n_new < kAllRefillTarget / 8) span = (span > 0x1FFFFFFFFFFFFFFFull) ? 0x7FFFFFFFFFFFFFFFull : span << 2;
+        else if (n_new < kAllRefillTarget / 2) span = (span > 0x3FFFFFFFFFFFFFFFull) ? 0x7FFFFFFFFFFFFFFFull : span << 1;
+        else if (n_new > kAllRefillTarget * 2) span = (span >> 1) > 1ull ? (span >> 1) : 1ull;
+        got = n_new > 0 || comp_lo <= (1ull << 32);
       }
     }
-    if (failed) break;
     __syncthreads();
   }
   __syncthreads();
-  if (failed) {
-    if (tid == 0) {
-      const int at = atomicAdd(&flags[0], C);
-      for (int c = 0; c < C; ++c) flags[1 + at + c] = b * C + c;
-      iflags[1 + atomicAdd(&iflags[0], 1)] = b;
-    }
-    return;
-  }
   // ---- rows, already in merge order: [label, prob, xmin, ymin, xmax, ymax] (layers.py:155-162), zero padding ----
   float* o = out + (size_t)b * K * 6;
   for (int r = tid; r < n_sel; r += kFastThreads) {
@@ -1286,14 +1276,10 @@ __global__ void __launch_bounds__(kMergeThreads)
     ssdx_nms_merge_kernel(const ssdx_box_src boxes, const u64* __restrict__ picks,
                           const int* __restrict__ pick_cnt, const int A, const int C, const int limit, const int K,
                           const int stage_in_smem, float* __restrict__ out, int* __restrict__ out_valid,
-                          int* __restrict__ out_idx, const int* __restrict__ iflags, const int batch) {
+                          int* __restrict__ out_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
-  // without a worklist every image of the batch is merged; with one (merged pipeline) only the handed-over images
-  const int n_work = (iflags != nullptr) ? iflags[0] : batch;
-  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
-  const int b = (iflags != nullptr) ? iflags[1 + work] : work;
-  __syncthreads();  // shared memory is reused across worklist items
+  const int b = blockIdx.x;  // one CTA per image
   const u64* img_picks = picks + (size_t)b * C * limit;
   const int* cnt = pick_cnt + (size_t)b * C;
   if (stage_in_smem) {  // the binary searches below then run on shared memory instead of L2
@@ -1334,13 +1320,12 @@ __global__ void __launch_bounds__(kMergeThreads)
   if (out_idx)
     for (int e = valid + tid; e < K; e += kMergeThreads) out_idx[(size_t)b * K + e] = -1;
   if (out_valid && tid == 0) out_valid[b] = valid;
-  }  // worklist loop
 }
 
 inline int nms_limit(int max_per_class, int A) { return max_per_class < A ? max_per_class : A; }
 
 struct NmsWorkspace {
-  size_t picks, pick_cnt, lists, info, flags, iflags, total;
+  size_t picks, pick_cnt, lists, info, flags, total;
 };
 
 inline NmsWorkspace nms_workspace(int batch, int A, int C, int max_per_class) {
@@ -1353,7 +1338,6 @@ inline NmsWorkspace nms_workspace(int batch, int A, int C, int max_per_class) {
   w.lists = off;    off += ssdx_align_up(seg * kCap * sizeof(u64), 256);
   w.info = off;     off += ssdx_align_up(seg * kInfo * sizeof(int), 256);
   w.flags = off;    off += ssdx_align_up((seg + 1) * sizeof(int), 256);
-  w.iflags = off;   off += ssdx_align_up(((size_t)batch + 1) * sizeof(int), 256);
   w.total = off;
   return w;
 }
@@ -1431,7 +1415,6 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
   if (fused_src != nullptr) bx = *fused_src;
   else bx = ssdx_box_src{(const float4*)boxes_yxyx, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f};
 
-  int* iflags = (int*)(base + w.iflags);
   const bool vec4 = (C == 4) && (((uintptr_t)scores & 15) == 0);
   // test hooks: "generic" = exact generic kernel alone, "perclass" = per-class fast pipeline even when the merged
   // one applies.  All paths give identical results.
@@ -1458,31 +1441,23 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
       all_rank = all_rank < 4 ? 4 : (all_rank > kAllRank ? kAllRank : all_rank);
       if (vec4)
         ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, all_rank,
-                                                                       lists, info, flags, iflags);
+                                                                       lists, info);
       else
         ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
-                                                                        all_rank, lists, info, flags, iflags);
+                                                                        all_rank, lists, info);
       SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
     }
     if (!ph2) return SSDX_OK;
     if (max_total <= 256)
       ssdx_nms_fast_all_kernel<256, SSDX_FAST_MINB><<<batch, kFastThreads, 0, s>>>(
           bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid,
-          out_anchor_idx, flags, iflags);
+          out_anchor_idx);
     else
       ssdx_nms_fast_all_kernel<kFastMaxSel, 6><<<batch, kFastThreads, 0, s>>>(
           bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid,
-          out_anchor_idx, flags, iflags);
+          out_anchor_idx);
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_all_kernel");
-    // handed-over images only (both kernels return at once when the worklists are empty)
-    const int sms = ssdx_sm_count(device);
-    ssdx_nms_generic_kernel<<<min(num_segments, 2 * sms), kGenThreads, gen_smem, s>>>(
-        bx, scores, cscale, A, C, limit, iou_threshold, score_threshold, picks, pick_cnt, flags, num_segments);
-    SSDX_LAUNCH_CHECK("ssdx_nms_generic_kernel");
-    ssdx_nms_merge_kernel<<<min(batch, 2 * sms), kMergeThreads, stage ? merge_smem : 0, s>>>(
-        bx, picks, pick_cnt, A, C, limit, max_total, stage, out, out_valid, out_anchor_idx, iflags, batch);
-    SSDX_LAUNCH_CHECK("ssdx_nms_merge_kernel");
-    return SSDX_OK;
+    return SSDX_OK;  // (no fallback: the band refills of fast_all split even massive score ties)
   }
 
   // ---- per-class pipeline ----
@@ -1519,7 +1494,7 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
   // 4. merge
   ssdx_nms_merge_kernel<<<batch, kMergeThreads, stage ? merge_smem : 0, s>>>(bx, picks, pick_cnt, A, C, limit,
                                                                              max_total, stage, out, out_valid,
-                                                                             out_anchor_idx, nullptr, batch);
+                                                                             out_anchor_idx);
   SSDX_LAUNCH_CHECK("ssdx_nms_merge_kernel");
   return SSDX_OK;
 }

@@ -297,6 +297,29 @@ def test_nms_massive_score_ties(lib):
     nms_check(lib, yxyx, scores, 200, 400, 0.3, 0.01)
 
 
+@pytest.mark.parametrize("layout", ["spread", "stacked", "mixed"])
+def test_nms_massive_score_ties_merged_pipeline(lib, layout):
+    """max_per_class >= max_total (merged one-pass pipeline, no fallback kernel behind it) with far more equal
+    scores than the candidate list holds: the first list overflows and the composite-band refills have to split the
+    ties by class and anchor.  'stacked' = every box identical (one survivor per class after visiting all ties)."""
+    rng = np.random.default_rng(11)
+    B, A, C = 2, 6000, 3
+    ctr = rng.uniform(50, 600, size=(B, A, 2))
+    wh = rng.uniform(10, 40, size=(B, A, 2))
+    if layout == "stacked":
+        ctr[:], wh[:] = 300.0, 50.0
+    yxyx = np.concatenate([ctr - wh / 2, ctr + wh / 2], -1).astype(np.float32)
+    scores = np.ones((B, A, C), np.float32)
+    if layout == "mixed":  # a few distinct high scores, a plateau of 0.75 that overflows, a distinct tail
+        scores = orc.dedup_scores(rng.uniform(0.02, 0.7, size=(B, A, C)).astype(np.float32))
+        scores[:, 100:4000, 1:] = 0.75
+        scores[:, :20, 0] = np.linspace(0.99, 0.8, 20, dtype=np.float32)
+    out = nms_check(lib, yxyx, scores, 400, 400, 0.3, 0.01)
+    nms_check(lib, yxyx, scores, 200, 200, 0.45, 0.01)
+    if layout == "stacked":
+        assert ((out[..., 1] > 0).sum(axis=1) == C).all()  # one survivor per class
+
+
 def test_nms_degenerate_boxes_and_small_sets(lib):
     rng = np.random.default_rng(12)
     # flipped corners + zero-area boxes (never suppress, never suppressed)
