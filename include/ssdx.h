@@ -184,6 +184,27 @@ SSDX_API int ssdx_iou_pred_vs_true(const int32_t* pred_label, const float* pred_
 SSDX_API int ssdx_metric_iou_boxes(const ssdx_anchors* anchors, const float* y_true, const float* y_pred, int32_t batch,
                                    const float* std_host, float* out, ssdx_stream stream);
 
+/* ---- training losses on the encoded targets: losses.py:5-50 (localization_loss), :52-172 (confidence_loss),
+ *      SURVEY 8(f) row 3 ----
+ * ssdx_localization_loss: y_true, y_pred (B,A,4) f32 (16-byte aligned); out_loss (B) f32 = smooth-L1 summed over the
+ * anchors whose target row is not background (sum |y_true| > 0) / max(their count, 1).  out_grad (B,A,4), nullable:
+ * d out_loss[b] / d y_pred[b] as TensorFlow's autodiff derives it (-(d) inside |d| < 1, -sign(d) outside, 0 on
+ * background rows, all over the count).
+ * ssdx_confidence_loss: y_true (B,A,C) one-hot targets (column 0 = background indicator), y_pred (B,A,C)
+ * probabilities; clip_min / clip_max = the fp32 values of epsilon and 1 - epsilon (Keras epsilon 1e-7, :89-90).
+ * out_loss (B) f32 = (cross-entropy of the non-background anchors + cross-entropy of the kept background anchors) /
+ * max(non-background anchors of the image, 1); kept = the k = min(3 * positives, negatives) largest background losses
+ * of the WHOLE batch (:117, :134-138), equal losses lower flat index first.  out_grad (B,A,C) nullable: d out_loss[b] /
+ * d y_pred[b] (0 where the clip saturates); out_keep (B,A) u8 nullable: the kept background anchors.  Stream-ordered,
+ * no host synchronisation (k and the threshold stay on the device). */
+SSDX_API int ssdx_localization_loss(const float* y_true, const float* y_pred, int32_t batch, int32_t num_anchors,
+                                    float* out_loss, float* out_grad, int device, ssdx_stream stream);
+SSDX_API size_t ssdx_confidence_loss_workspace_bytes(int32_t batch, int32_t num_anchors);
+SSDX_API int ssdx_confidence_loss(const float* y_true, const float* y_pred, int32_t batch, int32_t num_anchors,
+                                  int32_t num_classes, float clip_min, float clip_max, float* out_loss, float* out_grad,
+                                  uint8_t* out_keep, void* workspace, size_t workspace_bytes, int device,
+                                  ssdx_stream stream);
+
 /* ---- GT ingest (host): datacoder.py:194-203, evaluators.py:111-121 ----
  * Parses `label,xmin,ymin,xmax,ymax` records from `text` (host).  crlf_only != 0 reproduces datacoder.py:195
  * (records split on "\r\n" only); 0 accepts "\n", "\r\n" (csv.reader).  flip_width > 0 applies the horizontal flip

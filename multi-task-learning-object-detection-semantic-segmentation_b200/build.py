@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libssdx.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["capi.cu", "decode.cu", "encode.cu", "nms.cu", "eval.cu", "seg.cu", "metric.cu", "ap.cu"]
+SOURCES = ["capi.cu", "decode.cu", "encode.cu", "nms.cu", "eval.cu", "seg.cu", "metric.cu", "ap.cu", "loss.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -5,6 +5,6 @@ side).  The model / loss / metric / plot modules of the reference are untouched 
 Importing this package loads libssdx.so; it raises ImportError if the library has not been built.
 """
 from . import _ssdx  # noqa: F401  (fails loudly when the CUDA library is missing)
-from . import boxes, datacoder, evaluators, layers, metrics  # noqa: F401
+from . import boxes, datacoder, evaluators, layers, losses, metrics  # noqa: F401
 
-__all__ = ["boxes", "datacoder", "layers", "evaluators", "metrics"]
+__all__ = ["boxes", "datacoder", "layers", "evaluators", "metrics", "losses"]

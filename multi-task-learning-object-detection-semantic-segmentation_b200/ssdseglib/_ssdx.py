@@ -61,6 +61,10 @@ SIGNATURES = {
                                          C.c_int, _vp]),
     "ssdx_iou_pred_vs_true": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
     "ssdx_metric_iou_boxes": (C.c_int, [_vp, _vp, _vp, C.c_int32, c_float_p, _vp, _vp]),
+    "ssdx_localization_loss": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int, _vp]),
+    "ssdx_confidence_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "ssdx_confidence_loss": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp,
+                                       _vp, C.c_size_t, C.c_int, _vp]),
     "ssdx_parse_gt_csv": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_float, c_i32_p, c_float_p, C.c_int32,
                                     c_i32_p]),
     "ssdx_read_gt_csv_batch": (C.c_int, [C.POINTER(C.c_char_p), C.c_int32, C.c_int, C.POINTER(C.c_uint8), C.c_float,
@@ -346,6 +350,37 @@ def metric_iou_boxes(anchors: "Anchors", y_true, y_pred, std):
     check(lib.ssdx_metric_iou_boxes(anchors.handle, ptr(y_true), ptr(y_pred), B, std_array(std), ptr(out),
                                     stream_ptr(anchors.device)))
     return out
+
+
+def localization_loss(y_true, y_pred, with_gradient: bool = False):
+    """y_true, y_pred: CUDA float32 (B,A,4).  Returns loss (B,) [, gradient (B,A,4)]."""
+    dev = y_true.device.index
+    B, A = int(y_true.shape[0]), int(y_true.shape[1])
+    out = empty((B,), np.float32, dev)
+    grad = empty((B, A, 4), np.float32, dev) if with_gradient else None
+    check(lib.ssdx_localization_loss(ptr(y_true), ptr(y_pred), B, A, ptr(out), ptr(grad) if with_gradient else None, dev,
+                                     stream_ptr(dev)))
+    return (out, grad) if with_gradient else out
+
+
+def confidence_loss(y_true, y_pred, epsilon: float = 1e-7, with_gradient: bool = False, with_keep: bool = False):
+    """y_true, y_pred: CUDA float32 (B,A,C).  Returns loss (B,) [, gradient (B,A,C)] [, kept-background mask (B,A) u8]."""
+    dev = y_true.device.index
+    B, A, Cn = (int(v) for v in y_true.shape)
+    out = empty((B,), np.float32, dev)
+    grad = empty((B, A, Cn), np.float32, dev) if with_gradient else None
+    keep = empty((B, A), np.uint8, dev) if with_keep else None
+    nbytes = int(lib.ssdx_confidence_loss_workspace_bytes(B, A))
+    ws = workspace(max(nbytes, 256), dev)
+    check(lib.ssdx_confidence_loss(ptr(y_true), ptr(y_pred), B, A, Cn, float(np.float32(epsilon)),
+                                   float(np.float32(1 - epsilon)), ptr(out), ptr(grad) if with_gradient else None,
+                                   ptr(keep) if with_keep else None, ptr(ws), ws.numel(), dev, stream_ptr(dev)))
+    res = [out]
+    if with_gradient:
+        res.append(grad)
+    if with_keep:
+        res.append(keep)
+    return res[0] if len(res) == 1 else tuple(res)
 
 
 def seg_class_presence(seg_probs, depth: int = 4):

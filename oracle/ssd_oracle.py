@@ -443,6 +443,68 @@ def metric_iou_boxes(y_true, y_pred, anchors_cxcywh, std=(0.1, 0.1, 0.2, 0.2)) -
 
 
 # --------------------------------------------------------------------------
+# 8(f) rank 3: training losses that consume the encoded targets (losses.py:5-172)
+# --------------------------------------------------------------------------
+def localization_loss(y_true, y_pred, with_gradient=False):
+    """losses.py:5-50 statement by statement: smooth-L1 over the non-background anchors of each image, divided by
+    their count (at least 1); (batch,) fp32.  with_gradient: also d loss[b] / d y_pred[b] (what TF's autodiff gives:
+    -d inside |d| < 1, -sign(d) outside, times the mask over the count)."""
+    y_true = np.asarray(y_true, F32)
+    y_pred = np.asarray(y_pred, F32)
+    nb = (np.sum(np.abs(y_true), axis=-1, dtype=F32) > 0).astype(F32)             # :23-24
+    d = y_true - y_pred
+    ea, es = np.abs(d), d * d                                                      # :27-28 (pow(x, 2) = x * x)
+    quad = ea < F32(1)                                                             # :31
+    l = np.where(quad, es * F32(0.5), ea - F32(0.5))                               # :34
+    l = np.sum(l, axis=-1, dtype=F32) * nb                                         # :37-40
+    den = np.maximum(np.sum(nb, axis=-1, dtype=F32), F32(1))                       # :47
+    loss = (np.sum(l, axis=-1, dtype=F32) / den).astype(F32)                       # :43-47
+    if not with_gradient:
+        return loss
+    g = np.where(quad, -d, -np.sign(d)).astype(F32) * nb[..., None] / den[:, None, None]
+    return loss, g.astype(F32)
+
+
+def confidence_loss(y_true, y_pred, epsilon=1e-7, with_gradient=False, return_keep=False):
+    """losses.py:52-172 statement by statement: soft-max cross-entropy with hard-negative mining.  The k =
+    min(3 * positives, negatives) background anchors with the highest loss are kept, k and the top-k taken over the
+    WHOLE batch (:117, :134-138; equal losses: lower flat index first, as tf.math.top_k), every loss divided by the
+    image's own count of non-background anchors (at least 1); (batch,) fp32."""
+    y_true = np.asarray(y_true, F32)
+    y_pred = np.asarray(y_pred, F32)
+    B, A, _ = y_true.shape
+    is_bg = y_true[:, :, 0]                                                        # :69
+    not_bg = np.abs(is_bg - F32(1))                                                # :70
+    n_bg, n_nb = int(np.count_nonzero(is_bg)), int(np.count_nonzero(not_bg))       # :73-74
+    lo, hi = F32(epsilon), F32(1 - epsilon)                                        # :89-90 (clip bounds cast to fp32)
+    clipped = np.clip(y_pred, lo, hi)
+    logp = np.log(clipped)
+    la = -np.sum(y_true * logp, axis=-1, dtype=F32)                                # :93
+    l_nb = np.sum(la * not_bg, axis=-1, dtype=F32)                                 # :100-101
+    cnt_nb = np.sum(not_bg, axis=-1, dtype=F32)                                    # :104
+    k = min(3 * n_nb, n_bg)                                                        # :117
+    v = la * is_bg                                                                 # :120
+    keep = np.zeros(B * A, F32)
+    if n_bg > 0:                                                                   # :123
+        order = np.argsort(-v.reshape(-1), kind="stable")[:k]                      # :134-138
+        keep[order] = 1                                                            # :143-152
+    keep = keep.reshape(B, A)
+    l_bg = np.sum(v * keep, axis=-1, dtype=F32)                                    # :156-159
+    den = np.maximum(cnt_nb, F32(1))
+    loss = ((l_nb + l_bg) / den).astype(F32)                                       # :169-172
+    out = [loss]
+    if with_gradient:
+        w = not_bg + is_bg * keep                                                  # weight of each anchor's loss
+        passes = ((y_pred >= lo) & (y_pred <= hi)).astype(F32)                     # clip_by_value passes inside [lo, hi]
+        g = -(w / den[:, None])[..., None] * y_true / clipped * passes
+        out.append(g.astype(F32))
+    if return_keep:
+        out.append(keep.astype(np.uint8))
+        out.append(v.astype(F32))
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+# --------------------------------------------------------------------------
 # a17-a18: detection evaluation (evaluators.py:6-187)  [P7]
 # --------------------------------------------------------------------------
 def iou_pred_vs_true(labels_pred, boxes_pred, labels_true, boxes_true) -> np.ndarray:

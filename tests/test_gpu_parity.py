@@ -518,6 +518,103 @@ def test_box_iou_metric_golden_and_full_batch(lib, golden, std_anchors, coder):
         metric(y_true[:, :100], y_pred[:, :100])
 
 
+# ------------------------------------------------------------------------------------------- training losses
+def assert_kept_equal(keep, keep_ref, v_ref):
+    """The kept background set is index work: equal to the oracle's except, possibly, anchors whose loss lies within a
+    few ulp of the selection threshold (logf on the GPU vs NumPy's log differ by <= 2 ulp)."""
+    diff = keep != keep_ref
+    if not diff.any():
+        return
+    thr = v_ref[keep_ref == 1].min()
+    assert np.all(np.abs(v_ref[diff] - thr) <= 8 * np.spacing(np.float32(thr))), int(diff.sum())
+    assert int(keep.sum()) == int(keep_ref.sum())
+
+
+def test_localization_loss_golden_and_full_batch(lib, golden, coder):
+    g = golden("losses")
+    got = lib.losses.localization_loss(g["loc_y_true"], g["loc_y_pred"])
+    assert got.shape == (6,) and got.dtype == np.float32
+    np.testing.assert_allclose(got, g["loc_value"], rtol=RTOL)
+    assert got[2] == 0 and got[4] == 0
+    rng = np.random.default_rng(18)
+    labels, boxes, counts = orc.synth_gt(rng, 300, 16)
+    counts[7] = 0
+    _, y_true = coder.encode_batch(boxes, labels, counts)
+    y_pred = (y_true + rng.normal(0, 0.9, y_true.shape)).astype(np.float32)
+    loss, grad = lib.losses.localization_loss(y_true, y_pred, with_gradient=True)
+    ref, gref = orc.localization_loss(y_true, y_pred, with_gradient=True)
+    np.testing.assert_allclose(loss, ref, rtol=RTOL)
+    np.testing.assert_allclose(grad, gref, rtol=RTOL, atol=1e-12)
+    assert np.array_equal(grad != 0, gref != 0) and loss[7] == 0
+    with pytest.raises(ValueError):
+        lib.losses.localization_loss(y_true[:, :, :3], y_pred[:, :, :3])
+
+
+def test_confidence_loss_golden(lib, golden):
+    g = golden("losses")
+    got, keep = lib.losses.confidence_loss(g["conf_y_true"], g["conf_y_pred"], return_kept_background=True)
+    assert got.shape == (6,) and got.dtype == np.float32
+    np.testing.assert_allclose(got, g["conf_value"], rtol=RTOL)
+    _, keep_ref, v_ref = orc.confidence_loss(g["conf_y_true"], g["conf_y_pred"], return_keep=True)
+    assert_kept_equal(keep, keep_ref, v_ref)
+    got = lib.losses.confidence_loss(g["conf_y_true"][2:3], g["conf_y_pred"][2:3])      # no positive: k = 0
+    assert np.array_equal(got, g["conf_value_no_positive"])
+    got = lib.losses.confidence_loss(g["conf_few_y_true"], g["conf_few_y_pred"])        # k = all negatives
+    np.testing.assert_allclose(got, g["conf_few_value"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("B,A,C", [(64, 9600, 4), (5, 1001, 3), (3, 777, 21)])
+def test_confidence_loss_random_batches_with_gradient(lib, B, A, C):
+    rng = np.random.default_rng(B + C)
+    cls = rng.integers(1, C, (B, A)) * (rng.uniform(size=(B, A)) < 0.02)
+    y_true = np.zeros((B, A, C), np.float32)
+    np.put_along_axis(y_true, cls[..., None], 1.0, axis=-1)
+    y_pred = orc.softmax_f32((rng.normal(0, 2, (B, A, C)) + 1.5 * y_true).astype(np.float32))
+    y_pred[0, :50] = 0
+    y_pred[0, :50, 0] = 1                                    # saturated: both clip bounds, zero gradient there
+    loss, grad, keep = lib.losses.confidence_loss(y_true, y_pred, with_gradient=True, return_kept_background=True)
+    ref, gref, keep_ref, v_ref = orc.confidence_loss(y_true, y_pred, with_gradient=True, return_keep=True)
+    np.testing.assert_allclose(loss, ref, rtol=RTOL)
+    assert_kept_equal(keep, keep_ref, v_ref)
+    same = (keep == keep_ref)[..., None] & np.ones(C, bool)
+    np.testing.assert_allclose(grad[same], gref[same], rtol=RTOL, atol=1e-12)
+    assert int(keep.sum()) == min(3 * int((cls > 0).sum()), int((cls == 0).sum()))
+
+
+def test_confidence_loss_threshold_ties_are_split_in_index_order(lib):
+    """Thousands of background boxes with the SAME loss straddle the threshold (saturated predictions): the tied ones
+    are kept lower flat index first (tf.math.top_k), across image boundaries; here the kept set is bit-exact."""
+    B, A, C = 6, 2000, 4
+    y_true = np.zeros((B, A, C), np.float32)
+    y_true[..., 0] = 1
+    y_true[:, 10:40] = np.array([0, 0, 1, 0], np.float32)          # 30 positives per image -> k = 540
+    y_pred = np.full((B, A, C), 0.25, np.float32)                   # every background loss = log 4
+    y_pred[:, 100:110] = np.array([0.125, 0.5, 0.25, 0.125], np.float32)   # 10 per image clearly above
+    loss, keep = lib.losses.confidence_loss(y_true, y_pred, return_kept_background=True)
+    ref, keep_ref, _ = orc.confidence_loss(y_true, y_pred, return_keep=True)
+    assert np.array_equal(keep, keep_ref)
+    assert keep.sum(axis=1).tolist() == keep_ref.sum(axis=1).tolist() and keep[0].sum() == 490 and keep[2].sum() == 10
+    np.testing.assert_allclose(loss, ref, rtol=RTOL)
+    # no background box at all: the background part is zero (losses.py:123-124)
+    y_true[..., 0], y_true[..., 1] = 0, 1
+    got = lib.losses.confidence_loss(y_true, y_pred)
+    np.testing.assert_allclose(got, orc.confidence_loss(y_true, y_pred), rtol=RTOL)
+
+
+def test_losses_on_device_tensors(lib, golden):
+    import torch
+
+    g = golden("losses")
+    yt, yp = torch.from_numpy(g["conf_y_true"]).cuda(), torch.from_numpy(g["conf_y_pred"]).cuda()
+    out = lib.losses.confidence_loss(yt, yp)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    np.testing.assert_allclose(out.cpu().numpy(), g["conf_value"], rtol=RTOL)
+    lt, lp = torch.from_numpy(g["loc_y_true"]).cuda(), torch.from_numpy(g["loc_y_pred"]).cuda()
+    out, grad = lib.losses.localization_loss(lt, lp, with_gradient=True)
+    assert out.is_cuda and grad.shape == lt.shape
+    np.testing.assert_allclose(out.cpu().numpy(), g["loc_value"], rtol=RTOL)
+
+
 # ------------------------------------------------------------------------------------------- eval
 def test_eval_golden(lib, golden, tmp_path):
     g = golden("eval")

@@ -182,6 +182,61 @@ def test_box_iou_metric_matches_reference_source(golden, std_anchors):
     assert abs(float(got[2]) - 1.0) < 1e-6      # perfect predictions
 
 
+def test_losses_match_reference_source(golden):
+    """the oracle against losses.localization_loss / confidence_loss executed from the reference's
+    file (fixture: tests/golden/make_golden_losses.py), incl. an all-background image, saturated probabilities (both
+    clip bounds), a batch without positives (k = 0) and one with more positives than a third of the negatives."""
+    g = golden("losses")
+    np.testing.assert_allclose(orc.localization_loss(g["loc_y_true"], g["loc_y_pred"]), g["loc_value"], rtol=1e-6)
+    assert g["loc_value"][2] == 0 and g["loc_value"][4] == 0      # all background / perfect prediction
+    np.testing.assert_allclose(orc.confidence_loss(g["conf_y_true"], g["conf_y_pred"]), g["conf_value"], rtol=1e-6)
+    np.testing.assert_allclose(orc.confidence_loss(g["conf_y_true"][2:3], g["conf_y_pred"][2:3]),
+                               g["conf_value_no_positive"], rtol=0, atol=0)
+    np.testing.assert_allclose(orc.confidence_loss(g["conf_few_y_true"], g["conf_few_y_pred"]), g["conf_few_value"],
+                               rtol=1e-6)
+    # hard-negative mining: exactly min(3 * positives, negatives) background boxes are kept, the largest losses first
+    _, keep, v = orc.confidence_loss(g["conf_y_true"], g["conf_y_pred"], return_keep=True)
+    n_pos = int((g["conf_y_true"][..., 0] == 0).sum())
+    assert int(keep.sum()) == 3 * n_pos and v[keep == 1].min() >= v[(keep == 0) & (g["conf_y_true"][..., 0] == 1)].max()
+
+
+def test_loss_gradients_match_finite_differences():
+    """The analytic gradients of the oracle (what the CUDA kernels are checked against) against central differences of
+    a float64 restatement of the same statements on a small case."""
+    rng = np.random.default_rng(4)
+    B, A, C = 2, 40, 4
+    y_true = np.zeros((B, A, 4), np.float32)
+    y_true[:, ::5] = rng.normal(0, 1, (B, 8, 4))
+    y_pred = (y_true + rng.normal(0, 0.8, y_true.shape)).astype(np.float32)
+    _, g = orc.localization_loss(y_true, y_pred, with_gradient=True)
+
+    def loc64(p):
+        nb = (np.abs(y_true).sum(-1) > 0).astype(np.float64)
+        d = y_true.astype(np.float64) - p
+        l = np.where(np.abs(d) < 1, 0.5 * d * d, np.abs(d) - 0.5).sum(-1) * nb
+        return l.sum(-1) / np.maximum(nb.sum(-1), 1)
+
+    lab = np.zeros((B, A, C), np.float32)
+    cls = rng.integers(0, C, (B, A)) * (rng.uniform(size=(B, A)) < 0.15)
+    np.put_along_axis(lab, cls[..., None], 1.0, axis=-1)
+    prob = orc.softmax_f32(rng.normal(0, 1, (B, A, C)).astype(np.float32))
+    _, gc, keep, _ = orc.confidence_loss(lab, prob, with_gradient=True, return_keep=True)
+
+    def conf64(p):
+        la = -(lab * np.log(np.clip(p, 1e-7, 1 - 1e-7))).sum(-1)
+        w = (1 - lab[..., 0]) + lab[..., 0] * keep
+        return (la * w).sum(-1) / np.maximum((1 - lab[..., 0]).sum(-1), 1)
+
+    for f, x0, grad in ((loc64, y_pred.astype(np.float64), g), (conf64, prob.astype(np.float64), gc)):
+        for _ in range(25):
+            b, a, c = rng.integers(0, B), rng.integers(0, A), rng.integers(0, x0.shape[-1])
+            xp, xm = x0.copy(), x0.copy()
+            xp[b, a, c] += 1e-6
+            xm[b, a, c] -= 1e-6
+            fd = (f(xp)[b] - f(xm)[b]) / 2e-6
+            assert abs(fd - grad[b, a, c]) <= 1e-4 * max(1.0, abs(fd)), (b, a, c, fd, grad[b, a, c])
+
+
 def test_closed_form_equals_literal_property():
     """Property test (hypothesis): on small integer grids, where exact IoU ties and duplicated winners are the rule,
     the closed form of SURVEY P3 equals the literal concat -> unique -> sequential scatter for every threshold."""
