@@ -82,6 +82,33 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
                : "memory");
 }
 
+// Soft-max of a row of logits, the arithmetic every kernel that accepts logits shares (the Keras soft-max activation
+// of the reference's class head: exp(x - max) / sum).  Exponential = ONE hardware instruction, ex2.approx.ftz of
+// (x - max) * log2 e (2 ulp + the rounding of the product: ~(2 + 1.2 |x - max|) ulp per term); the sum runs in class
+// order; the normaliser is ONE rcp.approx.ftz (1 ulp; the sum lies in [1, C]).  Within ~4e-6 relative of the exact
+// value for |x - max| < 25 - inside the 1e-5 fp32 tolerance of the path - and 23 instructions per 4-class row, cheap
+// enough to sit inside the NMS score filter.  (expf + IEEE division cost ~140 instructions per row and made that
+// kernel ALU-bound: 81 us instead of 33 us per 1024 images; __expf / __frcp_rn without .ftz expand to multi-
+// instruction sequences as well.)  One instruction sequence everywhere (-fmad=false: no contraction), so every call
+// site produces the same bits.
+__device__ __forceinline__ float ssdx_softmax_exp(const float x, const float m) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(__fsub_rn(x, m), 1.4426950408889634f)));
+  return e;
+}
+__device__ __forceinline__ float ssdx_softmax_rcp(const float s) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+  return r;
+}
+__device__ __forceinline__ float4 ssdx_softmax4(const float4 x) {
+  const float m = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+  const float e0 = ssdx_softmax_exp(x.x, m), e1 = ssdx_softmax_exp(x.y, m);
+  const float e2 = ssdx_softmax_exp(x.z, m), e3 = ssdx_softmax_exp(x.w, m);
+  const float r = ssdx_softmax_rcp(__fadd_rn(__fadd_rn(__fadd_rn(e0, e1), e2), e3));
+  return make_float4(__fmul_rn(e0, r), __fmul_rn(e1, r), __fmul_rn(e2, r), __fmul_rn(e3, r));
+}
+
 // layers.py:57-79 for one anchor: ((t*s)*d)+c, (exp(t*s)-1)*d, c -/+ (s-1)/2 -> (ymin, xmin, ymax, xmax).  One definition
 // shared by the decode kernel and by the NMS kernels that decode their candidates on the fly (ssdx_decode_nms), so
 // that both produce the same bits.

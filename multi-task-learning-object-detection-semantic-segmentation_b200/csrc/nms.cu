@@ -657,11 +657,14 @@ __global__ void __launch_bounds__(kFastThreads, 6)
 
 // ------------------------------------------------------------------------------------------ 1m. merged select
 // info per image: [0] listed candidates (may exceed kCap), [1] threshold key (every candidate with key >= it is listed)
-template <bool VEC4>
+template <bool VEC4, bool LOGITS>
 __global__ void __launch_bounds__(kSelThreads)
     ssdx_nms_select_all_kernel(const float* __restrict__ scores, const float* __restrict__ cscale, const int A,
                                const int C, const float score_thr, const int all_rank, u64* __restrict__ lists,
                                int* __restrict__ info) {
+  constexpr bool logits = LOGITS;
+  // LOGITS (VEC4 only): `scores` holds raw logits, the probabilities are ssdx_softmax4 of each row, computed as
+  // the rows are read (never written to memory)
   __shared__ unsigned s_max[kSelThreads];  // per-thread maximum of the sampled keys
   __shared__ unsigned s_T;
   __shared__ int s_cnt;
@@ -678,7 +681,9 @@ __global__ void __launch_bounds__(kSelThreads)
       int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
       a = a < A ? a : A - 1;
       if (VEC4) {
-        const float4 s = mul4(__ldg(reinterpret_cast<const float4*>(img) + a), class_factor4(cscale));
+        float4 raw = __ldg(reinterpret_cast<const float4*>(img) + a);
+        if (logits) raw = ssdx_softmax4(raw);
+        const float4 s = mul4(raw, class_factor4(cscale));
         const float m = fmaxf(fmaxf(s.x, s.y), fmaxf(s.z, s.w));
         if (m > score_thr) kmax = max(kmax, score_to_key(m));
       } else {
@@ -746,12 +751,18 @@ __global__ void __launch_bounds__(kSelThreads)
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int a = a0 + u * kSelThreads;
-        sb[u] = (a < A) ? mul4(__ldcs(reinterpret_cast<const float4*>(img) + a), cf4)
+        sb[u] = (a < A) ? __ldcs(reinterpret_cast<const float4*>(img) + a)
                         : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+      if (logits) {
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          if (a0 + u * kSelThreads < A) sb[u] = ssdx_softmax4(sb[u]);
       }
       unsigned hits = 0u;  // bit 4*u + c
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
+        sb[u] = mul4(sb[u], cf4);
         hits |= (sb[u].x >= t_lo ? 1u : 0u) << (4 * u);
         hits |= (sb[u].y >= t_lo ? 2u : 0u) << (4 * u);
         hits |= (sb[u].z >= t_lo ? 4u : 0u) << (4 * u);
@@ -761,7 +772,13 @@ __global__ void __launch_bounds__(kSelThreads)
         const int bit = __ffs(hits) - 1;
         hits &= hits - 1u;
         const int a = a0 + (bit >> 2) * kSelThreads, c = bit & 3;
-        const float s = __fmul_rn(__ldg(img + (size_t)a * 4 + c), class_factor(cscale, c));
+        float s;
+        if (logits) {
+          const float4 p = ssdx_softmax4(__ldg(reinterpret_cast<const float4*>(img) + a));
+          s = __fmul_rn(c == 0 ? p.x : (c == 1 ? p.y : (c == 2 ? p.z : p.w)), class_factor(cscale, c));
+        } else {
+          s = __fmul_rn(__ldg(img + (size_t)a * 4 + c), class_factor(cscale, c));
+        }
         const int pos = atomicAdd(&s_cnt, 1);
         if (pos < kCap) lst[pos] = make_comp_all(score_to_key(s), c, a);
       }
@@ -785,12 +802,14 @@ __global__ void __launch_bounds__(kSelThreads)
 }
 
 // ------------------------------------------------------------------------------------------ 2m. merged fast path
-template <int MAXSEL, int MINB>  // MAXSEL >= K; MINB resident CTAs per SM (7 * 148 >= 1024: one wave at batch 1024)
+template <int MAXSEL, int MINB, bool LOGITS>  // MAXSEL >= K; MINB resident CTAs per SM (7 * 148 >= 1024: one wave at
+                                              // batch 1024); LOGITS: `scores` holds raw logits of 4 classes
 __global__ void __launch_bounds__(kFastThreads, MINB)
     ssdx_nms_fast_all_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                              const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                              const int K, const float iou_thr, const float score_thr, float* __restrict__ out,
                              int* __restrict__ out_valid, int* __restrict__ out_idx) {
+  constexpr bool logits = LOGITS;
   __shared__ u64 s_list[kCap];
   __shared__ u64 s_tmp[kCap];  // second exchange buffer of the sort; the candidate arrays below alias it
   __shared__ float4 s_sbox[MAXSEL];
@@ -980,28 +999,55 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
       if (tid == 0) s_n = 0;
       __syncthreads();
       const unsigned key_lo = (unsigned)(comp_lo >> 32), key_hi32 = (unsigned)((comp_hi - 1ull) >> 32);
-      const int total = A * C;
-      for (int e0 = tid; e0 < total; e0 += kFastThreads * 8) {  // 8 independent loads in flight per thread
-        float sv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * kFastThreads;
-          sv[u] = (e < total) ? (cscale ? __fmul_rn(__ldg(img_scores + e), __ldg(cscale + e % C)) : __ldg(img_scores + e))
-                              : -INFINITY;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (sv[u] > score_thr) {  // false for the -inf padding
-            const unsigned key = score_to_key(sv[u]);
-            if (key >= key_lo && key <= key_hi32) {  // cheap 32-bit pre-test, then the exact composite band
-              const int e = e0 + u * kFastThreads;
-              const int a = e / C;
-              const u64 cp = make_comp_all(key, e - a * C, a);
-              if (cp >= comp_lo && cp < comp_hi) {
-                const int pos = atomicAdd(&s_n, 1);
-                if (pos < kCap) s_list[pos] = cp;
-              }
+      auto consider = [&](const float sc, const int a, const int c) {
+        if (sc > score_thr) {  // false for the -inf padding
+          const unsigned key = score_to_key(sc);
+          if (key >= key_lo && key <= key_hi32) {  // cheap 32-bit pre-test, then the exact composite band
+            const u64 cp = make_comp_all(key, c, a);
+            if (cp >= comp_lo && cp < comp_hi) {
+              const int pos = atomicAdd(&s_n, 1);
+              if (pos < kCap) s_list[pos] = cp;
             }
+          }
+        }
+      };
+      if (logits) {  // (C == 4) rows of logits: probabilities recomputed as in the select kernel
+        const float4 cf4 = class_factor4(cscale);
+        for (int a0 = tid; a0 < A; a0 += kFastThreads * 4) {
+          float4 r[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * kFastThreads;
+            r[u] = (a < A) ? __ldg(reinterpret_cast<const float4*>(img_scores) + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * kFastThreads;
+            if (a < A) {
+              const float4 p = mul4(ssdx_softmax4(r[u]), cf4);
+              consider(p.x, a, 0);
+              consider(p.y, a, 1);
+              consider(p.z, a, 2);
+              consider(p.w, a, 3);
+            }
+          }
+        }
+      } else {
+        const int total = A * C;
+        for (int e0 = tid; e0 < total; e0 += kFastThreads * 8) {  // 8 independent loads in flight per thread
+          float sv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * kFastThreads;
+            sv[u] = (e < total)
+                        ? (cscale ? __fmul_rn(__ldg(img_scores + e), __ldg(cscale + e % C)) : __ldg(img_scores + e))
+                        : -INFINITY;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * kFastThreads;
+            const int a = e / C;
+            consider(sv[u], a, e - a * C);
           }
         }
       }
@@ -1370,12 +1416,20 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
                          device, stream);
 }
 
+// the merged one-pass-per-image pipeline applies (SSDX_NMS_PATH = generic | perclass force the other paths: test hooks)
+static bool nms_merged_applies(const int A, const int C, const int max_per_class, const int max_total) {
+  const char* force = getenv("SSDX_NMS_PATH");
+  if (force != nullptr && (force[0] == 'g' || force[0] == 'p')) return false;
+  return max_per_class >= max_total && C <= 256 && A <= (1 << 24) && (long long)A * C < (1ll << 31) &&
+         max_total <= kFastMaxSel;
+}
+
 // phases: 1 = candidate selection (reads only the scores), 2 = everything that needs the boxes.  ssdx_nms runs both;
 // ssdx_nms_select / ssdx_nms_finish expose them separately so that a caller can run phase 1 on another stream while
 // the boxes are still being decoded (in the reference's inference graph the two inputs of the NMS layer are
 // independent branches, models.py:402-414).
-static int nms_run(const int phases, const ssdx_box_src* fused_src, const float* boxes_yxyx, const float* scores,
-                   const float* class_scale,
+static int nms_run(const int phases, const int logits, const ssdx_box_src* fused_src, const float* boxes_yxyx,
+                   const float* scores, const float* class_scale,
                    int32_t batch, int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
                    float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
                    int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device, ssdx_stream stream) {
@@ -1420,7 +1474,6 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
   // one applies.  All paths give identical results.
   const char* force = getenv("SSDX_NMS_PATH");
   const bool force_generic = force != nullptr && force[0] == 'g';
-  const bool force_perclass = force != nullptr && force[0] == 'p';
   const size_t gen_smem_attr = gen_smem;
   SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)gen_smem_attr));
@@ -1432,30 +1485,36 @@ static int nms_run(const int phases, const ssdx_box_src* fused_src, const float*
                                    (int)merge_smem));
 
   // ---- merged pipeline: one list / sort / greedy pass per image ----
-  const bool merged = !force_generic && !force_perclass && max_per_class >= max_total && C <= 256 &&
-                      A <= (1 << 24) && (long long)A * C < (1ll << 31) && max_total <= kFastMaxSel;
+  const bool merged = nms_merged_applies(A, C, max_per_class, max_total);
+  SSDX_CHECK_ARG(!logits || (merged && vec4), "ssdx_nms: logits need the merged pipeline with 4 aligned classes");
   if (merged) {
     if (ph1) {
       // first list sized to max_total (rank (3 K + 63) / 16 of the thread maxima, at most kAllRank = the K = 200 tuning)
       int all_rank = (3 * max_total + 63) / 16;
       all_rank = all_rank < 4 ? 4 : (all_rank > kAllRank ? kAllRank : all_rank);
-      if (vec4)
-        ssdx_nms_select_all_kernel<true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, all_rank,
-                                                                       lists, info);
+      if (logits)
+        ssdx_nms_select_all_kernel<true, true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
+                                                                             all_rank, lists, info);
+      else if (vec4)
+        ssdx_nms_select_all_kernel<true, false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
+                                                                              all_rank, lists, info);
       else
-        ssdx_nms_select_all_kernel<false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
-                                                                        all_rank, lists, info);
+        ssdx_nms_select_all_kernel<false, false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
+                                                                               all_rank, lists, info);
       SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
     }
     if (!ph2) return SSDX_OK;
-    if (max_total <= 256)
-      ssdx_nms_fast_all_kernel<256, SSDX_FAST_MINB><<<batch, kFastThreads, 0, s>>>(
-          bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid,
-          out_anchor_idx);
-    else
-      ssdx_nms_fast_all_kernel<kFastMaxSel, 6><<<batch, kFastThreads, 0, s>>>(
-          bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid,
-          out_anchor_idx);
+#define SSDX_FAST_ALL(MAXSEL, MINB, LOG)                                                                            \
+  ssdx_nms_fast_all_kernel<MAXSEL, MINB, LOG><<<batch, kFastThreads, 0, s>>>(                                       \
+      bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx)
+    if (max_total <= 256) {
+      if (logits) SSDX_FAST_ALL(256, SSDX_FAST_MINB, true);
+      else SSDX_FAST_ALL(256, SSDX_FAST_MINB, false);
+    } else {
+      if (logits) SSDX_FAST_ALL(kFastMaxSel, 6, true);
+      else SSDX_FAST_ALL(kFastMaxSel, 6, false);
+    }
+#undef SSDX_FAST_ALL
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_all_kernel");
     return SSDX_OK;  // (no fallback: the band refills of fast_all split even massive score ties)
   }
@@ -1504,7 +1563,7 @@ extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, con
                                float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
                                int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
                                ssdx_stream stream) {
-  return nms_run(3, nullptr, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
+  return nms_run(3, 0, nullptr, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
                  iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes, device,
                  stream);
 }
@@ -1512,7 +1571,7 @@ extern "C" int ssdx_nms_scaled(const float* boxes_yxyx, const float* scores, con
 extern "C" int ssdx_nms_select(const float* scores, const float* class_scale, int32_t batch, int32_t num_anchors,
                                int32_t num_classes, int32_t max_per_class, int32_t max_total, float score_threshold,
                                void* workspace, size_t workspace_bytes, int device, ssdx_stream stream) {
-  return nms_run(1, nullptr, nullptr, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total, 0.5f,
+  return nms_run(1, 0, nullptr, nullptr, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total, 0.5f,
                  score_threshold, nullptr, nullptr, nullptr, workspace, workspace_bytes, device, stream);
 }
 
@@ -1521,7 +1580,7 @@ extern "C" int ssdx_nms_finish(const float* boxes_yxyx, const float* scores, con
                                float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
                                int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
                                ssdx_stream stream) {
-  return nms_run(2, nullptr, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
+  return nms_run(2, 0, nullptr, boxes_yxyx, scores, class_scale, batch, num_anchors, num_classes, max_per_class, max_total,
                  iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes, device,
                  stream);
 }
@@ -1536,7 +1595,46 @@ extern "C" int ssdx_decode_nms(const ssdx_anchors* anchors, const float* offsets
   SSDX_CHECK_ARG(((uintptr_t)offsets & 15) == 0, "ssdx_decode_nms: offsets must be 16-byte aligned");
   const ssdx_box_src src{nullptr, (const float4*)offsets, anchors->dec_cent, std_host[0], std_host[1], std_host[2],
                          std_host[3]};
-  return nms_run(3, &src, nullptr, scores, class_scale, batch, anchors->A, num_classes, max_per_class, max_total,
+  return nms_run(3, 0, &src, nullptr, scores, class_scale, batch, anchors->A, num_classes, max_per_class, max_total,
                  iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes,
                  anchors->device, stream);
+}
+
+// ---- NMS on raw logits: soft-max fused into the score filter ----
+extern "C" size_t ssdx_nms_logits_workspace_bytes(int32_t batch, int32_t num_anchors, int32_t num_classes,
+                                                  int32_t max_per_class, int32_t max_total) {
+  const size_t base = ssdx_nms_workspace_bytes(batch, num_anchors, num_classes, max_per_class, max_total);
+  if (base == 0) return 0;
+  // room to materialise the probabilities when the fused path does not apply (class count != 4, binding per-class cap)
+  return ssdx_align_up(base, 256) + ssdx_align_up((size_t)batch * num_anchors * num_classes * sizeof(float), 256);
+}
+
+extern "C" int ssdx_nms_logits(const float* boxes_yxyx, const float* logits, const float* class_scale, int32_t batch,
+                               int32_t num_anchors, int32_t num_classes, int32_t max_per_class, int32_t max_total,
+                               float iou_threshold, float score_threshold, float* out, int32_t* out_valid,
+                               int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
+                               ssdx_stream stream) {
+  SSDX_CHECK_ARG(logits != nullptr, "ssdx_nms_logits: NULL pointer argument");
+  SSDX_CHECK_ARG(batch >= 0 && num_anchors > 0 && num_classes > 0, "ssdx_nms_logits: bad shape (B=%d, A=%d, C=%d)", batch,
+                 num_anchors, num_classes);
+  SSDX_CHECK_ARG(max_per_class > 0 && max_total > 0, "ssdx_nms_logits: max_per_class and max_total must be > 0");
+  const size_t need = ssdx_nms_logits_workspace_bytes(batch, num_anchors, num_classes, max_per_class, max_total);
+  if (workspace == nullptr || workspace_bytes < need) {
+    ssdx_set_error("ssdx_nms_logits: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return SSDX_ERR_WORKSPACE;
+  }
+  const bool fused = num_classes == 4 && (((uintptr_t)logits & 15) == 0) &&
+                     nms_merged_applies(num_anchors, num_classes, max_per_class, max_total);
+  if (fused)  // the probabilities exist only in registers
+    return nms_run(3, 1, nullptr, boxes_yxyx, logits, class_scale, batch, num_anchors, num_classes, max_per_class,
+                   max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes,
+                   device, stream);
+  const size_t base = ssdx_align_up(
+      ssdx_nms_workspace_bytes(batch, num_anchors, num_classes, max_per_class, max_total), 256);
+  float* probs = (float*)((char*)workspace + base);
+  const int rc = ssdx_softmax_scores(logits, (int64_t)batch * num_anchors, num_classes, nullptr, probs, device, stream);
+  if (rc != SSDX_OK) return rc;
+  return nms_run(3, 0, nullptr, boxes_yxyx, probs, class_scale, batch, num_anchors, num_classes, max_per_class,
+                 max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, base, device,
+                 stream);
 }

@@ -108,7 +108,74 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// probabilities = softmax(logits) [* class_scale], one row per anchor (materialised form; the NMS can also take
+// the logits directly: ssdx_nms_logits)
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+    ssdx_softmax_scores_kernel(const float* __restrict__ logits, const long long rows, const int C,
+                               const float* __restrict__ cscale, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * 256;
+  if (VEC4) {
+    const float4 sc = cscale ? make_float4(__ldg(cscale), __ldg(cscale + 1), __ldg(cscale + 2), __ldg(cscale + 3))
+                             : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4* in4 = reinterpret_cast<const float4*>(logits);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    for (long long r0 = (long long)blockIdx.x * 256 + threadIdx.x; r0 < rows; r0 += stride * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * stride;
+        v[u] = (r < rows) ? ld_stream_f4(in4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * stride;
+        if (r < rows) {
+          const float4 p = ssdx_softmax4(v[u]);
+          st_stream_f4(out4 + r, cscale ? make_float4(__fmul_rn(p.x, sc.x), __fmul_rn(p.y, sc.y), __fmul_rn(p.z, sc.z),
+                                                      __fmul_rn(p.w, sc.w))
+                                        : p);
+        }
+      }
+    }
+  } else {
+    for (long long r = (long long)blockIdx.x * 256 + threadIdx.x; r < rows; r += stride) {
+      const float* x = logits + r * C;
+      float m = __ldg(x);
+      for (int c = 1; c < C; ++c) m = fmaxf(m, __ldg(x + c));
+      float sum = 0.0f;
+      for (int c = 0; c < C; ++c) sum = __fadd_rn(sum, ssdx_softmax_exp(__ldg(x + c), m));
+      const float rs = ssdx_softmax_rcp(sum);
+      for (int c = 0; c < C; ++c) {
+        const float p = __fmul_rn(ssdx_softmax_exp(__ldg(x + c), m), rs);
+        out[r * C + c] = cscale ? __fmul_rn(p, __ldg(cscale + c)) : p;
+      }
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int ssdx_softmax_scores(const float* logits, int64_t rows, int32_t num_classes, const float* class_scale,
+                                   float* out, int device, ssdx_stream stream) {
+  SSDX_CHECK_ARG(logits != nullptr && out != nullptr, "ssdx_softmax_scores: NULL pointer argument");
+  SSDX_CHECK_ARG(rows >= 0 && num_classes >= 1, "ssdx_softmax_scores: bad shape");
+  if (rows == 0) return SSDX_OK;
+  SSDX_CUDA(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int sms = ssdx_sm_count(device);
+  const bool vec4 = num_classes == 4 && (((uintptr_t)logits | (uintptr_t)out) & 15) == 0;
+  long long grid = (rows + 256 * 4 - 1) / (256 * 4);
+  const long long cap = (long long)sms * 16;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  if (vec4)
+    ssdx_softmax_scores_kernel<true><<<(int)grid, 256, 0, s>>>(logits, rows, num_classes, class_scale, out);
+  else
+    ssdx_softmax_scores_kernel<false><<<(int)grid, 256, 0, s>>>(logits, rows, num_classes, class_scale, out);
+  SSDX_LAUNCH_CHECK("ssdx_softmax_scores_kernel");
+  return SSDX_OK;
+}
 
 extern "C" int ssdx_seg_class_presence(const float* seg_probs, int64_t num_pixels, int32_t cm, int32_t depth,
                                        float* out_presence, void* workspace, size_t workspace_bytes, int device,

@@ -61,6 +61,10 @@ SIGNATURES = {
                                          C.c_int, _vp]),
     "ssdx_iou_pred_vs_true": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
     "ssdx_metric_iou_boxes": (C.c_int, [_vp, _vp, _vp, C.c_int32, c_float_p, _vp, _vp]),
+    "ssdx_softmax_scores": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int, _vp]),
+    "ssdx_nms_logits_workspace_bytes": (C.c_size_t, [C.c_int32] * 5),
+    "ssdx_nms_logits": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                  C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
     "ssdx_localization_loss": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int, _vp]),
     "ssdx_confidence_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "ssdx_confidence_loss": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp,
@@ -287,6 +291,31 @@ def nms(boxes_yxyx, scores, max_per_class: int, max_total: int, iou_threshold: f
                               int(max_total), float(iou_threshold), float(score_threshold), ptr(out), ptr(valid),
                               ptr(aidx), ptr(ws), ws.numel(), dev, stream_ptr(dev)))
     return out, valid, aidx
+
+
+def nms_logits(boxes_yxyx, logits, max_per_class: int, max_total: int, iou_threshold: float, score_threshold: float,
+               want_aux: bool = False, class_scale=None):
+    """NMS on raw class logits: soft-max fused into the score filter (ssdx_nms_logits)."""
+    B, A, Cn = (int(v) for v in logits.shape)
+    dev = boxes_yxyx.device.index
+    out = empty((B, max_total, 6), np.float32, dev)
+    valid = empty((B,), np.int32, dev) if want_aux else None
+    aidx = empty((B, max_total), np.int32, dev) if want_aux else None
+    ws = workspace(lib.ssdx_nms_logits_workspace_bytes(B, A, Cn, max_per_class, max_total), dev)
+    check(lib.ssdx_nms_logits(ptr(boxes_yxyx), ptr(logits), ptr(class_scale), B, A, Cn, int(max_per_class),
+                              int(max_total), float(iou_threshold), float(score_threshold), ptr(out), ptr(valid),
+                              ptr(aidx), ptr(ws), ws.numel(), dev, stream_ptr(dev)))
+    return out, valid, aidx
+
+
+def softmax_scores(logits, class_scale=None):
+    """logits: CUDA float32 (..., C) -> probabilities of the same shape [* class_scale]."""
+    dev = logits.device.index
+    Cn = int(logits.shape[-1])
+    out = empty(tuple(logits.shape), np.float32, dev)
+    check(lib.ssdx_softmax_scores(ptr(logits), int(logits.numel() // Cn), Cn, ptr(class_scale), ptr(out), dev,
+                                  stream_ptr(dev)))
+    return out
 
 
 def decode_nms(anchors: "Anchors", offsets, std, scores, max_per_class: int, max_total: int, iou_threshold: float,

@@ -117,6 +117,41 @@ class NonMaximumSuppression(_Layer):
             return res, _ssdx.from_device(valid, kind), _ssdx.from_device(aidx, kind)
         return res
 
+    def call_on_logits(self, boxes_corners_coordinates, labels_logits, return_aux: bool = False, class_scale=None):
+        """`self.call(boxes, softmax(logits))` as one operation (new entry point): the class head of the reference
+        ends in `tf.keras.layers.Softmax` (models.py:259, :694) whose only consumers at inference are SegmentationSuppression and this layer
+        (models.py:402-414).  When `max_number_of_boxes_per_class >= max_number_of_boxes_per_sample` and there are 4
+        classes, the probabilities are computed inside the score filter as the logits are read and never written to
+        memory; otherwise they are materialised in a workspace first.  Same result as `call` on
+        `softmax_probabilities(logits)`, bit for bit."""
+        boxes, kind = _ssdx.to_device(boxes_corners_coordinates, np.float32, None, "nms_boxes")
+        logits, _ = _ssdx.to_device(labels_logits, np.float32, boxes.device.index, "nms_logits")
+        if boxes.dim() != 3 or boxes.shape[2] != 4 or logits.dim() != 3 or logits.shape[:2] != boxes.shape[:2]:
+            raise ValueError("expected boxes (batch, boxes, 4) and logits (batch, boxes, classes)")
+        if class_scale is not None:
+            class_scale, _ = _ssdx.to_device(class_scale, np.float32, boxes.device.index, "nms_scale")
+            if tuple(class_scale.shape) != (int(logits.shape[2]),):
+                raise ValueError("class_scale must have one entry per class")
+        out, valid, aidx = _ssdx.nms_logits(boxes, logits, self.max_number_of_boxes_per_class,
+                                            self.max_number_of_boxes_per_sample, self.boxes_iou_threshold,
+                                            self.labels_probability_threshold, want_aux=return_aux,
+                                            class_scale=class_scale)
+        if self.suppress_background_boxes:
+            out = out[out[..., 0] > 0.0]
+        res = _ssdx.from_device(out, kind)
+        if return_aux:
+            return res, _ssdx.from_device(valid, kind), _ssdx.from_device(aidx, kind)
+        return res
+
+    @staticmethod
+    def softmax_probabilities(labels_logits, class_scale=None):
+        """The soft-max activation of the class head with the arithmetic `call_on_logits` uses (exp(x - max) / sum in
+        fp32), materialised: (batch, boxes, classes) -> same shape."""
+        logits, kind = _ssdx.to_device(labels_logits, np.float32, None, "softmax_logits")
+        if class_scale is not None:
+            class_scale, _ = _ssdx.to_device(class_scale, np.float32, logits.device.index, "softmax_scale")
+        return _ssdx.from_device(_ssdx.softmax_scores(logits, class_scale), kind)
+
     def call_on_offsets(self, decode_layer, boxes_centroids_offsets, labels_probabilities, return_aux: bool = False,
                         class_scale=None):
         """`self.call(decode_layer.call(offsets), probabilities)` as one operation (new entry point): the wiring of

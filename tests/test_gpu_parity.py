@@ -366,6 +366,33 @@ def test_nms_merged_runs_dry_and_refills(lib):
     assert (out[..., 1] > 0).sum(axis=1).max() <= 4 * 40 + 40  # ~ one survivor per (cluster, class)
 
 
+@pytest.mark.parametrize("C,mpc,mtot", [(4, 200, 200), (4, 400, 300), (4, 20, 50), (7, 100, 100)])
+def test_nms_on_logits_equals_softmax_then_nms(lib, golden, C, mpc, mtot):
+    """soft-max fused into the NMS score filter.  The soft-max arithmetic (hardware exponential) is
+    checked against the oracle's at the path's fp32 tolerance (1e-5 relative); the fused call must equal NMS on the materialised probabilities bit for bit
+    (4 classes + merged pipeline: probabilities only in registers; other shapes: materialised in the workspace), and
+    that NMS is itself checked against the oracle on the same probabilities."""
+    a = golden("anchors")["std_centroids"]
+    rng = np.random.default_rng(40 + C + mpc)
+    off, _ = orc.synth_predictions(rng, 3, 9600, 4)
+    yxyx = orc.decode_batched_yxyx(off, a, STD)
+    logits = rng.normal(0, 2.5, size=(3, 9600, C)).astype(np.float32)
+    logits[0, :500] = 0.0                                  # equal logits -> equal probabilities (ties by class, anchor)
+    logits[1, ::9] += 12.0                                 # saturated rows
+    layer = lib.layers.NonMaximumSuppression(mpc, mtot, 0.45, 0.05, False)
+    probs = layer.softmax_probabilities(logits)
+    np.testing.assert_allclose(probs, orc.softmax_f32(logits), rtol=RTOL, atol=1e-30)
+    assert np.abs(probs.sum(-1) - 1).max() < 1e-5
+    scale = np.array([1.0] + [0.0 if c == 2 else 1.0 for c in range(1, C)], np.float32)
+    for cs in (None, scale):
+        got = layer.call_on_logits(yxyx, logits, return_aux=True, class_scale=cs)
+        ref = layer.call(yxyx, probs, return_aux=True, class_scale=cs)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+    # and the chain to the oracle: NMS of those probabilities
+    nms_check(lib, yxyx, probs, mpc, mtot, 0.45, 0.05)
+
+
 def test_nms_two_phase_on_a_side_stream(lib, golden):
     """select (scores only, on a side stream) + finish == call, on the merged and on the per-class pipeline."""
     import torch

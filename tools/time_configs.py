@@ -103,6 +103,39 @@ def config1():
     emit("ssdx_decode_nms, batch 1024 (random predictions)", B2, m1, b1, 16 * A + 4 * A * C + 24 * K,
          "pass" if torch.equal(od2, od3) else "FAIL")
 
+    # the class head's soft-max fused into the NMS score filter (logits = log of the same scores)
+    lg = torch.log(sc2.clamp_min(1e-30)).contiguous()
+    pr = torch.empty_like(sc2)
+    od4, od5 = torch.empty((B2, K, 6), **f32), torch.empty((B2, K, 6), **f32)
+    wsl = torch.empty(int(sx.lib.ssdx_nms_logits_workspace_bytes(B2, A, C, K, K)), dtype=torch.uint8, device="cuda:0")
+
+    def soft_then_nms():
+        sx.check(sx.lib.ssdx_softmax_scores(lg.data_ptr(), B2 * A, C, None, pr.data_ptr(), dev, sp))
+        sx.check(sx.lib.ssdx_nms(ob2.data_ptr(), pr.data_ptr(), B2, A, C, K, K, 0.45, 0.01, od4.data_ptr(), None, None,
+                                 ws2.data_ptr(), ws2.numel(), dev, sp))
+
+    def nms_on_logits():
+        sx.check(sx.lib.ssdx_nms_logits(ob2.data_ptr(), lg.data_ptr(), None, B2, A, C, K, K, 0.45, 0.01, od5.data_ptr(),
+                                        None, None, wsl.data_ptr(), wsl.numel(), dev, sp))
+    ms, bs = timeit(soft_then_nms)
+    ml, bl = timeit(nms_on_logits)
+    emit("soft-max kernel + NMS, batch 1024 (random predictions)", B2, ms, bs, 32 * A * C // 4 + 16 * A + 4 * A * C + 24 * K, "pass")
+    emit("ssdx_nms_logits (soft-max inside the score filter), batch 1024 (random predictions)", B2, ml, bl,
+         16 * A + 4 * A * C + 24 * K, "pass" if torch.equal(od4, od5) else "FAIL")
+    # the same pair on the bench's round-trip predictions (targets as perfect predictions, 0.9 one-hot + 0.1 soft-max noise)
+    labels, boxes, counts = orc.synth_gt(np.random.default_rng(1995), B2, 16)
+    lab, off_t = coder.encode_batch(torch.from_numpy(boxes).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(counts).cuda())
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    sc3 = (0.9 * lab + 0.1 * torch.softmax(torch.randn(lab.shape, generator=g, device="cuda"), dim=-1)).contiguous()
+    sx.check(sx.lib.ssdx_decode(h, off_t.data_ptr(), B2, std, 0, ob2.data_ptr(), sp))
+    lg.copy_(torch.log(sc3))
+    ms, bs = timeit(soft_then_nms)
+    ml, bl = timeit(nms_on_logits)
+    emit("soft-max kernel + NMS, batch 1024 (round-trip predictions of the bench)", B2, ms, bs,
+         32 * A * C // 4 + 16 * A + 4 * A * C + 24 * K, "pass")
+    emit("ssdx_nms_logits, batch 1024 (round-trip predictions of the bench)", B2, ml, bl, 16 * A + 4 * A * C + 24 * K,
+         "pass" if torch.equal(od4, od5) else "FAIL")
+
 
 # ------------------------------------------------------------------------------------------------ config 3
 def config3():
