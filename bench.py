@@ -290,6 +290,14 @@ def gpu_arm(args, rank, world, local_rank):
     # of the other (encode match, NMS sort + suppression).  Same calls, same work, same outputs; P = 1 is one stream.
     n_pipe = max(1, min(args.pipeline, B))
     pipe_bounds = [(B * i // n_pipe, B * (i + 1) // n_pipe) for i in range(n_pipe)]
+    if args.pipeline_split:  # explicit sub-batch sizes (e.g. multiples of the SM count: one-CTA-per-image kernels then
+        sizes = [int(v) for v in args.pipeline_split.split(",")]   # leave no SM with an extra image)
+        assert sum(sizes) == B and all(v > 0 for v in sizes), "--pipeline-split must sum to the batch"
+        n_pipe = len(sizes)
+        edges = [0]
+        for v in sizes:
+            edges.append(edges[-1] + v)
+        pipe_bounds = list(zip(edges[:-1], edges[1:]))
     ws_enc_p = [ws_enc] + [torch.empty_like(ws_enc) for _ in range(n_pipe - 1)]
     ws_nms_p = [ws_nms] + [torch.empty_like(ws_nms) for _ in range(n_pipe - 1)]
     n_streams = max(1, min(args.pipeline_streams, n_pipe))
@@ -561,6 +569,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="single stream: ssdx_nms instead of select || encode/decode")
     ap.add_argument("--pipeline", type=int, default=2, help="sub-batches per step pipelined on two streams (1 = off)")
     ap.add_argument("--pipeline-streams", type=int, default=2)
+    ap.add_argument("--pipeline-split", default="", help="comma-separated sub-batch sizes instead of an even split")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks per step of the end-to-end leg (copy/compute overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -579,7 +588,8 @@ def main():
                args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
                    ["--no-graph"] if args.no_graph else []) + (["--no-overlap"] if args.no_overlap else []) + [
                    "--e2e-chunks", str(args.e2e_chunks), "--pipeline", str(args.pipeline),
-                   "--pipeline-streams", str(args.pipeline_streams)]
+                   "--pipeline-streams", str(args.pipeline_streams)] + (
+                   ["--pipeline-split", args.pipeline_split] if args.pipeline_split else [])
         raise SystemExit(subprocess.call(cmd))
     gpu_arm(args, rank, world, local_rank)
 
