@@ -59,6 +59,8 @@ constexpr int kTiledThreads = 256;  // grid (tile groups, images)
 constexpr int kTiledTilesPerCta = 16;
 constexpr int kGtTile = 256;        // GT boxes staged per shared-memory tile (tiled driver)
 constexpr int kEmitThreads = 256;
+constexpr int kEmitSpan = 8;  // chunks of kEmitThreads anchors per emit CTA
+constexpr int kEmitAnchors = kEmitSpan * kEmitThreads;
 constexpr int kFusedMaxG = 256;
 constexpr int kPosCap = 1024;   // compacted positives per image (more are encoded in place)
 constexpr int kBgRows = SSDX_ENC_BGROWS;  // background rows per bulk store (offsets: 16 B per row)
@@ -590,67 +592,85 @@ __global__ void __launch_bounds__(kEmitThreads)
                             const float sh, const u64* __restrict__ gt_best, const int* __restrict__ anchor_g2,
                             float* __restrict__ out_labels, float4* __restrict__ out_offsets,
                             int* __restrict__ out_match) {
-  __shared__ int s_s1max[kEmitThreads];
+  // one CTA per span of kEmitSpan * kEmitThreads consecutive anchors of one image: the scan over the image's GT boxes
+  // (step-1 winners that fall into the span) and the barriers are paid once per span
+  __shared__ int s_s1max[kEmitAnchors];
+  __shared__ int s_pos[kEmitAnchors];  // compacted positives of the span: (anchor - a_base) << 16 | matched GT
   __shared__ int s_lab[kEmitThreads];
+  __shared__ int s_npos;
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
-  const int a_base = blockIdx.x * kEmitThreads;
-  const int a = a_base + tid;
+  const int a_base = blockIdx.x * kEmitAnchors;
   int G = gt_count[b];
   G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
   const u64* best = gt_best + (size_t)b * Gmax;
 
-  s_s1max[tid] = -1;
+#pragma unroll
+  for (int k = 0; k < kEmitSpan; ++k) s_s1max[k * kEmitThreads + tid] = -1;
+  if (tid == 0) s_npos = 0;
   __syncthreads();
-  // S1: GT boxes whose best anchor (IoU > 0) lies in this tile
+  // S1: GT boxes whose best anchor (IoU > 0) lies in this span
   for (int g = tid; g < G; g += kEmitThreads) {
     const u64 p = best[g];
     if ((p >> 32) != 0ull) {
       const int ba = best_anchor(p);
-      if (ba >= a_base && ba < a_base + kEmitThreads) atomicMax(&s_s1max[ba - a_base], g);
+      if (ba >= a_base && ba < a_base + kEmitAnchors) atomicMax(&s_s1max[ba - a_base], g);
     }
   }
   __syncthreads();
 
-  int match = -1;
-  if (a < A) match = resolve_match(a, anchor_g2[(size_t)b * A + a], s_s1max[tid], best);
-  int lab = 0;  // background row = one_hot(0)
-  if (match >= 0) lab = __ldg(gt_label + (size_t)b * Gmax + match);
-  // offsets: background rows are written at once; the positives (log + six IEEE divisions each) are compacted and
-  // encoded densely by the first warps instead of diverging every warp of the CTA
-  __shared__ int s_pos[kEmitThreads];
-  __shared__ int s_npos;
-  if (tid == 0) s_npos = 0;
-  __syncthreads();
-  if (a < A) {
-    if (match >= 0) s_pos[atomicAdd(&s_npos, 1)] = (tid << 16) | match;  // match <= 32766
-    else st_stream_f4(out_offsets + (size_t)b * A + a, make_float4(0.f, 0.f, 0.f, 0.f));
-    if (out_match) out_match[(size_t)b * A + a] = match;
+  const size_t row0 = (size_t)b * A;
+  int g2[kEmitSpan];
+#pragma unroll
+  for (int k = 0; k < kEmitSpan; ++k) {  // kEmitSpan independent loads in flight
+    const int a = a_base + k * kEmitThreads + tid;
+    g2[k] = (a < A) ? __ldcs(anchor_g2 + row0 + a) : -1;
   }
-  __syncthreads();
-  if (tid < s_npos) {
-    const int pa = a_base + (s_pos[tid] >> 16), pm = s_pos[tid] & 0xFFFF;
-    st_stream_f4(out_offsets + (size_t)b * A + pa,
-                 pair_offsets(__ldg(gt_xyxy + (size_t)b * Gmax + pm), __ldg(anc_cent + pa), sx, sy, sw, sh));
-  }
-  const int n_here = min(kEmitThreads, A - a_base);
-  if (C == 4) {
+#pragma unroll
+  for (int k = 0; k < kEmitSpan; ++k) {
+    const int al = k * kEmitThreads + tid;
+    const int a = a_base + al;
+    int match = -1;
+    if (a < A) match = resolve_match(a, g2[k], s_s1max[al], best);
+    int lab = 0;  // background row = one_hot(0)
+    if (match >= 0) lab = __ldg(gt_label + (size_t)b * Gmax + match);
+    // offsets: background rows are written at once; the positives (log + six IEEE divisions each) are compacted and
+    // encoded densely afterwards instead of diverging every warp of the CTA
     if (a < A) {
-      const float4 oh = make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f,
-                                    lab == 3 ? 1.f : 0.f);
-      st_stream_f4(reinterpret_cast<float4*>(out_labels) + (size_t)b * A + a, oh);
+      if (match >= 0) s_pos[atomicAdd(&s_npos, 1)] = (al << 16) | match;  // al < 2^15, match <= 32766
+      else st_stream_f4(out_offsets + row0 + a, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (out_match) out_match[row0 + a] = match;
     }
-  } else {
-    // generic class count: flat coalesced walk over the tile's (n_here * C) floats
-    s_lab[tid] = lab;
-    __syncthreads();
-    float* dst = out_labels + ((size_t)b * A + a_base) * C;
-    const int total = n_here * C;
-    for (int e = tid; e < total; e += kEmitThreads) {
-      const int al = e / C;
-      const int c = e - al * C;
-      dst[e] = (s_lab[al] == c) ? 1.0f : 0.0f;
+    if (C == 4) {
+      if (a < A) {
+        const float4 oh = make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f,
+                                      lab == 3 ? 1.f : 0.f);
+        st_stream_f4(reinterpret_cast<float4*>(out_labels) + row0 + a, oh);
+      }
+    } else {
+      // generic class count: flat coalesced walk over the chunk's (n_here * C) floats
+      __syncthreads();
+      s_lab[tid] = lab;
+      __syncthreads();
+      const int c_base = a_base + k * kEmitThreads;
+      const int n_here = min(kEmitThreads, A - c_base);
+      if (n_here > 0) {
+        float* dst = out_labels + (row0 + c_base) * C;
+        const int total = n_here * C;
+        for (int e = tid; e < total; e += kEmitThreads) {
+          const int l = e / C;
+          const int c = e - l * C;
+          dst[e] = (s_lab[l] == c) ? 1.0f : 0.0f;
+        }
+      }
     }
+  }
+  __syncthreads();
+  const int npos = s_npos;
+  for (int i = tid; i < npos; i += kEmitThreads) {
+    const int pa = a_base + (s_pos[i] >> 16), pm = s_pos[i] & 0xFFFF;
+    st_stream_f4(out_offsets + row0 + pa,
+                 pair_offsets(__ldg(gt_xyxy + (size_t)b * Gmax + pm), __ldg(anc_cent + pa), sx, sy, sw, sh));
   }
 }
 
@@ -727,7 +747,7 @@ extern "C" int ssdx_encode(const ssdx_anchors* anchors, const float* gt_xyxy, co
                                                         (const float4*)gt_xyxy, gt_count, A, gm, iou_threshold,
                                                         gt_best, anchor_g2);
   SSDX_LAUNCH_CHECK("ssdx_encode_match_kernel");
-  dim3 g2((A + kEmitThreads - 1) / kEmitThreads, batch);
+  dim3 g2((A + kEmitAnchors - 1) / kEmitAnchors, batch);
   ssdx_encode_emit_kernel<<<g2, kEmitThreads, 0, s>>>(anchors->enc_cent, (const float4*)gt_xyxy, gt_label, gt_count,
                                                       A, gm, num_classes, std_host[0], std_host[1], std_host[2],
                                                       std_host[3], gt_best, anchor_g2, out_labels,
