@@ -204,7 +204,8 @@ def reference_arm(args, rank):
     value = sample / (ms / 1e3)
     line = {
         "impl": "reference", "metric": "images/sec encode+decode+NMS", "value": value, "unit": "images/s",
-        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "n_gpus": args.gpus, "gpus_used": 0,  # n_gpus = the N of the launch this line pairs with; the arm is CPU-only
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "stages": list(wl["stages"]), "anchors": A_STD, "gt_per_image": G_STD,
                    "classes": C_STD, "max_total": K_STD, "images_per_step": sample},
