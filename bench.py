@@ -221,6 +221,28 @@ def reference_arm(args, rank):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
+def bind_to_gpu_cores(torch, dev, allowed):
+    """sched_setaffinity to the CPU cores NVML reports as local to the GPU (PCIe root / NUMA node).  Returns a note
+    for the JSON line; any failure leaves the affinity untouched."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(dev)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & set(allowed)
+        if cpus and cpus != set(allowed):
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} of {len(allowed)} cores (GPU-local)"
+        return f"all {len(allowed)} cores (GPU reports no narrower affinity)"
+    except Exception as exc:  # no NVML, container cpuset, ...
+        return f"unchanged ({type(exc).__name__})"
+
+
 def gpu_arm(args, rank, world, local_rank):
     import torch
 
@@ -239,6 +261,11 @@ def gpu_arm(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.set_device(local_rank)
     dev = local_rank
+    # host side of the end-to-end leg: run this rank (and first-touch its pinned buffers) on the CPU cores next to its
+    # GPU, so that N ranks copying at PCIe rate do not all pull through one socket's memory controller / the
+    # inter-socket link.  The original affinity is restored for the CPU baseline, which uses every core.
+    cpu_all = os.sched_getaffinity(0)
+    numa_note = bind_to_gpu_cores(torch, dev, cpu_all) if not args.no_numa else "off"
     import ssdseglib
     from ssdseglib import _ssdx as sx
 
@@ -540,11 +567,13 @@ def gpu_arm(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "ssdseglib.datacoder.DataEncoderDecoder.encode_batch -> layers.DecodeBoxesCentroidsOffsets"
                            " -> layers.NonMaximumSuppression (inputs from pinned host memory, detections to pinned host"
-                           f" memory, {n_chunks} chunks per step on two streams)"},
+                           f" memory, {n_chunks} chunks per step on two streams)",
+                    "host_affinity": numa_note},
             "gpu_launches": kernels_per_step * (1 if args.no_overlap else n_pipe) * args.steps,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, cpu_all)
             threads = os.cpu_count() or 1
             sample = 1024
             v, secs, passes = run_cpu_sample(stages, sample, 1995, threads)
@@ -570,6 +599,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="single stream: ssdx_nms instead of select || encode/decode")
     ap.add_argument("--pipeline", type=int, default=2, help="sub-batches per step pipelined on two streams (1 = off)")
     ap.add_argument("--pipeline-streams", type=int, default=2)
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the CPU cores next to its GPU")
     ap.add_argument("--pipeline-split", default="", help="comma-separated sub-batch sizes instead of an even split")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks per step of the end-to-end leg (copy/compute overlap)")
     args = ap.parse_args()
@@ -590,7 +620,8 @@ def main():
                    ["--no-graph"] if args.no_graph else []) + (["--no-overlap"] if args.no_overlap else []) + [
                    "--e2e-chunks", str(args.e2e_chunks), "--pipeline", str(args.pipeline),
                    "--pipeline-streams", str(args.pipeline_streams)] + (
-                   ["--pipeline-split", args.pipeline_split] if args.pipeline_split else [])
+                   ["--pipeline-split", args.pipeline_split] if args.pipeline_split else []) + (
+                   ["--no-numa"] if args.no_numa else [])
         raise SystemExit(subprocess.call(cmd))
     gpu_arm(args, rank, world, local_rank)
 
