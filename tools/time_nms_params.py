@@ -16,8 +16,10 @@ onehot, off = coder.encode_batch(gb, gl, gc)
 scores = bench.make_scores_torch(onehot, 4242)
 yxyx = coder._decode(off, 0)
 sp = torch.cuda.current_stream().cuda_stream
-for mpc, mtot, iou, thr in ((200, 200, 0.45, 0.01), (4, 10, 0.025, 0.725), (100, 200, 0.45, 0.01), (20, 50, 0.3, 0.3),
-                            (50, 20, 0.3, 0.3), (100, 100, 0.45, 0.01)):
+SETTINGS = ((200, 200, 0.45, 0.01), (4, 10, 0.025, 0.725), (100, 200, 0.45, 0.01), (20, 50, 0.3, 0.3),
+            (50, 20, 0.3, 0.3), (100, 100, 0.45, 0.01))
+only = os.environ.get("NMS_SETTING")  # index into SETTINGS (profiling one setting under ncu)
+for mpc, mtot, iou, thr in (SETTINGS if only is None else (SETTINGS[int(only)],)):
     out = torch.empty((B, mtot, 6), device="cuda")
     ws = torch.empty(max(sx.lib.ssdx_nms_workspace_bytes(B, 9600, 4, mpc, mtot), 256), dtype=torch.uint8, device="cuda")
     fn = lambda: sx.check(sx.lib.ssdx_nms(yxyx.data_ptr(), scores.data_ptr(), B, 9600, 4, mpc, mtot, iou, thr, out.data_ptr(),
