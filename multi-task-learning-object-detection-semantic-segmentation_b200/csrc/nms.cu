@@ -655,6 +655,221 @@ __global__ void __launch_bounds__(kFastThreads, 6)
 }
 
 
+// ------------------------------------------------------------------------------------------ 2w. per-class, small caps
+// One WARP per (image, class) segment for per-class caps of at most 32 boxes (the reference's own inference setting is
+// 4 per class / 10 per image, 03-...ipynb): a CTA per segment spends its life in barriers and dependent loads for a
+// handful of boxes.  The warp holds up to kWarpSlots * 32 candidates in registers (composite, box, area) and runs the
+// classic form of the same greedy rule: take the best candidate still alive, keep it, kill every candidate whose IoU
+// with it exceeds the threshold - one round per KEPT box instead of one test per visited candidate.  When the list
+// runs dry it fetches the next band of the composite order (score key, anchor) from the scores, tests the newcomers
+// against the boxes kept so far and goes on; an over-full band is narrowed, down to a single candidate, so the kernel
+// never hands a segment over (thousands of equal scores included).
+constexpr int kWarpSlots = 8;
+constexpr int kWarpCap = kWarpSlots * 32;
+constexpr int kWarpSegs = kFastThreads / 32;  // segments per CTA
+constexpr int kWarpRefillTarget = 96;
+
+__global__ void __launch_bounds__(kFastThreads)
+    ssdx_nms_fast_warp_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
+                              const float* __restrict__ cscale, const u64* __restrict__ lists,
+                              const int* __restrict__ info, const int A, const int C, const int num_segments,
+                              const int limit, const float iou_thr, const float score_thr, u64* __restrict__ picks,
+                              int* __restrict__ pick_cnt) {
+  __shared__ u64 s_stage[kWarpSegs][kWarpCap];  // refill staging, one row per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const size_t seg = (size_t)blockIdx.x * kWarpSegs + warp;
+  if (seg >= (size_t)num_segments) return;  // warp-uniform
+  const int b = (int)(seg / C), c = (int)(seg - (size_t)b * C);
+  const size_t box_row0 = (size_t)b * A;
+  const float* cls_scores = scores + (size_t)b * A * C + c;
+  const float cf = class_factor(cscale, c);
+  u64* my_picks = picks + seg * limit;
+  u64* stage = s_stage[warp];
+
+  u64 comp[kWarpSlots];
+  float4 box[kWarpSlots];
+  float area[kWarpSlots];
+  unsigned alive = 0u;  // bit j: slot j holds a candidate that is neither kept nor suppressed
+  float4 kbox = make_float4(0.f, 0.f, 0.f, 0.f);  // lane k holds the k-th kept box
+  float karea = 0.0f;
+  int n_sel = 0;
+
+  auto load_boxes = [&](const int n) {  // slots of the current tier -> boxes; entry i sits in lane i % 32, slot i / 32
+#pragma unroll
+    for (int j = 0; j < kWarpSlots; ++j) {
+      const bool have = j * 32 + lane < n;
+      box[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      area[j] = 0.0f;
+      if (have) {
+        box[j] = normalise_box(ssdx_load_box(boxes, box_row0, comp_idx(comp[j])));
+        area[j] = box_area(box[j]);
+        alive |= 1u << j;
+      }
+    }
+  };
+  // kill the candidates that the kept box (kb, ka) suppresses
+  auto suppress_by = [&](const float4 kb, const float ka) {
+#pragma unroll
+    for (int j = 0; j < kWarpSlots; ++j)
+      if (((alive >> j) & 1u) && iou_exceeds(box[j], area[j], kb, ka, iou_thr)) alive &= ~(1u << j);
+  };
+
+  const int n_listed = info[seg * kInfo + 0];
+  const u64* lst = lists + seg * kCap;
+  // composites >= list_floor are in the list (when it was not truncated); below it only the scores know
+  const u64 list_floor = (u64)(unsigned)info[seg * kInfo + 2] << 32;
+  const bool list_ok = n_listed <= kCap;
+  u64 comp_hi;  // every candidate with composite >= comp_hi has been fetched
+  u64 span;
+#pragma unroll
+  for (int j = 0; j < kWarpSlots; ++j) comp[j] = 0ull;
+  if (n_listed <= kWarpCap) {  // the usual case: the whole listed tier fits the registers
+    u64 cmin = 0xFFFFFFFFFFFFFFFFull, cmax = 0ull;
+#pragma unroll
+    for (int j = 0; j < kWarpSlots; ++j)
+      if (j * 32 + lane < n_listed) {
+        comp[j] = __ldg(lst + j * 32 + lane);
+        cmin = comp[j] < cmin ? comp[j] : cmin;
+        cmax = comp[j] > cmax ? comp[j] : cmax;
+      }
+    load_boxes(n_listed);
+    // first refill band: the width that held kWarpRefillTarget candidates of this tier on average
+    const unsigned hmin = __reduce_min_sync(0xFFFFFFFFu, (unsigned)(cmin >> 32));
+    const unsigned hmax = __reduce_max_sync(0xFFFFFFFFu, (unsigned)(cmax >> 32));
+    const u64 w = (n_listed >= 2 && hmax > hmin) ? ((u64)(hmax - hmin) << 32) / (u64)n_listed * kWarpRefillTarget
+                                                 : (1024ull << 32);
+    span = w < (1ull << 32) ? (1ull << 32) : w;
+    comp_hi = list_floor;
+  } else if (list_ok) {  // a longer list (a sparse class is listed whole): served in bands, from the list itself
+    unsigned hmin = 0xFFFFFFFFu, hmax = 0u;
+    for (int i = lane; i < n_listed; i += 32) {
+      const unsigned k = (unsigned)(__ldg(lst + i) >> 32);
+      hmin = min(hmin, k);
+      hmax = max(hmax, k);
+    }
+    hmin = __reduce_min_sync(0xFFFFFFFFu, hmin);
+    hmax = __reduce_max_sync(0xFFFFFFFFu, hmax);
+    const u64 w = (hmax > hmin) ? ((u64)(hmax - hmin) << 32) / (u64)n_listed * kWarpRefillTarget : (1024ull << 32);
+    span = w < (1ull << 32) ? (1ull << 32) : w;
+    comp_hi = ((u64)hmax << 32) | 0xFFFFFFFFull;
+    comp_hi = comp_hi == 0xFFFFFFFFFFFFFFFFull ? comp_hi : comp_hi + 1ull;  // just above the best listed candidate
+  } else {  // truncated list (more than kCap candidates at or above the threshold key): bands from the scores
+    span = (0xFFFFFFFFFFFFFFFFull - list_floor) >> 3;
+    span = span < 1ull ? 1ull : span;
+    comp_hi = 0xFFFFFFFFFFFFFFFFull;
+  }
+
+  while (true) {
+    // ---- greedy rounds on the candidates in registers ----
+    while (n_sel < limit) {
+      u64 best = 0ull;
+#pragma unroll
+      for (int j = 0; j < kWarpSlots; ++j)
+        if (((alive >> j) & 1u) && comp[j] > best) best = comp[j];
+      if (__ballot_sync(0xFFFFFFFFu, best != 0ull) == 0u) break;  // nobody alive
+      const unsigned hi = __reduce_max_sync(0xFFFFFFFFu, (unsigned)(best >> 32));
+      const unsigned lo = __reduce_max_sync(0xFFFFFFFFu, (unsigned)(best >> 32) == hi ? (unsigned)best : 0u);
+      const u64 top = ((u64)hi << 32) | (u64)lo;  // composites are unique: exactly one lane owns it
+      const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, best == top)) - 1;
+      float4 tb = make_float4(0.f, 0.f, 0.f, 0.f);
+      float ta = 0.0f;
+#pragma unroll
+      for (int j = 0; j < kWarpSlots; ++j)
+        if (comp[j] == top && ((alive >> j) & 1u)) {
+          tb = box[j];
+          ta = area[j];
+          alive &= ~(1u << j);
+        }
+      tb.x = __shfl_sync(0xFFFFFFFFu, tb.x, owner);
+      tb.y = __shfl_sync(0xFFFFFFFFu, tb.y, owner);
+      tb.z = __shfl_sync(0xFFFFFFFFu, tb.z, owner);
+      tb.w = __shfl_sync(0xFFFFFFFFu, tb.w, owner);
+      ta = __shfl_sync(0xFFFFFFFFu, ta, owner);
+      if (lane == n_sel) {
+        kbox = tb;
+        karea = ta;
+        my_picks[n_sel] = top;
+      }
+      ++n_sel;
+      suppress_by(tb, ta);
+    }
+    if (n_sel >= limit || comp_hi <= (1ull << 32)) break;  // done, or every candidate has been visited
+    // ---- the tier ran dry: next band [comp_lo, comp_hi), from the list while it reaches that far down, else from
+    //      the scores of this class ----
+    int n_new = 0;
+    while (true) {
+      const bool from_list = list_ok && n_listed > kWarpCap && comp_hi > list_floor;
+      const u64 floor = from_list ? list_floor : (1ull << 32);
+      const u64 comp_lo = (comp_hi - floor > span) ? comp_hi - span : floor;
+      const unsigned key_lo = (unsigned)(comp_lo >> 32), key_hi32 = (unsigned)((comp_hi - 1ull) >> 32);
+      n_new = 0;
+      __syncwarp();
+      auto offer = [&](const bool in, const u64 cp) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, in);
+        if (in) {
+          const int pos = n_new + __popc(m & lt);
+          if (pos < kWarpCap) stage[pos] = cp;
+        }
+        n_new += __popc(m);
+      };
+      if (from_list) {
+        for (int i0 = 0; i0 < n_listed && n_new <= kWarpCap; i0 += 32) {
+          const u64 cp = (i0 + lane < n_listed) ? __ldg(lst + i0 + lane) : 0ull;
+          offer(cp >= comp_lo && cp < comp_hi, cp);
+        }
+      } else {
+        for (int a0 = 0; a0 < A && n_new <= kWarpCap; a0 += 32 * 16) {  // 16 independent loads in flight per lane
+          float sv[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int a = a0 + u * 32 + lane;
+            sv[u] = (a < A) ? __fmul_rn(__ldg(cls_scores + (size_t)a * C), cf) : -INFINITY;
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            bool in = false;
+            u64 cp = 0ull;
+            if (sv[u] > score_thr && a0 + u * 32 + lane < A) {
+              const unsigned key = score_to_key(sv[u]);
+              if (key >= key_lo && key <= key_hi32) {
+                cp = make_comp(key, a0 + u * 32 + lane);
+                in = cp >= comp_lo && cp < comp_hi;
+              }
+            }
+            offer(in, cp);
+          }
+        }
+      }
+      if (n_new > kWarpCap) {  // over-full: narrow the band and rescan
+        span = (span >> 2) > 1ull ? (span >> 2) : 1ull;
+        continue;
+      }
+      comp_hi = comp_lo;
+      if (n_new < kWarpRefillTarget / 8) span = (span > 0x1FFFFFFFFFFFFFFFull) ? 0x7FFFFFFFFFFFFFFFull : span << 2;
+      else if (n_new < kWarpRefillTarget / 2) span = (span > 0x3FFFFFFFFFFFFFFFull) ? 0x7FFFFFFFFFFFFFFFull : span << 1;
+      else if (n_new > kWarpRefillTarget * 2) span = (span >> 1) > 1ull ? (span >> 1) : 1ull;
+      if (n_new > 0 || comp_lo <= (1ull << 32)) break;
+    }
+    __syncwarp();
+    alive = 0u;
+#pragma unroll
+    for (int j = 0; j < kWarpSlots; ++j) comp[j] = (j * 32 + lane < n_new) ? stage[j * 32 + lane] : 0ull;
+    load_boxes(n_new);
+    // the newcomers against the boxes kept so far
+    for (int k = 0; k < n_sel; ++k) {
+      float4 kb;
+      kb.x = __shfl_sync(0xFFFFFFFFu, kbox.x, k);
+      kb.y = __shfl_sync(0xFFFFFFFFu, kbox.y, k);
+      kb.z = __shfl_sync(0xFFFFFFFFu, kbox.z, k);
+      kb.w = __shfl_sync(0xFFFFFFFFu, kbox.w, k);
+      const float ka = __shfl_sync(0xFFFFFFFFu, karea, k);
+      suppress_by(kb, ka);
+    }
+  }
+  if (lane == 0) pick_cnt[seg] = n_sel;
+}
+
 // ------------------------------------------------------------------------------------------ 1m. merged select
 // info per image: [0] listed candidates (may exceed kCap), [1] threshold key (every candidate with key >= it is listed)
 template <bool VEC4, bool LOGITS>
@@ -1537,6 +1752,19 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
     SSDX_LAUNCH_CHECK("ssdx_nms_select_kernel");
   }
   if (!ph2) return SSDX_OK;
+  const char* force_path = getenv("SSDX_NMS_PATH");
+  const bool no_warp = force_path != nullptr && force_path[0] == 'p' && force_path[1] == 'c';  // "pcta": test hook
+  if (use_fast && limit <= 32 && !no_warp) {
+    // 2w. one warp per segment, never hands over: select -> warp -> merge
+    ssdx_nms_fast_warp_kernel<<<(num_segments + kWarpSegs - 1) / kWarpSegs, kFastThreads, 0, s>>>(
+        bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt);
+    SSDX_LAUNCH_CHECK("ssdx_nms_fast_warp_kernel");
+    ssdx_nms_merge_kernel<<<batch, kMergeThreads, stage ? merge_smem : 0, s>>>(bx, picks, pick_cnt, A, C, limit,
+                                                                               max_total, stage, out, out_valid,
+                                                                               out_anchor_idx);
+    SSDX_LAUNCH_CHECK("ssdx_nms_merge_kernel");
+    return SSDX_OK;
+  }
   if (use_fast) {
     // 2. fast path
     dim3 gseg(C, batch);

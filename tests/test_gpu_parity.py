@@ -31,11 +31,12 @@ def encode_path(request, monkeypatch):
     return request.param
 
 
-@pytest.fixture(autouse=True, params=["fast", "perclass", "generic"])
+@pytest.fixture(autouse=True, params=["fast", "perclass", "pcta", "generic"])
 def nms_path(request, monkeypatch):
     """NMS tests run on the default dispatch (merged one-pass-per-image pipeline when max_per_class >= max_total,
-    else the per-class fast pipeline; generic only for handed-over work), with the per-class fast pipeline forced,
-    and with the exact generic kernel alone."""
+    else the per-class pipeline: one warp per segment for caps up to 32, one CTA per segment above; generic only for
+    handed-over work), with the per-class pipeline forced ("perclass"), with the per-class CTA kernel forced for every
+    cap ("pcta"), and with the exact generic kernel alone."""
     if request.param != "fast":
         if "nms" not in request.node.name:
             pytest.skip("NMS driver does not matter for this test")
@@ -318,6 +319,29 @@ def test_nms_massive_score_ties_merged_pipeline(lib, layout):
     nms_check(lib, yxyx, scores, 200, 200, 0.45, 0.01)
     if layout == "stacked":
         assert ((out[..., 1] > 0).sum(axis=1) == C).all()  # one survivor per class
+
+
+@pytest.mark.parametrize("mpc,mtot,iou,thr", [(4, 10, 0.025, 0.725), (1, 3, 0.0, 0.5), (32, 100, 0.2, 0.05),
+                                              (8, 40, 0.6, 0.0), (20, 50, 0.3, 0.3)])
+def test_nms_small_per_class_caps(lib, golden, mpc, mtot, iou, thr):
+    """Per-class caps up to 32 (one warp per (image, class); the reference's own setting is 4 / 10 / 0.025 / ~0.7) on
+    the bench's round-trip predictions (every anchor is a candidate of some class above 0.7: the listed tier runs dry
+    and band refills follow), on clustered boxes and on thousands of equal scores."""
+    a = golden("anchors")["std_centroids"]
+    rng = np.random.default_rng(mpc * 7 + mtot)
+    off, scores = orc.synth_predictions(rng, 3, 9600, 4)
+    yxyx = orc.decode_batched_yxyx(off, a, STD)
+    nms_check(lib, yxyx, scores, mpc, mtot, iou, thr)
+    # near one-hot scores: ~9500 candidates of class 0 above 0.7
+    onehot = np.zeros((2, 9600, 4), np.float32)
+    onehot[..., 0] = 1
+    onehot[:, ::53] = np.array([0, 0, 1, 0], np.float32)
+    s2 = orc.dedup_scores((0.9 * onehot + 0.1 * orc.softmax_f32(rng.normal(0, 1, onehot.shape).astype(np.float32))))
+    nms_check(lib, yxyx[:2], s2, mpc, mtot, iou, thr)
+    # thousands of exactly equal scores, identical and disjoint boxes
+    s3 = np.full((2, 9600, 4), 0.8, np.float32)
+    s3[:, ::3, 1] = 0.9
+    nms_check(lib, yxyx[:2], s3, mpc, mtot, iou, thr)
 
 
 def test_nms_degenerate_boxes_and_small_sets(lib):
