@@ -146,6 +146,20 @@ def test_encode_odd_anchor_counts(lib, std_anchors, A, C):
     assert_coords_close(c.decode_to_corners(O[3]), orc.decode_to_corners(Or[3], cent, STD), cent[:, 2:])
 
 
+def test_encode_randomized_differential(lib, encode_path):
+    """150 random cases (anchor subsets, integer grids with exact ties, random anchors; ragged / empty GT, duplicated GT
+    boxes, GT equal to an anchor, thresholds, class counts, labels out of range) against the C oracle on the encode
+    driver the fixture forces (tools/fuzz_encode.py)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_encode", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_encode.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(150, 21 if encode_path == "fused" else 22, verbose=False) == 0
+
+
 def test_encode_stress_shape_small_batch(lib):
     """BASELINE config 3 shape (A = 100k, G = 256) at batch 2 against the oracle."""
     anchors = orc.anchors_generate(**orc.STRESS_ANCHOR_CFG)
@@ -415,6 +429,20 @@ def test_nms_on_logits_equals_softmax_then_nms(lib, golden, C, mpc, mtot):
             assert np.array_equal(g, r)
     # and the chain to the oracle: NMS of those probabilities
     nms_check(lib, yxyx, probs, mpc, mtot, 0.45, 0.05)
+
+
+def test_nms_randomized_differential(lib, nms_path):
+    """250 random (shape, class count, caps, thresholds, score distribution, box layout) cases against the C oracle
+    on whichever NMS path the fixture forces (tools/fuzz_nms.py; 6,600 cases were run when the kernels were written)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_nms", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_nms.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    seed = {"fast": 11, "perclass": 12, "pcta": 13, "generic": 14}[nms_path]
+    assert mod.run(250 if nms_path == "fast" else 120, seed, verbose=False) == 0
 
 
 def test_nms_two_phase_on_a_side_stream(lib, golden):

@@ -1,0 +1,63 @@
+"""GPU box: randomized differential test of the encode drivers (one CTA per image / anchor-tiled) against the C oracle:
+random anchor subsets and synthetic grids, GT counts (incl. 0 and ragged), integer coordinates (exact IoU ties),
+duplicated GT boxes, GT boxes equal to anchors, thresholds, class counts, out-of-range labels.
+usage: python tools/fuzz_encode.py [cases] [seed]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multi-task-learning-object-detection-semantic-segmentation_b200"))
+import numpy as np
+import ssdseglib
+from oracle import c_oracle
+from oracle import ssd_oracle as orc
+
+STD = (0.1, 0.1, 0.2, 0.2)
+
+
+def run(cases: int, seed: int, verbose: bool = True) -> int:
+    c_oracle.build()
+    rng = np.random.default_rng(seed)
+    std_anchors = orc.anchors_generate(**orc.STD_ANCHOR_CFG)
+    bad = 0
+    for it in range(cases):
+        kind = rng.choice(["subset", "grid", "random"])
+        if kind == "subset":
+            A = int(rng.choice([1, 31, 64, 65, 700, 4097, 9600]))
+            anchors = std_anchors[rng.permutation(9600)[:A]]
+        elif kind == "grid":  # integer grid of equal boxes: exact ties everywhere
+            n = int(rng.integers(2, 24)); sz = float(rng.integers(8, 60)); step = float(rng.integers(4, 40))
+            xs, ys = np.meshgrid(np.arange(n) * step, np.arange(n) * step)
+            anchors = np.stack([xs.ravel(), ys.ravel(), xs.ravel() + sz - 1, ys.ravel() + sz - 1], 1).astype(np.float32)
+        else:
+            A = int(rng.integers(1, 3000))
+            c = rng.uniform(0, 640, size=(A, 2)); wh = rng.uniform(4, 300, size=(A, 2))
+            anchors = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        A = anchors.shape[0]
+        B = int(rng.integers(1, 6)); G = int(rng.choice([1, 2, 7, 16, 33, 64])); C = int(rng.choice([1, 2, 4, 4, 7]))
+        thr = float(rng.choice([0.0, 0.3, 0.5, 0.525, 0.9]))
+        labels, boxes, counts = orc.synth_gt(rng, B, G, n_fg=max(C - 1, 1), integer=bool(rng.integers(0, 2)),
+                                             wh_range=(float(rng.choice([4.0, 20.0])), float(rng.choice([60.0, 300.0]))))
+        counts = rng.integers(0, G + 1, size=B).astype(np.int32)
+        if G >= 3:
+            boxes[:, 2] = boxes[:, 0]                                  # duplicated GT box
+        if rng.integers(0, 2):
+            k = rng.integers(0, A, size=B)
+            boxes[np.arange(B), G - 1] = anchors[k]                    # a GT box equal to an anchor: IoU 1
+        if rng.integers(0, 4) == 0:
+            labels[:, 0] = C + 3                                       # label outside [0, C): all-zero label row
+        coder = ssdseglib.datacoder.DataEncoderDecoder(C, (480, 640), anchors[:, 0], anchors[:, 1], anchors[:, 2],
+                                                       anchors[:, 3], iou_threshold=thr)
+        L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
+        Lr, Or, Mr = c_oracle.encode_batch(anchors, labels, boxes, counts, C, thr, STD)
+        ok = (np.array_equal(M, Mr) and np.array_equal(L, Lr) and np.allclose(O, Or, rtol=1e-5, atol=1e-6)
+              and np.array_equal(O != 0, Or != 0))
+        if not ok:
+            bad += 1
+            print(f"MISMATCH case {it}: anchors={kind} A={A} B={B} G={G} C={C} thr={thr} counts={counts.tolist()} "
+                  f"match diffs={int((M != Mr).sum())}", flush=True)
+    if verbose:
+        print(f"fuzz_encode: {cases} cases, {bad} mismatches")
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 200, int(sys.argv[2]) if len(sys.argv) > 2 else 0) else 0)
