@@ -680,6 +680,20 @@ def test_confidence_loss_threshold_ties_are_split_in_index_order(lib):
     np.testing.assert_allclose(got, orc.confidence_loss(y_true, y_pred), rtol=RTOL)
 
 
+def test_losses_randomized_differential(lib):
+    """120 random cases (shapes, class counts, positive fractions 0..1, soft-max / saturated / constant / quantised
+    predictions: massive ties at the hard-negative threshold) of both losses, their gradients and the kept-background
+    mask against the NumPy oracle (tools/fuzz_losses.py)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_losses", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_losses.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(120, 31, verbose=False) == 0
+
+
 def test_losses_on_device_tensors(lib, golden):
     import torch
 
