@@ -655,6 +655,57 @@ __global__ void __launch_bounds__(kFastThreads, 6)
 }
 
 
+// number of entries of a descending list whose score key is > k (strict) or >= k
+__device__ __forceinline__ int count_before(const u64* lst, int n, unsigned k, bool inclusive) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const unsigned km = (unsigned)(lst[mid] >> 32);
+    const bool before = inclusive ? (km >= k) : (km > k);
+    if (before) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Rows of one image from its per-class pick lists (descending; list c at img_picks + c * stride, cnt[c] entries): the
+// rank of an entry = entries before it in its own list + entries of the other classes with a higher score (equal
+// scores: the lower class first).  Executed by `nthreads` threads (a CTA, or one warp of the small-caps kernel).
+__device__ __forceinline__ void merge_image_rows(const ssdx_box_src boxes, const u64* img_picks, const int* cnt,
+                                                 const int stride, const int b, const int A, const int C,
+                                                 const int limit, const int K, float* __restrict__ out,
+                                                 int* __restrict__ out_valid, int* __restrict__ out_idx, const int tid,
+                                                 const int nthreads) {
+  int total = 0;
+  for (int c = 0; c < C; ++c) total += cnt[c];
+  const int valid = min(total, K);
+  float* o = out + (size_t)b * K * 6;
+  for (int e = tid; e < C * limit; e += nthreads) {
+    const int c = e / limit, j = e - c * limit;
+    if (j >= cnt[c]) continue;
+    const u64 cp = img_picks[(size_t)c * stride + j];
+    const unsigned k = (unsigned)(cp >> 32);
+    int rank = j;
+    for (int c2 = 0; c2 < C && rank < K; ++c2)
+      if (c2 != c) rank += count_before(img_picks + (size_t)c2 * stride, cnt[c2], k, c2 < c);
+    if (rank < K) {
+      const int idx = comp_idx(cp);
+      const float4 bx = ssdx_load_box(boxes, (size_t)b * A, idx);  // raw (ymin, xmin, ymax, xmax)
+      float* r = o + (size_t)rank * 6;
+      r[0] = (float)c;
+      r[1] = key_to_score(k);
+      r[2] = bx.y;  // gather [1,0,3,2], layers.py:155
+      r[3] = bx.x;
+      r[4] = bx.w;
+      r[5] = bx.z;
+      if (out_idx) out_idx[(size_t)b * K + rank] = idx;
+    }
+  }
+  for (int e = valid * 6 + tid; e < K * 6; e += nthreads) o[e] = 0.0f;
+  if (out_idx)
+    for (int e = valid + tid; e < K; e += nthreads) out_idx[(size_t)b * K + e] = -1;
+  if (out_valid && tid == 0) out_valid[b] = valid;
+}
+
 // ------------------------------------------------------------------------------------------ 2w. per-class, small caps
 // One WARP per (image, class) segment for per-class caps of at most 32 boxes (the reference's own inference setting is
 // 4 per class / 10 per image, 03-...ipynb): a CTA per segment spends its life in barriers and dependent loads for a
@@ -674,12 +725,18 @@ __global__ void __launch_bounds__(kFastThreads)
                               const float* __restrict__ cscale, const u64* __restrict__ lists,
                               const int* __restrict__ info, const int A, const int C, const int num_segments,
                               const int limit, const float iou_thr, const float score_thr, u64* __restrict__ picks,
-                              int* __restrict__ pick_cnt) {
+                              int* __restrict__ pick_cnt, const int fuse_merge, const int K, float* __restrict__ out,
+                              int* __restrict__ out_valid, int* __restrict__ out_idx) {
+  // fuse_merge (the class count divides the segments of a CTA: every image lies inside one CTA): the picks stay in
+  // shared memory and one warp per image writes the image's rows at the end - no pick lists in memory, no merge launch
   __shared__ u64 s_stage[kWarpSegs][kWarpCap];  // refill staging, one row per warp
+  __shared__ u64 s_picks[kWarpSegs][32];
+  __shared__ int s_cnt[kWarpSegs];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const size_t seg = (size_t)blockIdx.x * kWarpSegs + warp;
-  if (seg >= (size_t)num_segments) return;  // warp-uniform
+  int n_sel = 0;
+  if (seg < (size_t)num_segments) {  // warp-uniform
   const int b = (int)(seg / C), c = (int)(seg - (size_t)b * C);
   const size_t box_row0 = (size_t)b * A;
   const float* cls_scores = scores + (size_t)b * A * C + c;
@@ -693,7 +750,6 @@ __global__ void __launch_bounds__(kFastThreads)
   unsigned alive = 0u;  // bit j: slot j holds a candidate that is neither kept nor suppressed
   float4 kbox = make_float4(0.f, 0.f, 0.f, 0.f);  // lane k holds the k-th kept box
   float karea = 0.0f;
-  int n_sel = 0;
 
   auto load_boxes = [&](const int n) {  // slots of the current tier -> boxes; entry i sits in lane i % 32, slot i / 32
 #pragma unroll
@@ -789,7 +845,8 @@ __global__ void __launch_bounds__(kFastThreads)
       if (lane == n_sel) {
         kbox = tb;
         karea = ta;
-        my_picks[n_sel] = top;
+        if (fuse_merge) s_picks[warp][n_sel] = top;
+        else my_picks[n_sel] = top;
       }
       ++n_sel;
       suppress_by(tb, ta);
@@ -867,7 +924,16 @@ __global__ void __launch_bounds__(kFastThreads)
       suppress_by(kb, ka);
     }
   }
-  if (lane == 0) pick_cnt[seg] = n_sel;
+  if (lane == 0 && !fuse_merge) pick_cnt[seg] = n_sel;
+  }  // segment
+  if (!fuse_merge) return;
+  if (lane == 0) s_cnt[warp] = n_sel;  // 0 for the warps beyond the last segment
+  __syncthreads();
+  const int imgs = kWarpSegs / C;  // images of this CTA: warp w writes the rows of image w
+  const int b_img = blockIdx.x * imgs + warp;
+  if (warp < imgs && (size_t)b_img * C < (size_t)num_segments)
+    merge_image_rows(boxes, &s_picks[warp * C][0], &s_cnt[warp * C], 32, b_img, A, C, limit, K, out, out_valid, out_idx,
+                     lane, 32);
 }
 
 // ------------------------------------------------------------------------------------------ 1m. merged select
@@ -1521,18 +1587,6 @@ __global__ void __launch_bounds__(kGenThreads)
 }
 
 // ------------------------------------------------------------------------------------------ 4. merge
-// number of entries of a descending list whose score key is > k (strict) or >= k
-__device__ __forceinline__ int count_before(const u64* lst, int n, unsigned k, bool inclusive) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    const unsigned km = (unsigned)(lst[mid] >> 32);
-    const bool before = inclusive ? (km >= k) : (km > k);
-    if (before) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
 __global__ void __launch_bounds__(kMergeThreads)
     ssdx_nms_merge_kernel(const ssdx_box_src boxes, const u64* __restrict__ picks,
                           const int* __restrict__ pick_cnt, const int A, const int C, const int limit, const int K,
@@ -1552,35 +1606,7 @@ __global__ void __launch_bounds__(kMergeThreads)
     __syncthreads();
     img_picks = s;
   }
-  int total = 0;
-  for (int c = 0; c < C; ++c) total += cnt[c];
-  const int valid = min(total, K);
-  float* o = out + (size_t)b * K * 6;
-  for (int e = tid; e < C * limit; e += kMergeThreads) {
-    const int c = e / limit, j = e - c * limit;
-    if (j >= cnt[c]) continue;
-    const u64 cp = img_picks[(size_t)c * limit + j];
-    const unsigned k = (unsigned)(cp >> 32);
-    int rank = j;
-    for (int c2 = 0; c2 < C && rank < K; ++c2)
-      if (c2 != c) rank += count_before(img_picks + (size_t)c2 * limit, cnt[c2], k, c2 < c);
-    if (rank < K) {
-      const int idx = comp_idx(cp);
-      const float4 bx = ssdx_load_box(boxes, (size_t)b * A, idx);  // raw (ymin, xmin, ymax, xmax)
-      float* r = o + (size_t)rank * 6;
-      r[0] = (float)c;
-      r[1] = key_to_score(k);
-      r[2] = bx.y;  // gather [1,0,3,2], layers.py:155
-      r[3] = bx.x;
-      r[4] = bx.w;
-      r[5] = bx.z;
-      if (out_idx) out_idx[(size_t)b * K + rank] = idx;
-    }
-  }
-  for (int e = valid * 6 + tid; e < K * 6; e += kMergeThreads) o[e] = 0.0f;
-  if (out_idx)
-    for (int e = valid + tid; e < K; e += kMergeThreads) out_idx[(size_t)b * K + e] = -1;
-  if (out_valid && tid == 0) out_valid[b] = valid;
+  merge_image_rows(boxes, img_picks, cnt, limit, b, A, C, limit, K, out, out_valid, out_idx, tid, kMergeThreads);
 }
 
 inline int nms_limit(int max_per_class, int A) { return max_per_class < A ? max_per_class : A; }
@@ -1756,9 +1782,12 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   const bool no_warp = force_path != nullptr && force_path[0] == 'p' && force_path[1] == 'c';  // "pcta": test hook
   if (use_fast && limit <= 32 && !no_warp) {
     // 2w. one warp per segment, never hands over: select -> warp -> merge
+    const int fuse_merge = (kWarpSegs % C) == 0;  // C = 1, 2, 4, 8: the rows are written by the same kernel
     ssdx_nms_fast_warp_kernel<<<(num_segments + kWarpSegs - 1) / kWarpSegs, kFastThreads, 0, s>>>(
-        bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt);
+        bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt,
+        fuse_merge, max_total, out, out_valid, out_anchor_idx);
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_warp_kernel");
+    if (fuse_merge) return SSDX_OK;
     ssdx_nms_merge_kernel<<<batch, kMergeThreads, stage ? merge_smem : 0, s>>>(bx, picks, pick_cnt, A, C, limit,
                                                                                max_total, stage, out, out_valid,
                                                                                out_anchor_idx);
