@@ -193,6 +193,16 @@ SSDX_API int ssdx_nms_logits(const float* boxes_yxyx, const float* logits, const
                              int32_t* out_anchor_idx, void* workspace, size_t workspace_bytes, int device,
                              ssdx_stream stream);
 
+/* The whole inference tail of get_model_for_inference (models.py:402-414) in one call: == ssdx_decode(mode YXYX) +
+ * ssdx_softmax_scores + ssdx_nms_scaled, bit for bit, with the boxes decoded per candidate and the probabilities
+ * computed inside the score filter (4 classes, max_per_class >= max_total; otherwise the probabilities are materialised
+ * in the workspace).  Workspace: ssdx_nms_logits_workspace_bytes. */
+SSDX_API int ssdx_decode_nms_logits(const ssdx_anchors* anchors, const float* offsets, const float* std_host,
+                                    const float* logits, const float* class_scale, int32_t batch, int32_t num_classes,
+                                    int32_t max_per_class, int32_t max_total, float iou_threshold, float score_threshold,
+                                    float* out, int32_t* out_valid, int32_t* out_anchor_idx, void* workspace,
+                                    size_t workspace_bytes, ssdx_stream stream);
+
 /* ---- training-time box metric: metrics.py:53-173 (jaccard_iou_bounding_boxes), SURVEY 8(f) row 3 ----
  * y_true, y_pred (B,A,4) f32 standardised centroid offsets (y_true = encode output, background rows all zero);
  * out (B) f32 = mean over the non-background anchors of IoU(decoded prediction, decoded target) with the reference's

@@ -1895,3 +1895,39 @@ extern "C" int ssdx_nms_logits(const float* boxes_yxyx, const float* logits, con
                  max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, base, device,
                  stream);
 }
+
+// ---- the whole inference tail in one call: offsets + logits (+ class scale) -> detections.  Boxes are decoded per
+//      candidate (ssdx_decode_nms), probabilities are computed inside the score filter (ssdx_nms_logits): neither the
+//      (B,A,4) box tensor nor the (B,A,C) probability tensor is written.  Same workspace as ssdx_nms_logits. ----
+extern "C" int ssdx_decode_nms_logits(const ssdx_anchors* anchors, const float* offsets, const float* std_host,
+                                      const float* logits, const float* class_scale, int32_t batch, int32_t num_classes,
+                                      int32_t max_per_class, int32_t max_total, float iou_threshold,
+                                      float score_threshold, float* out, int32_t* out_valid, int32_t* out_anchor_idx,
+                                      void* workspace, size_t workspace_bytes, ssdx_stream stream) {
+  SSDX_CHECK_ARG(anchors != nullptr && offsets != nullptr && std_host != nullptr && logits != nullptr,
+                 "ssdx_decode_nms_logits: NULL pointer argument");
+  SSDX_CHECK_ARG(((uintptr_t)offsets & 15) == 0, "ssdx_decode_nms_logits: offsets must be 16-byte aligned");
+  SSDX_CHECK_ARG(batch >= 0 && num_classes > 0 && max_per_class > 0 && max_total > 0,
+                 "ssdx_decode_nms_logits: bad shape or caps");
+  const int A = anchors->A;
+  const size_t need = ssdx_nms_logits_workspace_bytes(batch, A, num_classes, max_per_class, max_total);
+  if (workspace == nullptr || workspace_bytes < need) {
+    ssdx_set_error("ssdx_decode_nms_logits: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return SSDX_ERR_WORKSPACE;
+  }
+  const ssdx_box_src src{nullptr, (const float4*)offsets, anchors->dec_cent, std_host[0], std_host[1], std_host[2],
+                         std_host[3]};
+  const bool fused = num_classes == 4 && (((uintptr_t)logits & 15) == 0) &&
+                     nms_merged_applies(A, num_classes, max_per_class, max_total);
+  if (fused)
+    return nms_run(3, 1, &src, nullptr, logits, class_scale, batch, A, num_classes, max_per_class, max_total,
+                   iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes,
+                   anchors->device, stream);
+  const size_t base = ssdx_align_up(ssdx_nms_workspace_bytes(batch, A, num_classes, max_per_class, max_total), 256);
+  float* probs = (float*)((char*)workspace + base);
+  const int rc = ssdx_softmax_scores(logits, (int64_t)batch * A, num_classes, nullptr, probs, anchors->device, stream);
+  if (rc != SSDX_OK) return rc;
+  return nms_run(3, 0, &src, nullptr, probs, class_scale, batch, A, num_classes, max_per_class, max_total,
+                 iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, base, anchors->device,
+                 stream);
+}

@@ -65,6 +65,8 @@ SIGNATURES = {
     "ssdx_nms_logits_workspace_bytes": (C.c_size_t, [C.c_int32] * 5),
     "ssdx_nms_logits": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                   C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "ssdx_decode_nms_logits": (C.c_int, [_vp, _vp, c_float_p, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ssdx_localization_loss": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int, _vp]),
     "ssdx_confidence_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "ssdx_confidence_loss": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp,
@@ -305,6 +307,20 @@ def nms_logits(boxes_yxyx, logits, max_per_class: int, max_total: int, iou_thres
     check(lib.ssdx_nms_logits(ptr(boxes_yxyx), ptr(logits), ptr(class_scale), B, A, Cn, int(max_per_class),
                               int(max_total), float(iou_threshold), float(score_threshold), ptr(out), ptr(valid),
                               ptr(aidx), ptr(ws), ws.numel(), dev, stream_ptr(dev)))
+    return out, valid, aidx
+
+
+def decode_nms_logits(anchors: "Anchors", offsets, std, logits, max_per_class: int, max_total: int,
+                      iou_threshold: float, score_threshold: float, want_aux: bool = False, class_scale=None):
+    B, A, Cn = (int(v) for v in logits.shape)
+    dev = anchors.device
+    out = empty((B, max_total, 6), np.float32, dev)
+    valid = empty((B,), np.int32, dev) if want_aux else None
+    aidx = empty((B, max_total), np.int32, dev) if want_aux else None
+    ws = workspace(lib.ssdx_nms_logits_workspace_bytes(B, A, Cn, max_per_class, max_total), dev)
+    check(lib.ssdx_decode_nms_logits(anchors.handle, ptr(offsets), std_array(std), ptr(logits), ptr(class_scale), B, Cn,
+                                     int(max_per_class), int(max_total), float(iou_threshold), float(score_threshold),
+                                     ptr(out), ptr(valid), ptr(aidx), ptr(ws), ws.numel(), stream_ptr(dev)))
     return out, valid, aidx
 
 

@@ -152,6 +152,31 @@ class NonMaximumSuppression(_Layer):
             class_scale, _ = _ssdx.to_device(class_scale, np.float32, logits.device.index, "softmax_scale")
         return _ssdx.from_device(_ssdx.softmax_scores(logits, class_scale), kind)
 
+    def call_on_offsets_and_logits(self, decode_layer, boxes_centroids_offsets, labels_logits, return_aux: bool = False,
+                                   class_scale=None):
+        """The whole inference tail as one operation (new entry point): `call_on_offsets` with the class head's raw
+        logits instead of probabilities, i.e. `self.call(decode_layer.call(offsets), softmax(logits))` without writing
+        the decoded boxes or the probabilities.  Same result as that chain with `softmax_probabilities`, bit for bit."""
+        off, kind = _ssdx.to_device(boxes_centroids_offsets, np.float32, decode_layer._anchors.device, "nms_off")
+        logits, _ = _ssdx.to_device(labels_logits, np.float32, off.device.index, "nms_logits")
+        if off.dim() != 3 or off.shape[2] != 4 or logits.dim() != 3 or logits.shape[:2] != off.shape[:2]:
+            raise ValueError("expected offsets (batch, boxes, 4) and logits (batch, boxes, classes)")
+        if int(off.shape[1]) != decode_layer._anchors.num_anchors:
+            raise ValueError("offsets do not match the number of default boxes of the decode layer")
+        if class_scale is not None:
+            class_scale, _ = _ssdx.to_device(class_scale, np.float32, off.device.index, "nms_scale")
+        out, valid, aidx = _ssdx.decode_nms_logits(decode_layer._anchors, off, decode_layer._std, logits,
+                                                   self.max_number_of_boxes_per_class,
+                                                   self.max_number_of_boxes_per_sample, self.boxes_iou_threshold,
+                                                   self.labels_probability_threshold, want_aux=return_aux,
+                                                   class_scale=class_scale)
+        if self.suppress_background_boxes:
+            out = out[out[..., 0] > 0.0]
+        res = _ssdx.from_device(out, kind)
+        if return_aux:
+            return res, _ssdx.from_device(valid, kind), _ssdx.from_device(aidx, kind)
+        return res
+
     def call_on_offsets(self, decode_layer, boxes_centroids_offsets, labels_probabilities, return_aux: bool = False,
                         class_scale=None):
         """`self.call(decode_layer.call(offsets), probabilities)` as one operation (new entry point): the wiring of

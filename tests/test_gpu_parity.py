@@ -445,6 +445,24 @@ def test_nms_randomized_differential(lib, nms_path):
     assert mod.run(250 if nms_path == "fast" else 120, seed, verbose=False) == 0
 
 
+@pytest.mark.parametrize("C,mpc,mtot", [(4, 200, 200), (4, 4, 10), (6, 50, 50)])
+def test_inference_tail_offsets_and_logits_in_one_call(lib, golden, C, mpc, mtot):
+    """decode + soft-max + NMS as one call (boxes decoded per candidate, probabilities inside the score filter) equals
+    the three separate layers bit for bit, on the fused path (4 classes, merged pipeline) and on the others."""
+    a = golden("anchors")["std_centroids"]
+    rng = np.random.default_rng(60 + C + mpc)
+    off, _ = orc.synth_predictions(rng, 3, 9600, 4)
+    logits = rng.normal(0, 2.5, size=(3, 9600, C)).astype(np.float32)
+    dec = lib.layers.DecodeBoxesCentroidsOffsets(a[:, 0], a[:, 1], a[:, 2], a[:, 3], *STD)
+    layer = lib.layers.NonMaximumSuppression(mpc, mtot, 0.45, 0.05, False)
+    scale = np.array([1.0, 0.0] + [1.0] * (C - 2), np.float32)
+    for cs in (None, scale):
+        got = layer.call_on_offsets_and_logits(dec, off, logits, return_aux=True, class_scale=cs)
+        ref = layer.call(dec(off), layer.softmax_probabilities(logits), return_aux=True, class_scale=cs)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+
+
 def test_nms_two_phase_on_a_side_stream(lib, golden):
     """select (scores only, on a side stream) + finish == call, on the merged and on the per-class pipeline."""
     import torch

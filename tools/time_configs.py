@@ -135,6 +135,24 @@ def config1():
          32 * A * C // 4 + 16 * A + 4 * A * C + 24 * K, "pass")
     emit("ssdx_nms_logits, batch 1024 (round-trip predictions of the bench)", B2, ml, bl, 16 * A + 4 * A * C + 24 * K,
          "pass" if torch.equal(od4, od5) else "FAIL")
+    # the whole inference tail: offsets + logits -> detections, three kernels / tensors vs one call
+    od6, od7 = torch.empty((B2, K, 6), **f32), torch.empty((B2, K, 6), **f32)
+
+    def three_layers():
+        sx.check(sx.lib.ssdx_decode(h, off_t.data_ptr(), B2, std, 0, ob2.data_ptr(), sp))
+        sx.check(sx.lib.ssdx_softmax_scores(lg.data_ptr(), B2 * A, C, None, pr.data_ptr(), dev, sp))
+        sx.check(sx.lib.ssdx_nms(ob2.data_ptr(), pr.data_ptr(), B2, A, C, K, K, 0.45, 0.01, od6.data_ptr(), None, None,
+                                 ws2.data_ptr(), ws2.numel(), dev, sp))
+
+    def one_call():
+        sx.check(sx.lib.ssdx_decode_nms_logits(h, off_t.data_ptr(), std, lg.data_ptr(), None, B2, C, K, K, 0.45, 0.01,
+                                               od7.data_ptr(), None, None, wsl.data_ptr(), wsl.numel(), sp))
+    m3, b3 = timeit(three_layers)
+    m1, b1 = timeit(one_call)
+    emit("inference tail as three layers: decode + soft-max + NMS, batch 1024 (round-trip predictions)", B2, m3, b3,
+         32 * A + 32 * A * C // 4 + 16 * A + 4 * A * C + 24 * K, "pass")
+    emit("inference tail in one call: ssdx_decode_nms_logits, batch 1024 (round-trip predictions)", B2, m1, b1,
+         16 * A + 4 * A * C + 24 * K, "pass" if torch.equal(od6, od7) else "FAIL")
 
 
 # ------------------------------------------------------------------------------------------------ config 3
