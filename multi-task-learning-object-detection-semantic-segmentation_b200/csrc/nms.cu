@@ -282,7 +282,7 @@ __device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n,
 // info per (image, class): [0] listed candidates (may exceed kCap), [2] threshold key (every candidate with key >= it
 // is listed).  Same scheme as the merged select below, per class: threshold = the kTierRank-th largest of the
 // per-thread maxima of a 1/16 sample, then one streaming pass with one compare per score and marked hits.
-template <bool VEC4>
+template <bool VEC4, bool LOGITS>  // LOGITS (VEC4 only): `scores` holds raw logits, see ssdx_nms_select_all_kernel
 __global__ void __launch_bounds__(kSelThreads)
     ssdx_nms_select_kernel(const float* __restrict__ scores, const float* __restrict__ cscale, const int A,
                            const int C, const float score_thr, const int tier_rank, u64* __restrict__ lists,
@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(kSelThreads)
     int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
     a = a < A ? a : A - 1;
     if (VEC4) {
-      const float4 s = mul4(__ldg(reinterpret_cast<const float4*>(img) + a), class_factor4(cscale));
+      float4 raw = __ldg(reinterpret_cast<const float4*>(img) + a);
+      if (LOGITS) raw = ssdx_softmax4(raw);
+      const float4 s = mul4(raw, class_factor4(cscale));
       const float sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -375,12 +377,18 @@ __global__ void __launch_bounds__(kSelThreads)
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int a = a0 + u * kSelThreads;
-        sb[u] = (a < A) ? mul4(__ldcs(reinterpret_cast<const float4*>(img) + a), cf4)
+        sb[u] = (a < A) ? __ldcs(reinterpret_cast<const float4*>(img) + a)
                         : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+      if (LOGITS) {
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          if (a0 + u * kSelThreads < A) sb[u] = ssdx_softmax4(sb[u]);
       }
       unsigned hits = 0u;  // bit 4*u + c
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
+        sb[u] = mul4(sb[u], cf4);
         hits |= (sb[u].x >= t0 ? 1u : 0u) << (4 * u);
         hits |= (sb[u].y >= t1 ? 2u : 0u) << (4 * u);
         hits |= (sb[u].z >= t2 ? 4u : 0u) << (4 * u);
@@ -390,7 +398,13 @@ __global__ void __launch_bounds__(kSelThreads)
         const int bit = __ffs(hits) - 1;
         hits &= hits - 1u;
         const int a = a0 + (bit >> 2) * kSelThreads, c = bit & 3;
-        const float s = __fmul_rn(__ldg(img + (size_t)a * 4 + c), class_factor(cscale, c));
+        float s;
+        if (LOGITS) {
+          const float4 p = ssdx_softmax4(__ldg(reinterpret_cast<const float4*>(img) + a));
+          s = __fmul_rn(c == 0 ? p.x : (c == 1 ? p.y : (c == 2 ? p.z : p.w)), class_factor(cscale, c));
+        } else {
+          s = __fmul_rn(__ldg(img + (size_t)a * 4 + c), class_factor(cscale, c));
+        }
         const int pos = atomicAdd(&s_cnt[c], 1);
         if (pos < kCap) img_lists[(size_t)c * kCap + pos] = make_comp(score_to_key(s), a);
       }
@@ -720,6 +734,7 @@ constexpr int kWarpCap = kWarpSlots * 32;
 constexpr int kWarpSegs = kFastThreads / 32;  // segments per CTA
 constexpr int kWarpRefillTarget = 96;
 
+template <bool LOGITS>  // LOGITS: `scores` holds raw logits of 4 classes (band refills recompute the soft-max rows)
 __global__ void __launch_bounds__(kFastThreads)
     ssdx_nms_fast_warp_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                               const float* __restrict__ cscale, const u64* __restrict__ lists,
@@ -881,7 +896,13 @@ __global__ void __launch_bounds__(kFastThreads)
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const int a = a0 + u * 32 + lane;
-            sv[u] = (a < A) ? __fmul_rn(__ldg(cls_scores + (size_t)a * C), cf) : -INFINITY;
+            if (LOGITS) {
+              const float4 p = (a < A) ? ssdx_softmax4(__ldg(reinterpret_cast<const float4*>(cls_scores - c) + a))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+              sv[u] = (a < A) ? __fmul_rn(c == 0 ? p.x : (c == 1 ? p.y : (c == 2 ? p.z : p.w)), cf) : -INFINITY;
+            } else {
+              sv[u] = (a < A) ? __fmul_rn(__ldg(cls_scores + (size_t)a * C), cf) : -INFINITY;
+            }
           }
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
@@ -1665,6 +1686,17 @@ static bool nms_merged_applies(const int A, const int C, const int max_per_class
          max_total <= kFastMaxSel;
 }
 
+// raw logits can be consumed directly (soft-max inside the kernels that read the scores): 4 aligned classes on the
+// merged pipeline, or on the per-class pipeline with caps small enough for the one-warp-per-segment kernel
+static bool nms_logits_fusable(const int A, const int C, const int max_per_class, const int max_total,
+                               const float* logits) {
+  if (C != 4 || (((uintptr_t)logits & 15) != 0)) return false;
+  if (nms_merged_applies(A, C, max_per_class, max_total)) return true;
+  const char* force = getenv("SSDX_NMS_PATH");
+  if (force != nullptr && (force[0] == 'g' || (force[0] == 'p' && force[1] == 'c'))) return false;
+  return (max_per_class < A ? max_per_class : A) <= 32;
+}
+
 // phases: 1 = candidate selection (reads only the scores), 2 = everything that needs the boxes.  ssdx_nms runs both;
 // ssdx_nms_select / ssdx_nms_finish expose them separately so that a caller can run phase 1 on another stream while
 // the boxes are still being decoded (in the reference's inference graph the two inputs of the NMS layer are
@@ -1727,7 +1759,8 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
 
   // ---- merged pipeline: one list / sort / greedy pass per image ----
   const bool merged = nms_merged_applies(A, C, max_per_class, max_total);
-  SSDX_CHECK_ARG(!logits || (merged && vec4), "ssdx_nms: logits need the merged pipeline with 4 aligned classes");
+  SSDX_CHECK_ARG(!logits || nms_logits_fusable(A, C, max_per_class, max_total, scores),
+                 "ssdx_nms: logits on a path that cannot fuse the soft-max");
   if (merged) {
     if (ph1) {
       // first list sized to max_total (rank (3 K + 63) / 16 of the thread maxima, at most kAllRank = the K = 200 tuning)
@@ -1769,12 +1802,15 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   tier_rank = tier_rank < 4 ? 4 : (tier_rank > kTierRank ? kTierRank : tier_rank);
   if (use_fast && ph1) {
     dim3 gsel((C + kSelGroup - 1) / kSelGroup, batch);
-    if (vec4)
-      ssdx_nms_select_kernel<true><<<gsel, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, tier_rank,
-                                                                lists, info, flags);
+    if (logits)
+      ssdx_nms_select_kernel<true, true><<<gsel, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, tier_rank,
+                                                                      lists, info, flags);
+    else if (vec4)
+      ssdx_nms_select_kernel<true, false><<<gsel, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
+                                                                       tier_rank, lists, info, flags);
     else
-      ssdx_nms_select_kernel<false><<<gsel, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold, tier_rank,
-                                                                 lists, info, flags);
+      ssdx_nms_select_kernel<false, false><<<gsel, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
+                                                                        tier_rank, lists, info, flags);
     SSDX_LAUNCH_CHECK("ssdx_nms_select_kernel");
   }
   if (!ph2) return SSDX_OK;
@@ -1783,9 +1819,15 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   if (use_fast && limit <= 32 && !no_warp) {
     // 2w. one warp per segment, never hands over: select -> warp -> merge
     const int fuse_merge = (kWarpSegs % C) == 0;  // C = 1, 2, 4, 8: the rows are written by the same kernel
-    ssdx_nms_fast_warp_kernel<<<(num_segments + kWarpSegs - 1) / kWarpSegs, kFastThreads, 0, s>>>(
-        bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt,
-        fuse_merge, max_total, out, out_valid, out_anchor_idx);
+    const int warp_grid = (num_segments + kWarpSegs - 1) / kWarpSegs;
+    if (logits)
+      ssdx_nms_fast_warp_kernel<true><<<warp_grid, kFastThreads, 0, s>>>(
+          bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt,
+          fuse_merge, max_total, out, out_valid, out_anchor_idx);
+    else
+      ssdx_nms_fast_warp_kernel<false><<<warp_grid, kFastThreads, 0, s>>>(
+          bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt,
+          fuse_merge, max_total, out, out_valid, out_anchor_idx);
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_warp_kernel");
     if (fuse_merge) return SSDX_OK;
     ssdx_nms_merge_kernel<<<batch, kMergeThreads, stage ? merge_smem : 0, s>>>(bx, picks, pick_cnt, A, C, limit,
@@ -1880,8 +1922,7 @@ extern "C" int ssdx_nms_logits(const float* boxes_yxyx, const float* logits, con
     ssdx_set_error("ssdx_nms_logits: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return SSDX_ERR_WORKSPACE;
   }
-  const bool fused = num_classes == 4 && (((uintptr_t)logits & 15) == 0) &&
-                     nms_merged_applies(num_anchors, num_classes, max_per_class, max_total);
+  const bool fused = nms_logits_fusable(num_anchors, num_classes, max_per_class, max_total, logits);
   if (fused)  // the probabilities exist only in registers
     return nms_run(3, 1, nullptr, boxes_yxyx, logits, class_scale, batch, num_anchors, num_classes, max_per_class,
                    max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes,
@@ -1917,8 +1958,7 @@ extern "C" int ssdx_decode_nms_logits(const ssdx_anchors* anchors, const float* 
   }
   const ssdx_box_src src{nullptr, (const float4*)offsets, anchors->dec_cent, std_host[0], std_host[1], std_host[2],
                          std_host[3]};
-  const bool fused = num_classes == 4 && (((uintptr_t)logits & 15) == 0) &&
-                     nms_merged_applies(A, num_classes, max_per_class, max_total);
+  const bool fused = nms_logits_fusable(A, num_classes, max_per_class, max_total, logits);
   if (fused)
     return nms_run(3, 1, &src, nullptr, logits, class_scale, batch, A, num_classes, max_per_class, max_total,
                    iou_threshold, score_threshold, out, out_valid, out_anchor_idx, workspace, workspace_bytes,

@@ -153,6 +153,25 @@ def config1():
          32 * A + 32 * A * C // 4 + 16 * A + 4 * A * C + 24 * K, "pass")
     emit("inference tail in one call: ssdx_decode_nms_logits, batch 1024 (round-trip predictions)", B2, m1, b1,
          16 * A + 4 * A * C + 24 * K, "pass" if torch.equal(od6, od7) else "FAIL")
+    # the same at the reference's own inference setting (4 per class, 10 per image, IoU 0.025, probability 0.725)
+    o8, o9 = torch.empty((B2, 10, 6), **f32), torch.empty((B2, 10, 6), **f32)
+    wsn = torch.empty(int(sx.lib.ssdx_nms_logits_workspace_bytes(B2, A, C, 4, 10)), dtype=torch.uint8, device="cuda:0")
+
+    def three_layers_nb():
+        sx.check(sx.lib.ssdx_decode(h, off_t.data_ptr(), B2, std, 0, ob2.data_ptr(), sp))
+        sx.check(sx.lib.ssdx_softmax_scores(lg.data_ptr(), B2 * A, C, None, pr.data_ptr(), dev, sp))
+        sx.check(sx.lib.ssdx_nms(ob2.data_ptr(), pr.data_ptr(), B2, A, C, 4, 10, 0.025, 0.725, o8.data_ptr(), None, None,
+                                 wsn.data_ptr(), wsn.numel(), dev, sp))
+
+    def one_call_nb():
+        sx.check(sx.lib.ssdx_decode_nms_logits(h, off_t.data_ptr(), std, lg.data_ptr(), None, B2, C, 4, 10, 0.025, 0.725,
+                                               o9.data_ptr(), None, None, wsn.data_ptr(), wsn.numel(), sp))
+    m3, b3 = timeit(three_layers_nb)
+    m1, b1 = timeit(one_call_nb)
+    emit("inference tail as three layers at the notebook's NMS setting (4 / 10 / 0.025 / 0.725), batch 1024", B2, m3, b3,
+         32 * A + 32 * A * C // 4 + 16 * A + 4 * A * C + 24 * 10, "pass")
+    emit("inference tail in one call at the notebook's NMS setting, batch 1024", B2, m1, b1, 16 * A + 4 * A * C + 24 * 10,
+         "pass" if torch.equal(o8, o9) else "FAIL")
 
 
 # ------------------------------------------------------------------------------------------------ config 3
