@@ -143,7 +143,10 @@ __device__ __forceinline__ float anchor_loss(const float* __restrict__ yt, const
                                              const float lo, const float hi, float& is_bg) {
   float acc = 0.0f;
   is_bg = __ldg(yt);
-  for (int c = 0; c < C; ++c) acc = __fadd_rn(acc, __fmul_rn(__ldg(yt + c), logf(fminf(fmaxf(__ldg(yp + c), lo), hi))));
+  for (int c = 0; c < C; ++c) {
+    const float t = __ldg(yt + c);
+    if (t != 0.0f) acc = __fadd_rn(acc, __fmul_rn(t, logf(fminf(fmaxf(__ldg(yp + c), lo), hi))));  // (zero terms: see below)
+  }
   return -acc;
 }
 
@@ -181,11 +184,14 @@ __global__ void __launch_bounds__(kLossThreads)
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        // a term with a zero target is +-0 (the clipped logarithm is finite) and leaves the running sum unchanged
+        // bit for bit, so its logarithm is skipped: one logf per one-hot row instead of four (the four full-precision
+        // logarithms made this pass instruction-bound: 73 us against 58 us)
         float acc = 0.0f;
-        acc = __fadd_rn(acc, __fmul_rn(t[u].x, logf(fminf(fmaxf(p[u].x, lo), hi))));
-        acc = __fadd_rn(acc, __fmul_rn(t[u].y, logf(fminf(fmaxf(p[u].y, lo), hi))));
-        acc = __fadd_rn(acc, __fmul_rn(t[u].z, logf(fminf(fmaxf(p[u].z, lo), hi))));
-        acc = __fadd_rn(acc, __fmul_rn(t[u].w, logf(fminf(fmaxf(p[u].w, lo), hi))));
+        if (t[u].x != 0.0f) acc = __fadd_rn(acc, __fmul_rn(t[u].x, logf(fminf(fmaxf(p[u].x, lo), hi))));
+        if (t[u].y != 0.0f) acc = __fadd_rn(acc, __fmul_rn(t[u].y, logf(fminf(fmaxf(p[u].y, lo), hi))));
+        if (t[u].z != 0.0f) acc = __fadd_rn(acc, __fmul_rn(t[u].z, logf(fminf(fmaxf(p[u].z, lo), hi))));
+        if (t[u].w != 0.0f) acc = __fadd_rn(acc, __fmul_rn(t[u].w, logf(fminf(fmaxf(p[u].w, lo), hi))));
         la[u] = -acc;
         is_bg[u] = t[u].x;
       }
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(kLossThreads)
       float r[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const bool pass = pp[c] >= lo && pp[c] <= hi;
+        const bool pass = pp[c] >= lo && pp[c] <= hi && tt[c] != 0.0f;  // zero target: the quotient is +-0, skipped
         r[c] = pass ? __fdiv_rn(__fmul_rn(w, tt[c]), fminf(fmaxf(pp[c], lo), hi)) : 0.0f;
       }
       st_stream_f4(reinterpret_cast<float4*>(g), make_float4(r[0], r[1], r[2], r[3]));
@@ -459,9 +465,9 @@ __global__ void __launch_bounds__(kLossThreads)
       const float is_bg = __ldg(t), not_bg = fabsf(__fsub_rn(is_bg, 1.0f));
       const float w = -__fdiv_rn(__fadd_rn(not_bg, keep ? is_bg : 0.0f), den);
       for (int c = 0; c < C; ++c) {
-        const float pc = __ldg(p + c);
-        const bool pass = pc >= lo && pc <= hi;
-        g[c] = pass ? __fdiv_rn(__fmul_rn(w, __ldg(t + c)), fminf(fmaxf(pc, lo), hi)) : 0.0f;
+        const float pc = __ldg(p + c), tc = __ldg(t + c);
+        const bool pass = pc >= lo && pc <= hi && tc != 0.0f;
+        g[c] = pass ? __fdiv_rn(__fmul_rn(w, tc), fminf(fmaxf(pc, lo), hi)) : 0.0f;
       }
     }
   };
