@@ -723,19 +723,21 @@ __device__ __forceinline__ void merge_image_rows(const ssdx_box_src boxes, const
 // ------------------------------------------------------------------------------------------ 2w. per-class, small caps
 // One WARP per (image, class) segment for per-class caps of at most 32 boxes (the reference's own inference setting is
 // 4 per class / 10 per image, 03-...ipynb): a CTA per segment spends its life in barriers and dependent loads for a
-// handful of boxes.  The warp holds up to kWarpSlots * 32 candidates in registers (composite, box, area) and runs the
+// handful of boxes.  The warp holds up to SLOTS * 32 candidates in registers (composite, box, area) and runs the
 // classic form of the same greedy rule: take the best candidate still alive, keep it, kill every candidate whose IoU
 // with it exceeds the threshold - one round per KEPT box instead of one test per visited candidate.  When the list
 // runs dry it fetches the next band of the composite order (score key, anchor) from the scores, tests the newcomers
 // against the boxes kept so far and goes on; an over-full band is narrowed, down to a single candidate, so the kernel
 // never hands a segment over (thousands of equal scores included).
-constexpr int kWarpSlots = 8;
-constexpr int kWarpCap = kWarpSlots * 32;
 constexpr int kWarpSegs = kFastThreads / 32;  // segments per CTA
 constexpr int kWarpRefillTarget = 96;
 
-template <bool LOGITS>  // LOGITS: `scores` holds raw logits of 4 classes (band refills recompute the soft-max rows)
-__global__ void __launch_bounds__(kFastThreads)
+// LOGITS: `scores` holds raw logits of 4 classes (band refills recompute the soft-max rows).  SLOTS candidates per lane
+// in registers, MINB resident CTAs per SM: <8, 1> for caps up to 8 (few rounds: the whole listed tier in registers
+// matters more than occupancy), <4, 4> above (many rounds: 32 resident warps per SM hide their latency; 20 / 50 / 0.3
+// / 0.3 at batch 1024: 79 us against 104 us).
+template <bool LOGITS, int SLOTS, int MINB>
+__global__ void __launch_bounds__(kFastThreads, MINB)
     ssdx_nms_fast_warp_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                               const float* __restrict__ cscale, const u64* __restrict__ lists,
                               const int* __restrict__ info, const int A, const int C, const int num_segments,
@@ -744,6 +746,7 @@ __global__ void __launch_bounds__(kFastThreads)
                               int* __restrict__ out_valid, int* __restrict__ out_idx) {
   // fuse_merge (the class count divides the segments of a CTA: every image lies inside one CTA): the picks stay in
   // shared memory and one warp per image writes the image's rows at the end - no pick lists in memory, no merge launch
+  constexpr int kWarpSlots = SLOTS, kWarpCap = SLOTS * 32;
   __shared__ u64 s_stage[kWarpSegs][kWarpCap];  // refill staging, one row per warp
   __shared__ u64 s_picks[kWarpSegs][32];
   __shared__ int s_cnt[kWarpSegs];
@@ -1820,14 +1823,18 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
     // 2w. one warp per segment, never hands over: select -> warp -> merge
     const int fuse_merge = (kWarpSegs % C) == 0;  // C = 1, 2, 4, 8: the rows are written by the same kernel
     const int warp_grid = (num_segments + kWarpSegs - 1) / kWarpSegs;
-    if (logits)
-      ssdx_nms_fast_warp_kernel<true><<<warp_grid, kFastThreads, 0, s>>>(
-          bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt,
-          fuse_merge, max_total, out, out_valid, out_anchor_idx);
-    else
-      ssdx_nms_fast_warp_kernel<false><<<warp_grid, kFastThreads, 0, s>>>(
-          bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt,
-          fuse_merge, max_total, out, out_valid, out_anchor_idx);
+#define SSDX_WARP_LAUNCH(LOG, SLOTS, MINB)                                                                         \
+  ssdx_nms_fast_warp_kernel<LOG, SLOTS, MINB><<<warp_grid, kFastThreads, 0, s>>>(                                  \
+      bx, scores, cscale, lists, info, A, C, num_segments, limit, iou_threshold, score_threshold, picks, pick_cnt, \
+      fuse_merge, max_total, out, out_valid, out_anchor_idx)
+    if (limit <= 8) {
+      if (logits) SSDX_WARP_LAUNCH(true, 8, 1);
+      else SSDX_WARP_LAUNCH(false, 8, 1);
+    } else {
+      if (logits) SSDX_WARP_LAUNCH(true, 4, 4);
+      else SSDX_WARP_LAUNCH(false, 4, 4);
+    }
+#undef SSDX_WARP_LAUNCH
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_warp_kernel");
     if (fuse_merge) return SSDX_OK;
     ssdx_nms_merge_kernel<<<batch, kMergeThreads, stage ? merge_smem : 0, s>>>(bx, picks, pick_cnt, A, C, limit,
