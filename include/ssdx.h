@@ -56,6 +56,12 @@ SSDX_API int ssdx_version(void);
 SSDX_API const char* ssdx_last_error(void);
 /* Number of CUDA devices visible; SSDX_ERR_CUDA if the driver is unusable. */
 SSDX_API int ssdx_device_count(int* count);
+/* Process-level dispatch override; every path of an entry point gives identical results, the options exist for tests
+ * and tuning runs.  key "encode_path": "auto" | "grid_fused" | "grid_split" (closed-form windows, anchor tables that
+ * are unions of regular grids) | "tile_fused" | "tile_tiled" (tile match, any anchor table);
+ * key "nms_path": "auto" | "perclass" | "pcta" | "generic".  A forced path that cannot serve a call (table is not a
+ * grid, shapes too large for one CTA per image) falls back to the automatic choice for that call. */
+SSDX_API int ssdx_set_option(const char* key, const char* value);
 
 /* ---- anchors: datacoder.py:6-117 (ctor), boxes.py:391-445 (conversions) ----
  * corners_xyxy_host : host, (A,4) xmin,ymin,xmax,ymax - what the ctor stores or derives (:59-62, :84-89)
@@ -67,6 +73,20 @@ SSDX_API int ssdx_anchors_create(const float* corners_xyxy_host, const float* ce
 SSDX_API int ssdx_anchors_destroy(ssdx_anchors* anchors);
 SSDX_API int ssdx_anchors_count(const ssdx_anchors* anchors, int32_t* num_anchors);
 SSDX_API int ssdx_anchors_device(const ssdx_anchors* anchors, int* device);
+/* num_grids > 0 when the table was recognised as a union of regular (feature map, box shape) grids - true for every
+ * output of boxes.DefaultBoundingBoxes (boxes.py:112-146, :198-205); encode then finds the pairs that can matter in
+ * closed form.  num_spans = row ranges the large-table / small-batch encode driver cuts the maps into.  Either
+ * pointer may be NULL. */
+SSDX_API int ssdx_anchors_grid_info(const ssdx_anchors* anchors, int32_t* num_grids, int32_t* num_spans);
+/* The same detection on the host alone (no device): grids_out, when not NULL, receives up to `capacity` rows of
+ * (first anchor, rows, columns, shapes per cell) - anchor(row, col) of grid i = first + (row * columns + col) * shapes. */
+SSDX_API int ssdx_grid_probe(const float* corners_xyxy_host, int32_t num_anchors, int32_t* num_grids,
+                             int32_t* num_spans, int32_t* grids_out, int32_t capacity);
+/* Host-only: the cell window ssdx_encode's grid drivers enumerate for every (GT box i, grid q) at the IoU bound
+ * t_host[i] - no anchor outside the window reaches IoU >= t with the box (datacoder.py:205-220 arithmetic).
+ * out (n_boxes, num_grids, 4) i32 = (first row, rows, first column, columns); rows = 0: empty window. */
+SSDX_API int ssdx_grid_window_probe(const float* corners_xyxy_host, int32_t num_anchors, const float* gt_xyxy_host,
+                                    const float* t_host, int32_t n_boxes, int32_t* out);
 
 /* ---- encode: datacoder.py:205-300 (_encode_ground_truth_labels_boxes, after the CSV read) ----
  * gt_xyxy   (B,Gmax,4) f32, gt_label (B,Gmax) i32, gt_count (B) i32 (0 <= count <= Gmax; 0 => all background)

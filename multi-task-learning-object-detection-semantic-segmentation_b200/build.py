@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libssdx.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["capi.cu", "decode.cu", "encode.cu", "nms.cu", "eval.cu", "seg.cu", "metric.cu", "ap.cu", "loss.cu"]
+SOURCES = ["capi.cu", "decode.cu", "encode.cu", "encode_grid.cu", "nms.cu", "eval.cu", "seg.cu", "metric.cu", "ap.cu", "loss.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -56,16 +56,60 @@ def build(force: bool = False, verbose: bool = False, debug_timers: bool = False
 
 
 def _compile(out: str, verbose: bool, extra) -> str:
+    """One nvcc per translation unit (in parallel, objects cached under build/ by source + flag hash), then one link."""
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + ["-I", INCLUDE, "-I", CSRC]
+    objdir = os.path.join(os.path.dirname(HERE), "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = find_nvcc()
+    cflags = [f for f in NVCC_FLAGS if f != "--shared"] + list(extra) + ["-I", INCLUDE, "-I", CSRC]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+        cflags += ["-Xptxas", "-v"]
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    headers.append(os.path.join(INCLUDE, "ssdx.h"))
+    hdr_hash = hashlib.sha1()
+    for h in headers:
+        with open(h, "rb") as f:
+            hdr_hash.update(f.read())
+    hdr_hash.update(" ".join(cflags).encode())
+
+    def one(src_name):
+        src = os.path.join(CSRC, src_name)
+        hsh = hashlib.sha1(hdr_hash.digest())
+        with open(src, "rb") as f:
+            hsh.update(f.read())
+        obj = os.path.join(objdir, f"{os.path.splitext(src_name)[0]}.{hsh.hexdigest()[:16]}.o")
+        if os.path.exists(obj) and not verbose:
+            return obj, 0, ""
+        r = subprocess.run([nvcc] + cflags + ["-c", "-o", obj, src], capture_output=True, text=True)
+        if r.returncode != 0 and os.path.exists(obj):
+            os.remove(obj)
+        return obj, r.returncode, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(one, SOURCES))
+    log = "".join(r[2] for r in results)
+    if verbose or any(r[1] != 0 for r in results):
+        sys.stderr.write(log)
+    if any(r[1] != 0 for r in results):
+        raise RuntimeError("nvcc failed building " + os.path.basename(out))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-Xcompiler", "-fPIC",
+           "-o", out] + [r[0] for r in results]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building " + os.path.basename(out))
+        raise RuntimeError("nvcc failed linking " + os.path.basename(out))
+    keep = {os.path.basename(r[0]) for r in results}
+    for f in os.listdir(objdir):  # drop objects of older sources of the same unit (variants keep their own hashes)
+        stem = f.split(".")[0]
+        if f not in keep and not extra and any(k.startswith(stem + ".") for k in keep):
+            try:
+                os.remove(os.path.join(objdir, f))
+            except OSError:
+                pass
     return out
 
 

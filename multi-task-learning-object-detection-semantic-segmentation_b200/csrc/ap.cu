@@ -147,7 +147,7 @@ extern "C" int ssdx_average_precision(const uint8_t* tp, const float* confidence
     return SSDX_ERR_WORKSPACE;
   }
   SSDX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "ssdx_average_precision: workspace must be 256-byte aligned");
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   cudaStream_t s = (cudaStream_t)stream;
   char* base = (char*)workspace;
   u64* keys_in = (u64*)(base + w.keys_in);

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "grid_window.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -23,8 +24,19 @@ void ssdx_set_error(const char* fmt, ...) {
 }
 
 bool ssdx_debug_sync() {
-  const char* e = getenv("SSDX_DEBUG_SYNC");
-  return e != nullptr && e[0] == '1';
+  static const bool on = [] {  // read once: the check sits behind every launch
+    const char* e = getenv("SSDX_DEBUG_SYNC");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
+static std::atomic<int> g_encode_path(SSDX_ENC_AUTO);
+static std::atomic<int> g_nms_path(0);
+int ssdx_option_encode_path() { return g_encode_path.load(std::memory_order_relaxed); }
+const char* ssdx_option_nms_path() {
+  static const char* const names[4] = {nullptr, "perclass", "pcta", "generic"};
+  return names[g_nms_path.load(std::memory_order_relaxed) & 3];
 }
 
 int ssdx_sm_count(int device) {
@@ -38,11 +50,174 @@ int ssdx_sm_count(int device) {
   return cache[device];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Grid detection (encode_grid.cu).  boxes.DefaultBoundingBoxes lays the anchors out map-major, then row, column,
+// box shape (boxes.py:198-205), with corners = centre -/+ (size - 1) / 2 from a meshgrid of per-axis centres
+// (boxes.py:112-146) - so inside one map the x extents of (row, col, k) do not depend on the row and the y extents do
+// not depend on the column, bit for bit, whatever rescale or corner/centroid conversion came after.  The table is
+// scanned for that structure; any table that does not have it (subsets, permutations, hand-made anchors) keeps the
+// general tile match.  Only exact equalities decide; the centre model below merely sizes windows and carries its own
+// measured error.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct GridMap { size_t off; int H, W, nb; };
+
+inline bool same_x(const float* c, size_t i, size_t j) {
+  return memcmp(c + 4 * i, c + 4 * j, 4) == 0 && memcmp(c + 4 * i + 2, c + 4 * j + 2, 4) == 0;
+}
+inline bool same_y(const float* c, size_t i, size_t j) {
+  return memcmp(c + 4 * i + 1, c + 4 * j + 1, 4) == 0 && memcmp(c + 4 * i + 3, c + 4 * j + 3, 4) == 0;
+}
+
+// rows [r_from, r_to) of the candidate map repeat the x extents of row 0 and hold one y extent per shape
+bool rows_ok(const float* c, size_t off, int r_from, int r_to, int W, int nb) {
+  const size_t L = (size_t)W * nb;
+  for (int r = r_from; r < r_to; ++r) {
+    const size_t row = off + (size_t)r * L;
+    for (size_t j = 0; j < L; ++j) {
+      if (!same_x(c, off + j, row + j)) return false;
+      if (!same_y(c, row + j % nb, row + j)) return false;
+    }
+  }
+  return true;
+}
+
+// model + pads of one (map, shape); false = unusable for windows (the caller tries another decomposition)
+bool make_combo(const float* c, const float* area, const GridMap& m, int k, ssdx_grid_combo* out) {
+  const int H = m.H, W = m.W, nb = m.nb;
+  const size_t L = (size_t)W * nb;
+  auto X0 = [&](int col) { return (double)c[4 * (m.off + (size_t)col * nb + k) + 0]; };
+  auto X1 = [&](int col) { return (double)c[4 * (m.off + (size_t)col * nb + k) + 2]; };
+  auto Y0 = [&](int row) { return (double)c[4 * (m.off + (size_t)row * L + k) + 1]; };
+  auto Y1 = [&](int row) { return (double)c[4 * (m.off + (size_t)row * L + k) + 3]; };
+  double hx = -1e300, hy = -1e300, maxabs = 0;
+  for (int col = 0; col < W; ++col) {
+    if (!(X1(col) - X0(col) + 1.0 > 0.0)) return false;  // (boxes smaller than one cell have x1 < x0: boxes.py:143)
+    hx = std::max(hx, 0.5 * (X1(col) - X0(col)));
+    maxabs = std::max(maxabs, std::max(fabs(X0(col)), fabs(X1(col))));
+  }
+  for (int row = 0; row < H; ++row) {
+    if (!(Y1(row) - Y0(row) + 1.0 > 0.0)) return false;
+    hy = std::max(hy, 0.5 * (Y1(row) - Y0(row)));
+    maxabs = std::max(maxabs, std::max(fabs(Y0(row)), fabs(Y1(row))));
+  }
+  const double cx0 = 0.5 * (X0(0) + X1(0)), cy0 = 0.5 * (Y0(0) + Y1(0));
+  const double dx = W > 1 ? (0.5 * (X0(W - 1) + X1(W - 1)) - cx0) / (W - 1) : 1.0;
+  const double dy = H > 1 ? (0.5 * (Y0(H - 1) + Y1(H - 1)) - cy0) / (H - 1) : 1.0;
+  if (!(dx > 0.0) || !(dy > 0.0)) return false;
+  double ex = 0, ey = 0;
+  for (int col = 0; col < W; ++col)
+    ex = std::max(ex, fabs(0.5 * (X0(col) + X1(col)) - (cx0 + col * dx)) + fabs(0.5 * (X1(col) - X0(col)) - hx));
+  for (int row = 0; row < H; ++row)
+    ey = std::max(ey, fabs(0.5 * (Y0(row) + Y1(row)) - (cy0 + row * dy)) + fabs(0.5 * (Y1(row) - Y0(row)) - hy));
+  if ((W > 1 && ex > 0.25 * dx) || (H > 1 && ey > 0.25 * dy)) return false;  // not a regular grid after all
+  float amin = INFINITY, amax = -INFINITY;
+  for (int row = 0; row < H; ++row)
+    for (int col = 0; col < W; ++col) {
+      const float a = area[m.off + ((size_t)row * W + col) * nb + k];
+      if (!(a > 0.0f) || !std::isfinite(a)) return false;
+      amin = std::min(amin, a);
+      amax = std::max(amax, a);
+    }
+  // rounding margin: the device evaluates the window bounds in fp32 on coordinates of this magnitude
+  const double margin = 0.01 + 1e-5 * maxabs;
+  out->off = (int)(m.off + k);
+  out->H = H; out->W = W; out->nb = nb;
+  out->cx0 = (float)cx0; out->inv_dx = (float)(1.0 / dx);
+  out->cy0 = (float)cy0; out->inv_dy = (float)(1.0 / dy);
+  out->hx = (float)(hx + 1e-6 * fabs(hx)); out->hy = (float)(hy + 1e-6 * fabs(hy));
+  out->px = (float)(1.01 * ex + margin); out->py = (float)(1.01 * ey + margin);
+  out->aw = (float)((2 * hx + 1) * (1 + 1e-6)); out->ah = (float)((2 * hy + 1) * (1 + 1e-6));
+  out->amin = amin; out->amax = amax;
+  return std::isfinite(out->inv_dx) && std::isfinite(out->inv_dy) && std::isfinite(out->px) && std::isfinite(out->py);
+}
+
+bool detect_grids(const float* c, const float* area, size_t A, std::vector<ssdx_grid_combo>& combos,
+                  std::vector<ssdx_grid_span>& spans) {
+  combos.clear();
+  spans.clear();
+  for (size_t i = 0; i < 4 * A; ++i)
+    if (!std::isfinite(c[i])) return false;
+  size_t off = 0;
+  while (off < A) {
+    const size_t rem = A - off;
+    bool found = false;
+    for (int nb = 1; nb <= 64 && (size_t)nb <= rem && !found; ++nb) {
+      int W = 0, H = 0;
+      if ((size_t)nb == rem) {
+        W = 1; H = 1;  // one cell at the end of the table (a 1 x 1 feature map)
+      } else if (same_y(c, off, off + nb)) {  // next column
+        for (size_t col = 2; col * nb <= rem; ++col) {
+          const size_t i = off + col * nb;
+          if (i == A) { W = (int)col; H = 1; break; }                        // one-row map ends the table
+          if (!same_y(c, off, i)) { W = (int)col; if (!same_x(c, off, i)) H = 1; break; }  // next row, or next map
+          if (col > 65535) break;
+        }
+      } else if (same_x(c, off, off + nb)) {
+        W = 1;  // one column: the next cell is the next row
+      }
+      if (W == 0 || (size_t)W * nb > 16384) continue;
+      const size_t L = (size_t)W * nb;
+      if (H == 0) {
+        H = 1;
+        while (off + (size_t)(H + 1) * L <= A && H < 32767 && rows_ok(c, off, H, H + 1, W, nb)) ++H;
+      }
+      if (!rows_ok(c, off, 0, 1, W, nb)) continue;  // row 0 itself: one y extent per shape
+      const GridMap m{off, H, W, nb};
+      std::vector<ssdx_grid_combo> mine(nb);
+      bool ok = combos.size() + nb <= (size_t)kSsdxMaxCombos;
+      for (int k = 0; k < nb && ok; ++k) ok = make_combo(c, area, m, k, &mine[k]);
+      if (!ok) continue;
+      const int combo0 = (int)combos.size();
+      combos.insert(combos.end(), mine.begin(), mine.end());
+      const int rps = std::max(1, (int)(kSsdxSpanAnchors / L));
+      for (int r = 0; r < H; r += rps) {
+        ssdx_grid_span s;
+        s.row0 = r; s.nrows = std::min(rps, H - r);
+        s.a_lo = (int)(off + (size_t)r * L); s.n = (int)((size_t)s.nrows * L);
+        s.combo0 = combo0; s.nb = nb; s.pad0 = s.pad1 = 0;
+        spans.push_back(s);
+      }
+      off += (size_t)H * L;
+      found = true;
+    }
+    if (!found) { combos.clear(); spans.clear(); return false; }
+  }
+  return !combos.empty();
+}
+
+}  // namespace
+
 extern "C" {
 
 int ssdx_version(void) { return SSDX_VERSION; }
 
 const char* ssdx_last_error(void) { return g_err; }
+
+int ssdx_set_option(const char* key, const char* value) {
+  SSDX_CHECK_ARG(key != nullptr && value != nullptr, "ssdx_set_option: NULL argument");
+  if (strcmp(key, "encode_path") == 0) {
+    static const char* const v[5] = {"auto", "tile_fused", "tile_tiled", "grid_fused", "grid_split"};
+    for (int i = 0; i < 5; ++i)
+      if (strcmp(value, v[i]) == 0) {
+        g_encode_path.store(i);
+        return SSDX_OK;
+      }
+  } else if (strcmp(key, "nms_path") == 0) {
+    static const char* const v[4] = {"auto", "perclass", "pcta", "generic"};
+    for (int i = 0; i < 4; ++i)
+      if (strcmp(value, v[i]) == 0) {
+        g_nms_path.store(i);
+        return SSDX_OK;
+      }
+  } else {
+    ssdx_set_error("ssdx_set_option: unknown key '%s'", key);
+    return SSDX_ERR_INVALID;
+  }
+  ssdx_set_error("ssdx_set_option: bad value '%s' for '%s'", value, key);
+  return SSDX_ERR_INVALID;
+}
 
 int ssdx_device_count(int* count) {
   SSDX_CHECK_ARG(count != nullptr, "ssdx_device_count: count is NULL");
@@ -57,7 +232,7 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
   *out = nullptr;
   SSDX_CHECK_ARG(corners_xyxy_host != nullptr, "you must pass all default bounding boxes corners coordinates!");
   SSDX_CHECK_ARG(num_anchors > 0, "ssdx_anchors_create: num_anchors must be > 0 (got %d)", num_anchors);
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   const size_t A = (size_t)num_anchors;
   std::vector<float> area(A), enc(4 * A), dec(4 * A);
   for (size_t a = 0; a < A; ++a) {
@@ -140,16 +315,36 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
     t_area[2 * t + 0] = amin; t_area[2 * t + 1] = amax;
   }
 
+  std::vector<ssdx_grid_combo> combos;
+  std::vector<ssdx_grid_span> spans;
+  detect_grids(corners_xyxy_host, area.data(), A, combos, spans);
+  const size_t nq = combos.size(), ns = spans.size();
+
   ssdx_anchors* h = (ssdx_anchors*)calloc(1, sizeof(ssdx_anchors));
-  SSDX_CHECK_ARG(h != nullptr, "ssdx_anchors_create: out of host memory");
+  ssdx_grid_combo* combos_host = nq ? (ssdx_grid_combo*)malloc(nq * sizeof(ssdx_grid_combo)) : nullptr;
+  if (h == nullptr || (nq && combos_host == nullptr)) {
+    free(h);
+    free(combos_host);
+    ssdx_set_error("ssdx_anchors_create: out of host memory");
+    return SSDX_ERR_INVALID;
+  }
   h->device = device;
   h->A = num_anchors;
   h->n_tiles = (int32_t)n_tiles;
+  h->n_combos = (int32_t)nq;
+  h->n_spans = (int32_t)ns;
+  h->combos_host = combos_host;
+  for (size_t i = 0; i < nq; ++i) combos_host[i] = combos[i];
+  for (size_t i = 0; i < ns; ++i) {
+    h->max_span_anchors = std::max(h->max_span_anchors, (int32_t)spans[i].n);
+    h->max_span_combos = std::max(h->max_span_combos, (int32_t)spans[i].nb);
+  }
   cudaError_t e = cudaSuccess;
-  // one allocation: corners | enc_cent | dec_cent | m_box | t_bbox | t_area | area | m_area | m_idx
+  // one allocation: corners | enc_cent | dec_cent | m_box | t_bbox | t_area | area | m_area | m_idx | combos | spans
   char* base = nullptr;
   const size_t bytes = A * (3 * sizeof(float4) + sizeof(float)) + Ap * (sizeof(float4) + sizeof(float) + sizeof(int)) +
-                       n_tiles * (sizeof(float4) + sizeof(float2));
+                       n_tiles * (sizeof(float4) + sizeof(float2)) + 64 + nq * sizeof(ssdx_grid_combo) +
+                       ns * sizeof(ssdx_grid_span);
   e = cudaMalloc((void**)&base, bytes);
   if (e == cudaSuccess) {
     h->corners = (float4*)base;
@@ -161,6 +356,8 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
     h->area = (float*)(h->t_area + n_tiles);
     h->m_area = h->area + A;
     h->m_idx = (int*)(h->m_area + Ap);
+    h->combos = (ssdx_grid_combo*)ssdx_align_up((size_t)(h->m_idx + Ap), 32);
+    h->spans = (ssdx_grid_span*)(h->combos + nq);
     e = cudaMemcpy(h->corners, corners_xyxy_host, A * sizeof(float4), cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) e = cudaMemcpy(h->enc_cent, enc.data(), A * sizeof(float4), cudaMemcpyHostToDevice);
@@ -171,9 +368,14 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
   if (e == cudaSuccess) e = cudaMemcpy(h->m_idx, m_idx.data(), Ap * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->t_bbox, t_bbox.data(), n_tiles * sizeof(float4), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->t_area, t_area.data(), n_tiles * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nq)
+    e = cudaMemcpy(h->combos, combos.data(), nq * sizeof(ssdx_grid_combo), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && ns)
+    e = cudaMemcpy(h->spans, spans.data(), ns * sizeof(ssdx_grid_span), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     ssdx_set_error("ssdx_anchors_create: CUDA error: %s", cudaGetErrorString(e));
     if (base) cudaFree(base);
+    free(combos_host);
     free(h);
     return SSDX_ERR_CUDA;
   }
@@ -183,9 +385,83 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
 
 int ssdx_anchors_destroy(ssdx_anchors* anchors) {
   if (anchors == nullptr) return SSDX_OK;
-  cudaSetDevice(anchors->device);
-  if (anchors->corners) cudaFree(anchors->corners);
+  {
+    // at interpreter teardown the context may already be gone: errors are ignored on purpose
+    ssdx_device_guard guard(anchors->device);
+    if (guard.err == cudaSuccess && anchors->corners) cudaFree(anchors->corners);
+    (void)cudaGetLastError();
+  }
+  free(anchors->combos_host);
   free(anchors);
+  return SSDX_OK;
+}
+
+/* Host-only probe of the grid detection (no device needed): what ssdx_anchors_create would find for this table. */
+int ssdx_grid_probe(const float* corners_xyxy_host, int32_t num_anchors, int32_t* num_grids, int32_t* num_spans,
+                    int32_t* grids_out, int32_t capacity) {
+  SSDX_CHECK_ARG(corners_xyxy_host != nullptr && num_anchors > 0, "ssdx_grid_probe: bad anchor table");
+  const size_t A = (size_t)num_anchors;
+  std::vector<float> area(A);
+  for (size_t a = 0; a < A; ++a) {
+    volatile float hh = corners_xyxy_host[4 * a + 3] - corners_xyxy_host[4 * a + 1];
+    volatile float ww = corners_xyxy_host[4 * a + 2] - corners_xyxy_host[4 * a + 0];
+    hh = hh + 1.0f;
+    ww = ww + 1.0f;
+    volatile float ar = hh * ww;
+    area[a] = ar;
+  }
+  std::vector<ssdx_grid_combo> combos;
+  std::vector<ssdx_grid_span> spans;
+  detect_grids(corners_xyxy_host, area.data(), A, combos, spans);
+  if (num_grids) *num_grids = (int32_t)combos.size();
+  if (num_spans) *num_spans = (int32_t)spans.size();
+  if (grids_out)
+    for (size_t i = 0; i < combos.size() && (int32_t)i < capacity; ++i) {
+      grids_out[4 * i + 0] = combos[i].off;
+      grids_out[4 * i + 1] = combos[i].H;
+      grids_out[4 * i + 2] = combos[i].W;
+      grids_out[4 * i + 3] = combos[i].nb;
+    }
+  return SSDX_OK;
+}
+
+/* Host-only: the window ssdx_encode's grid drivers would enumerate for every (GT box, grid) of this table at the IoU
+ * bounds t[i]; out (n_boxes, num_grids, 4) = (first row, rows, first column, columns), rows = 0 for an empty window. */
+int ssdx_grid_window_probe(const float* corners_xyxy_host, int32_t num_anchors, const float* gt_xyxy_host,
+                           const float* t_host, int32_t n_boxes, int32_t* out) {
+  SSDX_CHECK_ARG(corners_xyxy_host && gt_xyxy_host && t_host && out && num_anchors > 0 && n_boxes >= 0,
+                 "ssdx_grid_window_probe: bad argument");
+  const size_t A = (size_t)num_anchors;
+  std::vector<float> area(A);
+  for (size_t a = 0; a < A; ++a) {
+    volatile float hh = corners_xyxy_host[4 * a + 3] - corners_xyxy_host[4 * a + 1];
+    volatile float ww = corners_xyxy_host[4 * a + 2] - corners_xyxy_host[4 * a + 0];
+    hh = hh + 1.0f;
+    ww = ww + 1.0f;
+    volatile float ar = hh * ww;
+    area[a] = ar;
+  }
+  std::vector<ssdx_grid_combo> combos;
+  std::vector<ssdx_grid_span> spans;
+  detect_grids(corners_xyxy_host, area.data(), A, combos, spans);
+  for (int32_t i = 0; i < n_boxes; ++i)
+    for (size_t q = 0; q < combos.size(); ++q) {
+      float4 gb;
+      gb.x = gt_xyxy_host[4 * i + 0]; gb.y = gt_xyxy_host[4 * i + 1];
+      gb.z = gt_xyxy_host[4 * i + 2]; gb.w = gt_xyxy_host[4 * i + 3];
+      ssdx_grid_rect r{0, 0, 0, 0};
+      if (!ssdx_grid_window(combos[q], gb, t_host[i], 0, combos[q].H, r)) r = ssdx_grid_rect{0, 0, 0, 0};
+      int32_t* o = out + ((size_t)i * combos.size() + q) * 4;
+      o[0] = r.r0; o[1] = r.nr; o[2] = r.c0; o[3] = r.nc;
+    }
+  return SSDX_OK;
+}
+
+/* 1 when the anchor table was recognised as a union of regular grids (encode then uses closed-form windows). */
+int ssdx_anchors_grid_info(const ssdx_anchors* anchors, int32_t* num_grids, int32_t* num_spans) {
+  SSDX_CHECK_ARG(anchors != nullptr, "ssdx_anchors_grid_info: anchors is NULL");
+  if (num_grids) *num_grids = anchors->n_combos;
+  if (num_spans) *num_spans = anchors->n_spans;
   return SSDX_OK;
 }
 

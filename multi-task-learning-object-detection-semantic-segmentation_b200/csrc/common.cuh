@@ -7,6 +7,26 @@
 
 #include "ssdx.h"
 
+// One (feature map, box shape) grid of the anchor table: anchor(row, col) = off + (row * W + col) * nb, x extents a
+// function of the column only, y extents of the row only (verified bit for bit at creation).  The centre model
+// cx(col) ~ cx0 + col / inv_dx, cy(row) ~ cy0 + row / inv_dy and the half extents hx, hy only have to be right up to
+// the pads px, py, which hold the measured deviation of the table from the model plus a rounding margin: they size
+// the windows of encode_grid.cu, the IoU itself is always evaluated on the table.
+struct ssdx_grid_combo {
+  int off, H, W, nb;
+  float cx0, inv_dx, cy0, inv_dy;
+  float hx, hy;      // upper bounds of (x1 - x0) / 2, (y1 - y0) / 2
+  float px, py;      // pads on the centre range
+  float aw, ah;      // upper bounds of the +1 width / height (datacoder.py:143-144)
+  float amin, amax;  // smallest / largest anchor area (datacoder.py:111-114) in the grid
+};
+// A row range of one feature map: anchors [a_lo, a_lo + n), rows [row0, row0 + nrows) of combos [combo0, combo0 + nb)
+struct ssdx_grid_span {
+  int a_lo, n, combo0, nb, row0, nrows, pad0, pad1;
+};
+constexpr int kSsdxSpanAnchors = 4096;
+constexpr int kSsdxMaxCombos = 256;
+
 // device-resident anchor table (immutable after ssdx_anchors_create)
 struct ssdx_anchors {
   int device;
@@ -24,6 +44,16 @@ struct ssdx_anchors {
   int* m_idx;      // (n_tiles*kSsdxTile) original anchor index, -1 for padding
   float4* t_bbox;  // (n_tiles) bounding box of the tile's anchors
   float2* t_area;  // (n_tiles) (min, max) anchor area in the tile
+  // Grid description (encode_grid.cu), present when the table is a union of regular grids - every output of
+  // boxes.DefaultBoundingBoxes is (boxes.py:112-146): per feature map and box shape the x extents depend only on the
+  // column and the y extents only on the row.  n_combos == 0: not a grid, the tile match above is used.
+  int32_t n_combos;
+  ssdx_grid_combo* combos;       // device (n_combos)
+  ssdx_grid_combo* combos_host;  // host copy
+  int32_t n_spans;
+  ssdx_grid_span* spans;         // device (n_spans): row ranges of one map, at most kSsdxSpanAnchors anchors each
+  int32_t max_span_anchors;      // largest span
+  int32_t max_span_combos;       // largest number of shapes of a map
 };
 
 #ifndef SSDX_APT
@@ -51,6 +81,29 @@ void ssdx_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
+// Every entry point runs on the device its handle / `device` argument names and leaves the calling thread's current
+// device as it found it (a process may drive several GPUs from one thread).
+struct ssdx_device_guard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t err = cudaSuccess;
+  explicit ssdx_device_guard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) {
+      err = cudaSetDevice(device);
+      changed = (err == cudaSuccess);
+    }
+  }
+  ~ssdx_device_guard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  ssdx_device_guard(const ssdx_device_guard&) = delete;
+  ssdx_device_guard& operator=(const ssdx_device_guard&) = delete;
+};
+#define SSDX_DEVICE(device)            \
+  ssdx_device_guard dev_guard__(device); \
+  SSDX_CUDA(dev_guard__.err)
+
 // SSDX_DEBUG_SYNC=1 in the environment makes every launch synchronous so a device fault names its kernel
 bool ssdx_debug_sync();
 
@@ -65,6 +118,12 @@ bool ssdx_debug_sync();
   } while (0)
 
 static inline size_t ssdx_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Process-level dispatch overrides (ssdx_set_option; default "auto").  All paths of one entry point give identical
+// results - the options exist so that tests and tuning runs can pin one.
+enum { SSDX_ENC_AUTO = 0, SSDX_ENC_TILE_FUSED, SSDX_ENC_TILE_TILED, SSDX_ENC_GRID_FUSED, SSDX_ENC_GRID_SPLIT };
+int ssdx_option_encode_path();
+const char* ssdx_option_nms_path();  // NULL (auto) | "perclass" | "pcta" | "generic"
 
 // number of SMs of a device (cached per device)
 int ssdx_sm_count(int device);

@@ -79,7 +79,7 @@ extern "C" int ssdx_decode(const ssdx_anchors* anchors, const float* offsets, in
   SSDX_CHECK_ARG(((uintptr_t)offsets & 15) == 0 && ((uintptr_t)out & 15) == 0,
                  "ssdx_decode: offsets/out must be 16-byte aligned");
   if (batch == 0) return SSDX_OK;
-  SSDX_CUDA(cudaSetDevice(anchors->device));
+  SSDX_DEVICE(anchors->device);
   const int A = anchors->A;
   const int gx = (A + kThreads * kUnroll - 1) / (kThreads * kUnroll);
   // ~16 resident CTAs per SM; every CTA walks >= 1 image

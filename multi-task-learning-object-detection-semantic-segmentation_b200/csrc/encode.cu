@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "encode_common.cuh"
 
 #ifdef SSDX_PHASE_TIMERS
 static __device__ unsigned long long g_phase_cycles[32];
@@ -43,6 +44,8 @@ extern "C" __attribute__((visibility("default"))) int ssdx_debug_phase_cycles_en
 #endif
 
 namespace {
+
+using namespace ssdx_enc;
 
 constexpr int kApt = kSsdxApt;      // anchors per lane per tile
 #ifndef SSDX_ENC_THREADS
@@ -61,25 +64,9 @@ constexpr int kGtTile = 256;        // GT boxes staged per shared-memory tile (t
 constexpr int kEmitThreads = 256;
 constexpr int kEmitSpan = 8;  // chunks of kEmitThreads anchors per emit CTA
 constexpr int kEmitAnchors = kEmitSpan * kEmitThreads;
-constexpr int kFusedMaxG = 256;
 constexpr int kPosCap = 1024;   // compacted positives per image (more are encoded in place)
 constexpr int kBgRows = SSDX_ENC_BGROWS;  // background rows per bulk store (offsets: 16 B per row)
 constexpr float kSlackUp = 1.0001f, kSlackDown = 0.9999f;
-constexpr unsigned kFull = 0xFFFFFFFFu;
-
-typedef unsigned long long u64;
-
-// packed (iou bits, inverted anchor index): larger = better IoU, ties -> lower anchor index
-__device__ __forceinline__ u64 pack_best(unsigned iou_bits, int a) {
-  return ((u64)iou_bits << 32) | (u64)(0xFFFFFFFFu - (unsigned)a);
-}
-__device__ __forceinline__ int best_anchor(u64 p) { return (int)(0xFFFFFFFFu - (unsigned)(p & 0xFFFFFFFFull)); }
-__device__ __forceinline__ unsigned best_bits(const u64* p) { return reinterpret_cast<const unsigned*>(p)[1]; }
-
-__device__ __forceinline__ float gt_area(const float4 b) {
-  // datacoder.py:206  (xmax-xmin+1)*(ymax-ymin+1)
-  return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
-}
 
 struct AnchorTile {
   float4 box[kApt];
@@ -245,31 +232,6 @@ __device__ __forceinline__ void seed_gt_best(const float4* __restrict__ m_box, c
   const int amin = __reduce_min_sync(kFull, (mvb == mbits) ? ma : 0x7FFFFFFF);
   if (lane == 0) atomicMax(s_best_g, pack_best(mbits, amin));
 }
-
-// datacoder.py:251-269 for one matched pair
-__device__ __forceinline__ float4 pair_offsets(const float4 gb, const float4 d, float sx, float sy, float sw,
-                                               float sh) {
-  const float gcx = __fmul_rn(__fadd_rn(gb.z, gb.x), 0.5f);
-  const float gcy = __fmul_rn(__fadd_rn(gb.w, gb.y), 0.5f);
-  const float gw = __fadd_rn(__fsub_rn(gb.z, gb.x), 1.0f);
-  const float gh = __fadd_rn(__fsub_rn(gb.w, gb.y), 1.0f);
-  float4 off;  // two successive divisions; +1.0 inside the log
-  off.x = __fdiv_rn(__fdiv_rn(__fsub_rn(gcx, d.x), d.z), sx);
-  off.y = __fdiv_rn(__fdiv_rn(__fsub_rn(gcy, d.y), d.w), sy);
-  off.z = __fdiv_rn(logf(__fadd_rn(__fdiv_rn(gw, d.z), 1.0f)), sw);
-  off.w = __fdiv_rn(logf(__fadd_rn(__fdiv_rn(gh, d.w), 1.0f)), sh);
-  return off;
-}
-
-// ---- TMA bulk store (shared -> global), one bulk group per issuing thread ----
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
-               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ fused driver
 __host__ __device__ inline int fused_label_rows(int C) {  // rows per constant label block (multiple of 4)
@@ -674,12 +636,11 @@ __global__ void __launch_bounds__(kEmitThreads)
   }
 }
 
-inline bool use_fused(int A, int gmax, int C, int batch, int sms) {
+inline bool use_fused(int A, int gmax, int C, int batch, int sms, int opt) {
   // one CTA per image needs enough images to fill the GPU, and A/G small enough for shared memory
   const bool fits = gmax <= kFusedMaxG && A <= 32768 && fused_smem_bytes(A, gmax, C) <= 100 * 1024;
-  const char* force = getenv("SSDX_ENCODE_PATH");  // "fused" | "tiled": test hook, both paths are bit-identical
-  if (force != nullptr && force[0] == 't') return false;
-  if (force != nullptr && force[0] == 'f') return fits;
+  if (opt == SSDX_ENC_TILE_TILED) return false;
+  if (opt == SSDX_ENC_TILE_FUSED) return fits;
   return fits && batch >= sms;
 }
 
@@ -715,11 +676,21 @@ extern "C" int ssdx_encode(const ssdx_anchors* anchors, const float* gt_xyxy, co
     return SSDX_ERR_WORKSPACE;
   }
   SSDX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "ssdx_encode: workspace must be 256-byte aligned");
-  SSDX_CUDA(cudaSetDevice(anchors->device));
+  SSDX_DEVICE(anchors->device);
   cudaStream_t s = (cudaStream_t)stream;
   const int gm = gmax > 0 ? gmax : 1;
 
-  if (use_fused(A, gmax, num_classes, batch, ssdx_sm_count(anchors->device))) {
+  const int opt = ssdx_option_encode_path();  // ssdx_set_option("encode_path", ...): every path gives the same bits
+  const int sms = ssdx_sm_count(anchors->device);
+  if (opt != SSDX_ENC_TILE_FUSED && opt != SSDX_ENC_TILE_TILED &&
+      ssdx_encode_grid_applies(anchors, gmax, num_classes, iou_threshold)) {
+    // the anchor table is a union of regular grids (every DefaultBoundingBoxes output): closed-form windows
+    const bool fits = ssdx_encode_grid_fused_fits(anchors, gmax, num_classes);
+    const bool fused = fits && (opt == SSDX_ENC_GRID_FUSED || (opt != SSDX_ENC_GRID_SPLIT && batch >= sms));
+    return ssdx_encode_grid_launch(anchors, fused, gt_xyxy, gt_label, gt_count, batch, gmax, num_classes,
+                                   iou_threshold, std_host, out_labels, out_offsets, out_match, workspace, s);
+  }
+  if (use_fused(A, gmax, num_classes, batch, sms, opt)) {
     const size_t smem = fused_smem_bytes(A, gmax, num_classes);
     SSDX_CUDA(cudaFuncSetAttribute(ssdx_encode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ssdx_encode_fused_kernel<<<batch, kFusedThreads, smem, s>>>(

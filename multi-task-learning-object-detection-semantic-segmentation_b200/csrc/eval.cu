@@ -155,7 +155,7 @@ extern "C" int ssdx_iou_pred_vs_true(const int32_t* pred_label, const float* pre
   SSDX_CHECK_ARG(pred_label && pred_xyxy && gt_label && gt_xyxy && out, "ssdx_iou_pred_vs_true: NULL pointer");
   SSDX_CHECK_ARG(((uintptr_t)pred_xyxy & 15) == 0 && ((uintptr_t)gt_xyxy & 15) == 0,
                  "ssdx_iou_pred_vs_true: box arrays must be 16-byte aligned");
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   const size_t n = (size_t)num_pred * num_gt;
   int blocks = (int)((n + 255) / 256);
   const int cap = ssdx_sm_count(device) * 8;
@@ -177,7 +177,7 @@ extern "C" int ssdx_eval_tp(const int32_t* pred_label, const float* pred_xyxy, c
   SSDX_CHECK_ARG(((uintptr_t)pred_xyxy & 15) == 0 && ((uintptr_t)gt_xyxy & 15) == 0,
                  "ssdx_eval_tp: box arrays must be 16-byte aligned");
   if (batch == 0) return SSDX_OK;
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   const int per = kEvalThreads / 32;
   const int smem_counts = num_classes <= 2048;  // 24 KB of CTA-local counters at most
   const long long tasks = (long long)batch * (k > 0 ? (k + 31) / 32 : 1);

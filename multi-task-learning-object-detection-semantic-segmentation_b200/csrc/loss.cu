@@ -517,7 +517,7 @@ extern "C" int ssdx_localization_loss(const float* y_true, const float* y_pred, 
   SSDX_CHECK_ARG(((uintptr_t)y_true & 15) == 0 && ((uintptr_t)y_pred & 15) == 0 && ((uintptr_t)out_grad & 15) == 0,
                  "ssdx_localization_loss: y_true / y_pred / out_grad must be 16-byte aligned");
   if (batch == 0) return SSDX_OK;
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   ssdx_localization_loss_kernel<<<batch, kLossThreads, 0, (cudaStream_t)stream>>>(
       (const float4*)y_true, (const float4*)y_pred, num_anchors, out_loss, (float4*)out_grad);
   SSDX_LAUNCH_CHECK("ssdx_localization_loss_kernel");
@@ -547,7 +547,7 @@ extern "C" int ssdx_confidence_loss(const float* y_true, const float* y_pred, in
   SSDX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "ssdx_confidence_loss: workspace must be 256-byte aligned");
   const bool vec4 = num_classes == 4 && ((uintptr_t)y_true & 15) == 0 && ((uintptr_t)y_pred & 15) == 0 &&
                     ((uintptr_t)out_grad & 15) == 0;
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   cudaStream_t s = (cudaStream_t)stream;
   char* base = (char*)workspace;
   ConfState* st = (ConfState*)(base + w.state);

@@ -93,7 +93,7 @@ extern "C" int ssdx_metric_iou_boxes(const ssdx_anchors* anchors, const float* y
   SSDX_CHECK_ARG(((uintptr_t)y_true & 15) == 0 && ((uintptr_t)y_pred & 15) == 0,
                  "ssdx_metric_iou_boxes: y_true / y_pred must be 16-byte aligned");
   if (batch == 0) return SSDX_OK;
-  SSDX_CUDA(cudaSetDevice(anchors->device));
+  SSDX_DEVICE(anchors->device);
   ssdx_metric_iou_boxes_kernel<<<batch, kMetricThreads, 0, (cudaStream_t)stream>>>(
       anchors->dec_cent, (const float4*)y_true, (const float4*)y_pred, anchors->A, std_host[0], std_host[1],
       std_host[2], std_host[3], out);

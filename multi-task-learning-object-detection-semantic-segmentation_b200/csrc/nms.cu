@@ -1681,9 +1681,9 @@ extern "C" int ssdx_nms(const float* boxes_yxyx, const float* scores, int32_t ba
                          device, stream);
 }
 
-// the merged one-pass-per-image pipeline applies (SSDX_NMS_PATH = generic | perclass force the other paths: test hooks)
+// the merged one-pass-per-image pipeline applies (ssdx_set_option("nms_path", generic | perclass) forces the other paths)
 static bool nms_merged_applies(const int A, const int C, const int max_per_class, const int max_total) {
-  const char* force = getenv("SSDX_NMS_PATH");
+  const char* force = ssdx_option_nms_path();
   if (force != nullptr && (force[0] == 'g' || force[0] == 'p')) return false;
   return max_per_class >= max_total && C <= 256 && A <= (1 << 24) && (long long)A * C < (1ll << 31) &&
          max_total <= kFastMaxSel;
@@ -1695,7 +1695,7 @@ static bool nms_logits_fusable(const int A, const int C, const int max_per_class
                                const float* logits) {
   if (C != 4 || (((uintptr_t)logits & 15) != 0)) return false;
   if (nms_merged_applies(A, C, max_per_class, max_total)) return true;
-  const char* force = getenv("SSDX_NMS_PATH");
+  const char* force = ssdx_option_nms_path();
   if (force != nullptr && (force[0] == 'g' || (force[0] == 'p' && force[1] == 'c'))) return false;
   return (max_per_class < A ? max_per_class : A) <= 32;
 }
@@ -1733,7 +1733,7 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   SSDX_CHECK_ARG(gen_smem <= 227 * 1024,
                  "ssdx_nms: num_anchors=%d with max_per_class=%d needs %zu B of shared memory (limit 232448)", A,
                  max_per_class, gen_smem);
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   cudaStream_t s = (cudaStream_t)stream;
   char* base = (char*)workspace;
   u64* picks = (u64*)(base + w.picks);
@@ -1748,7 +1748,7 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   const bool vec4 = (C == 4) && (((uintptr_t)scores & 15) == 0);
   // test hooks: "generic" = exact generic kernel alone, "perclass" = per-class fast pipeline even when the merged
   // one applies.  All paths give identical results.
-  const char* force = getenv("SSDX_NMS_PATH");
+  const char* force = ssdx_option_nms_path();
   const bool force_generic = force != nullptr && force[0] == 'g';
   const size_t gen_smem_attr = gen_smem;
   SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1817,7 +1817,7 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
     SSDX_LAUNCH_CHECK("ssdx_nms_select_kernel");
   }
   if (!ph2) return SSDX_OK;
-  const char* force_path = getenv("SSDX_NMS_PATH");
+  const char* force_path = ssdx_option_nms_path();
   const bool no_warp = force_path != nullptr && force_path[0] == 'p' && force_path[1] == 'c';  // "pcta": test hook
   if (use_fast && limit <= 32 && !no_warp) {
     // 2w. one warp per segment, never hands over: select -> warp -> merge

@@ -161,7 +161,7 @@ extern "C" int ssdx_softmax_scores(const float* logits, int64_t rows, int32_t nu
   SSDX_CHECK_ARG(logits != nullptr && out != nullptr, "ssdx_softmax_scores: NULL pointer argument");
   SSDX_CHECK_ARG(rows >= 0 && num_classes >= 1, "ssdx_softmax_scores: bad shape");
   if (rows == 0) return SSDX_OK;
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   cudaStream_t s = (cudaStream_t)stream;
   const int sms = ssdx_sm_count(device);
   const bool vec4 = num_classes == 4 && (((uintptr_t)logits | (uintptr_t)out) & 15) == 0;
@@ -189,7 +189,7 @@ extern "C" int ssdx_seg_class_presence(const float* seg_probs, int64_t num_pixel
     return SSDX_ERR_WORKSPACE;
   }
   SSDX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "ssdx_seg_class_presence: workspace must be 256-byte aligned");
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   cudaStream_t s = (cudaStream_t)stream;
   SSDX_CUDA(cudaMemsetAsync(workspace, 0, 8, s));
   const int sms = ssdx_sm_count(device);
@@ -207,7 +207,7 @@ extern "C" int ssdx_scale_scores(const float* scores, int64_t rows, int32_t num_
   SSDX_CHECK_ARG(scores != nullptr && class_scale != nullptr && out != nullptr, "ssdx_scale_scores: NULL pointer argument");
   SSDX_CHECK_ARG(rows >= 0 && num_classes >= 1, "ssdx_scale_scores: bad shape");
   if (rows == 0) return SSDX_OK;
-  SSDX_CUDA(cudaSetDevice(device));
+  SSDX_DEVICE(device);
   cudaStream_t s = (cudaStream_t)stream;
   const int sms = ssdx_sm_count(device);
   const bool vec4 = num_classes == 4 && (((uintptr_t)scores | (uintptr_t)out) & 15) == 0;

@@ -37,6 +37,10 @@ SIGNATURES = {
     "ssdx_anchors_destroy": (C.c_int, [_vp]),
     "ssdx_anchors_count": (C.c_int, [_vp, c_i32_p]),
     "ssdx_anchors_device": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "ssdx_anchors_grid_info": (C.c_int, [_vp, c_i32_p, c_i32_p]),
+    "ssdx_set_option": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "ssdx_grid_probe": (C.c_int, [c_float_p, C.c_int32, c_i32_p, c_i32_p, c_i32_p, C.c_int32]),
+    "ssdx_grid_window_probe": (C.c_int, [c_float_p, C.c_int32, c_float_p, c_float_p, C.c_int32, c_i32_p]),
     "ssdx_encode_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "ssdx_encode": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, c_float_p, _vp, _vp,
                               _vp, _vp, C.c_size_t, _vp]),
@@ -98,6 +102,36 @@ def check(status: int) -> None:
 
 def version() -> int:
     return lib.ssdx_version()
+
+
+def grid_probe(corners_xyxy: np.ndarray) -> np.ndarray:
+    """Host-only: the (first anchor, rows, columns, shapes) rows of the regular grids ssdx_anchors_create finds in an
+    (A,4) anchor table, shape (0,4) when the table is not a union of grids (encode then uses the tile match)."""
+    c = np.ascontiguousarray(corners_xyxy, dtype=np.float32).reshape(-1, 4)
+    n, ns = C.c_int32(0), C.c_int32(0)
+    out = np.zeros((256, 4), np.int32)
+    check(lib.ssdx_grid_probe(c.ctypes.data_as(c_float_p), c.shape[0], C.byref(n), C.byref(ns),
+                              out.ctypes.data_as(c_i32_p), 256))
+    return out[: n.value].copy()
+
+
+def grid_windows(corners_xyxy: np.ndarray, gt_xyxy: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """Host-only: (n_boxes, num_grids, 4) = (first row, rows, first column, columns) of the cell windows the grid
+    encode drivers enumerate for the IoU bounds t (the same code the kernels run, compiled for the host)."""
+    c = np.ascontiguousarray(corners_xyxy, dtype=np.float32).reshape(-1, 4)
+    g = np.ascontiguousarray(gt_xyxy, dtype=np.float32).reshape(-1, 4)
+    tt = np.ascontiguousarray(t, dtype=np.float32).reshape(-1)
+    nq = len(grid_probe(c))
+    out = np.zeros((g.shape[0], nq, 4), np.int32)
+    check(lib.ssdx_grid_window_probe(c.ctypes.data_as(c_float_p), c.shape[0], g.ctypes.data_as(c_float_p),
+                                     tt.ctypes.data_as(c_float_p), g.shape[0], out.ctypes.data_as(c_i32_p)))
+    return out
+
+
+def set_option(key: str, value: str) -> None:
+    """Process-level dispatch override (include/ssdx.h: ssdx_set_option), e.g. ("encode_path", "tile_fused").
+    Every path of an entry point gives identical results; tests and tuning runs pin one."""
+    check(lib.ssdx_set_option(key.encode(), value.encode()))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -239,3 +239,99 @@ def test_all_gather_counts_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------------------- grid detection and windows (host)
+def _windows_cover(ssdseglib, anchors, boxes, t):
+    """Every pair with IoU >= t (and > 0) lies inside the window of its (GT box, grid); returns the cell count."""
+    grids = ssdseglib._ssdx.grid_probe(anchors)
+    assert len(grids) > 0
+    win = ssdseglib._ssdx.grid_windows(anchors, boxes, t)
+    iou = orc.iou_matrix(anchors, boxes)
+    covered = np.zeros(iou.shape, bool)
+    cells = 0
+    for g in range(boxes.shape[0]):
+        for q, (first, H, W, nb) in enumerate(grids):
+            r0, nr, c0, nc = win[g, q]
+            if nr == 0:
+                continue
+            assert 0 <= r0 and r0 + nr <= H and 0 <= c0 and c0 + nc <= W
+            rr, cc = np.meshgrid(np.arange(r0, r0 + nr), np.arange(c0, c0 + nc), indexing="ij")
+            covered[(first + (rr * W + cc) * nb).ravel(), g] = True
+            cells += nr * nc
+    need = (iou >= t[None, :]) & (iou > 0)
+    assert not (need & ~covered).any(), np.argwhere(need & ~covered)[:5]
+    return cells, int(need.sum())
+
+
+def test_grid_detection_on_reference_tables(ssdseglib, std_anchors):
+    probe = ssdseglib._ssdx.grid_probe
+    g = probe(std_anchors)  # notebook-03 table: 4 maps x 6 shapes (boxes.py:198-205 order)
+    assert len(g) == 24 and g[0].tolist() == [0, 30, 40, 6] and g[6].tolist() == [7200, 15, 20, 6]
+    assert g[18].tolist() == [9480, 4, 5, 6] and g[23].tolist() == [9485, 4, 5, 6]
+    g = probe(orc.anchors_generate(**orc.STRESS_ANCHOR_CFG))
+    assert [r.tolist() for r in g] == [[k, 125, 160, 5] for k in range(5)]
+    # the table as the centroid constructor derives it (datacoder.py:84-89) keeps the structure
+    cx, cy, w, h = orc.corners_to_centroids(*[std_anchors[:, i] for i in range(4)])
+    assert len(probe(np.stack(orc.centroids_to_corners(cx, cy, w, h), 1).astype(np.float32))) == 24
+    # anything else is not a grid: subsets, permutations, a perturbed coordinate, random boxes
+    rng = np.random.default_rng(0)
+    assert len(probe(std_anchors[rng.permutation(9600)[:700]])) == 0
+    assert len(probe(std_anchors[::-1])) == 0
+    bad = std_anchors.copy()  # one perturbed coordinate in row 18 of map 0: rows 0-17 | row 18 | rows 19-29 | maps 1-3
+    bad[4321, 0] = np.nextafter(bad[4321, 0], np.float32(1e9))
+    g = probe(bad)
+    assert len(g) == 36 and g[0].tolist() == [0, 18, 40, 6] and g[6].tolist() == [4320, 1, 40, 6]
+    assert g[12].tolist() == [4560, 11, 40, 6]
+    _windows_cover(ssdseglib, bad, orc.synth_gt(rng, 1, 16)[1][0], np.full(16, 0.4, np.float32))
+    assert len(probe(rng.uniform(0, 500, size=(1000, 4)).astype(np.float32))) == 0
+    bad = std_anchors.copy()
+    bad[17, 2] = np.nan
+    assert len(probe(bad)) == 0
+
+
+def test_grid_windows_are_conservative_and_tight(ssdseglib, std_anchors):
+    rng = np.random.default_rng(1993)
+    _, boxes, _ = orc.synth_gt(rng, 12, 16)
+    cells = pairs = 0
+    for b in range(12):
+        for t in (np.full(16, 0.5, np.float32), rng.uniform(0, 0.9, 16).astype(np.float32), np.zeros(16, np.float32)):
+            c, p = _windows_cover(ssdseglib, std_anchors, boxes[b], t)
+            if t[0] == 0.5 and np.all(t == 0.5):
+                cells += c
+                pairs += p
+    assert cells < 1.6 * pairs, (cells, pairs)  # ~250 cells for ~200 pairs above 0.5 per image
+    # integer coordinates (boxes that coincide with cell borders), boxes outside the image, tiny and huge boxes
+    _, boxes, _ = orc.synth_gt(rng, 4, 16, integer=True)
+    boxes[1] += np.float32(500.0)
+    boxes[2, :, 2:] = boxes[2, :, :2] + np.float32(0.25)
+    boxes[3, :8] = np.array([-300.0, -200.0, 1500.0, 900.0], np.float32)
+    for b in range(4):
+        for t in (0.0, 0.3, 0.5, 0.95):
+            _windows_cover(ssdseglib, std_anchors, boxes[b], np.full(16, t, np.float32))
+
+
+def test_grid_windows_random_tables(ssdseglib):
+    rng = np.random.default_rng(7)
+    done = 0
+    for it in range(40):
+        shapes, h, w = [], int(rng.integers(6, 30)), int(rng.integers(6, 36))
+        for _ in range(int(rng.integers(1, 4))):
+            shapes.append((h, w))
+            h, w = max(6, (h + 1) // 2), max(6, (w + 1) // 2)
+        ratios = tuple(float(r) for r in rng.choice([1, 2, 3, 0.5, 1 / 3, 1.5], size=int(rng.integers(1, 5)),
+                                                     replace=False))
+        hw = (int(rng.integers(64, 1200)), int(rng.integers(64, 1400)))
+        anchors = orc.anchors_generate(
+            feature_maps_shapes=tuple(shapes), feature_maps_aspect_ratios=ratios,
+            boxes_scales=(float(rng.uniform(0.35, 0.5)), float(rng.uniform(0.6, 1.1))),
+            centers_padding_from_borders_percentage=float(rng.uniform(0.0, 0.2)),
+            additional_square_box=bool(rng.integers(0, 2)), image_shape=hw)
+        if len(ssdseglib._ssdx.grid_probe(anchors)) == 0:
+            continue
+        done += 1
+        _, boxes, _ = orc.synth_gt(rng, 1, 12, image_hw=hw, integer=bool(rng.integers(0, 2)),
+                                   wh_range=(4.0, float(rng.choice([60.0, 600.0]))))
+        boxes = boxes[0] + np.float32(rng.uniform(-0.3, 0.3) * hw[1] * rng.integers(0, 2))
+        _windows_cover(ssdseglib, anchors, boxes, rng.choice([0.0, 0.1, 0.5, 0.7], size=12).astype(np.float32))
+    assert done >= 30

@@ -22,17 +22,20 @@ def lib():
     return ssdseglib
 
 
-@pytest.fixture(autouse=True, params=["fused", "tiled"])
-def encode_path(request, monkeypatch):
-    """Every test runs against both encode drivers (one CTA per image / anchor-tiled + emit)."""
-    if request.param == "tiled" and "encode" not in request.node.name:
+@pytest.fixture(autouse=True, params=["grid_fused", "grid_split", "tile_fused", "tile_tiled"])
+def encode_path(request, lib):
+    """Every encode test runs against the four encode drivers: closed-form windows on grid anchor tables (one CTA
+    per image / split into GT-side and row-span kernels) and the tile match for arbitrary tables (one CTA per image /
+    anchor-tiled + emit).  A forced grid driver falls back to the tile match when the table is not a grid."""
+    if request.param != "grid_fused" and "encode" not in request.node.name:
         pytest.skip("encode driver does not matter for this test")
-    monkeypatch.setenv("SSDX_ENCODE_PATH", request.param)
-    return request.param
+    lib._ssdx.set_option("encode_path", request.param)
+    yield request.param
+    lib._ssdx.set_option("encode_path", "auto")
 
 
 @pytest.fixture(autouse=True, params=["fast", "perclass", "pcta", "generic"])
-def nms_path(request, monkeypatch):
+def nms_path(request, lib):
     """NMS tests run on the default dispatch (merged one-pass-per-image pipeline when max_per_class >= max_total,
     else the per-class pipeline: one warp per segment for caps up to 32, one CTA per segment above; generic only for
     handed-over work), with the per-class pipeline forced ("perclass"), with the per-class CTA kernel forced for every
@@ -40,8 +43,9 @@ def nms_path(request, monkeypatch):
     if request.param != "fast":
         if "nms" not in request.node.name:
             pytest.skip("NMS driver does not matter for this test")
-        monkeypatch.setenv("SSDX_NMS_PATH", request.param)
-    return request.param
+        lib._ssdx.set_option("nms_path", request.param)
+    yield request.param
+    lib._ssdx.set_option("nms_path", "auto")
 
 
 @pytest.fixture(scope="module")
@@ -157,7 +161,8 @@ def test_encode_randomized_differential(lib, encode_path):
         "fuzz_encode", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_encode.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    assert mod.run(150, 21 if encode_path == "fused" else 22, verbose=False) == 0
+    seed = {"grid_fused": 21, "grid_split": 22, "tile_fused": 23, "tile_tiled": 24}[encode_path]
+    assert mod.run(150, seed, verbose=False) == 0
 
 
 def test_encode_stress_shape_small_batch(lib):
