@@ -112,13 +112,12 @@ bool make_combo(const float* c, const float* area, const GridMap& m, int k, ssdx
   for (int row = 0; row < H; ++row)
     ey = std::max(ey, fabs(0.5 * (Y0(row) + Y1(row)) - (cy0 + row * dy)) + fabs(0.5 * (Y1(row) - Y0(row)) - hy));
   if ((W > 1 && ex > 0.25 * dx) || (H > 1 && ey > 0.25 * dy)) return false;  // not a regular grid after all
-  float amin = INFINITY, amax = -INFINITY;
+  float amin = INFINITY;
   for (int row = 0; row < H; ++row)
     for (int col = 0; col < W; ++col) {
       const float a = area[m.off + ((size_t)row * W + col) * nb + k];
       if (!(a > 0.0f) || !std::isfinite(a)) return false;
       amin = std::min(amin, a);
-      amax = std::max(amax, a);
     }
   // rounding margin: the device evaluates the window bounds in fp32 on coordinates of this magnitude
   const double margin = 0.01 + 1e-5 * maxabs;
@@ -129,14 +128,16 @@ bool make_combo(const float* c, const float* area, const GridMap& m, int k, ssdx
   out->hx = (float)(hx + 1e-6 * fabs(hx)); out->hy = (float)(hy + 1e-6 * fabs(hy));
   out->px = (float)(1.01 * ex + margin); out->py = (float)(1.01 * ey + margin);
   out->aw = (float)((2 * hx + 1) * (1 + 1e-6)); out->ah = (float)((2 * hy + 1) * (1 + 1e-6));
-  out->amin = amin; out->amax = amax;
+  out->amin = amin;
+  out->ax = 0;  // set by detect_grids
   return std::isfinite(out->inv_dx) && std::isfinite(out->inv_dy) && std::isfinite(out->px) && std::isfinite(out->py);
 }
 
 bool detect_grids(const float* c, const float* area, size_t A, std::vector<ssdx_grid_combo>& combos,
-                  std::vector<ssdx_grid_span>& spans) {
+                  std::vector<ssdx_grid_span>& spans, std::vector<float>& axes) {
   combos.clear();
   spans.clear();
+  axes.clear();
   for (size_t i = 0; i < 4 * A; ++i)
     if (!std::isfinite(c[i])) return false;
   size_t off = 0;
@@ -170,6 +171,14 @@ bool detect_grids(const float* c, const float* area, size_t A, std::vector<ssdx_
       for (int k = 0; k < nb && ok; ++k) ok = make_combo(c, area, m, k, &mine[k]);
       if (!ok) continue;
       const int combo0 = (int)combos.size();
+      for (int k = 0; k < nb; ++k) {  // axis arrays: x0[W] | x1[W] | y0[H] | y1[H], the floats of the table
+        mine[k].ax = (int)axes.size();
+        for (int col = 0; col < W; ++col) axes.push_back(c[4 * (off + (size_t)col * nb + k) + 0]);
+        for (int col = 0; col < W; ++col) axes.push_back(c[4 * (off + (size_t)col * nb + k) + 2]);
+        for (int row = 0; row < H; ++row) axes.push_back(c[4 * (off + (size_t)row * L + k) + 1]);
+        for (int row = 0; row < H; ++row) axes.push_back(c[4 * (off + (size_t)row * L + k) + 3]);
+        while (axes.size() % 4) axes.push_back(0.0f);  // 16-byte granules for the vector copy into shared memory
+      }
       combos.insert(combos.end(), mine.begin(), mine.end());
       const int rps = std::max(1, (int)(kSsdxSpanAnchors / L));
       for (int r = 0; r < H; r += rps) {
@@ -182,7 +191,7 @@ bool detect_grids(const float* c, const float* area, size_t A, std::vector<ssdx_
       off += (size_t)H * L;
       found = true;
     }
-    if (!found) { combos.clear(); spans.clear(); return false; }
+    if (!found) { combos.clear(); spans.clear(); axes.clear(); return false; }
   }
   return !combos.empty();
 }
@@ -317,8 +326,9 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
 
   std::vector<ssdx_grid_combo> combos;
   std::vector<ssdx_grid_span> spans;
-  detect_grids(corners_xyxy_host, area.data(), A, combos, spans);
-  const size_t nq = combos.size(), ns = spans.size();
+  std::vector<float> axes;
+  detect_grids(corners_xyxy_host, area.data(), A, combos, spans, axes);
+  const size_t nq = combos.size(), ns = spans.size(), nax = axes.size();
 
   ssdx_anchors* h = (ssdx_anchors*)calloc(1, sizeof(ssdx_anchors));
   ssdx_grid_combo* combos_host = nq ? (ssdx_grid_combo*)malloc(nq * sizeof(ssdx_grid_combo)) : nullptr;
@@ -335,16 +345,21 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
   h->n_spans = (int32_t)ns;
   h->combos_host = combos_host;
   for (size_t i = 0; i < nq; ++i) combos_host[i] = combos[i];
+  h->n_axes = (int32_t)nax;
   for (size_t i = 0; i < ns; ++i) {
     h->max_span_anchors = std::max(h->max_span_anchors, (int32_t)spans[i].n);
     h->max_span_combos = std::max(h->max_span_combos, (int32_t)spans[i].nb);
+    const ssdx_grid_combo& first = combos[spans[i].combo0];
+    const ssdx_grid_combo& last = combos[spans[i].combo0 + spans[i].nb - 1];
+    const int map_axes = (last.ax + (2 * last.W + 2 * last.H + 3) / 4 * 4) - first.ax;
+    h->max_map_axes = std::max(h->max_map_axes, (int32_t)map_axes);
   }
   cudaError_t e = cudaSuccess;
   // one allocation: corners | enc_cent | dec_cent | m_box | t_bbox | t_area | area | m_area | m_idx | combos | spans
   char* base = nullptr;
   const size_t bytes = A * (3 * sizeof(float4) + sizeof(float)) + Ap * (sizeof(float4) + sizeof(float) + sizeof(int)) +
                        n_tiles * (sizeof(float4) + sizeof(float2)) + 64 + nq * sizeof(ssdx_grid_combo) +
-                       ns * sizeof(ssdx_grid_span);
+                       ns * sizeof(ssdx_grid_span) + nax * sizeof(float);
   e = cudaMalloc((void**)&base, bytes);
   if (e == cudaSuccess) {
     h->corners = (float4*)base;
@@ -358,6 +373,7 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
     h->m_idx = (int*)(h->m_area + Ap);
     h->combos = (ssdx_grid_combo*)ssdx_align_up((size_t)(h->m_idx + Ap), 32);
     h->spans = (ssdx_grid_span*)(h->combos + nq);
+    h->axes = (float*)(h->spans + ns);
     e = cudaMemcpy(h->corners, corners_xyxy_host, A * sizeof(float4), cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) e = cudaMemcpy(h->enc_cent, enc.data(), A * sizeof(float4), cudaMemcpyHostToDevice);
@@ -372,6 +388,7 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
     e = cudaMemcpy(h->combos, combos.data(), nq * sizeof(ssdx_grid_combo), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && ns)
     e = cudaMemcpy(h->spans, spans.data(), ns * sizeof(ssdx_grid_span), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nax) e = cudaMemcpy(h->axes, axes.data(), nax * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     ssdx_set_error("ssdx_anchors_create: CUDA error: %s", cudaGetErrorString(e));
     if (base) cudaFree(base);
@@ -412,7 +429,8 @@ int ssdx_grid_probe(const float* corners_xyxy_host, int32_t num_anchors, int32_t
   }
   std::vector<ssdx_grid_combo> combos;
   std::vector<ssdx_grid_span> spans;
-  detect_grids(corners_xyxy_host, area.data(), A, combos, spans);
+  std::vector<float> axes;
+  detect_grids(corners_xyxy_host, area.data(), A, combos, spans, axes);
   if (num_grids) *num_grids = (int32_t)combos.size();
   if (num_spans) *num_spans = (int32_t)spans.size();
   if (grids_out)
@@ -443,7 +461,8 @@ int ssdx_grid_window_probe(const float* corners_xyxy_host, int32_t num_anchors, 
   }
   std::vector<ssdx_grid_combo> combos;
   std::vector<ssdx_grid_span> spans;
-  detect_grids(corners_xyxy_host, area.data(), A, combos, spans);
+  std::vector<float> axes;
+  detect_grids(corners_xyxy_host, area.data(), A, combos, spans, axes);
   for (int32_t i = 0; i < n_boxes; ++i)
     for (size_t q = 0; q < combos.size(); ++q) {
       float4 gb;

@@ -18,7 +18,8 @@ struct ssdx_grid_combo {
   float hx, hy;      // upper bounds of (x1 - x0) / 2, (y1 - y0) / 2
   float px, py;      // pads on the centre range
   float aw, ah;      // upper bounds of the +1 width / height (datacoder.py:143-144)
-  float amin, amax;  // smallest / largest anchor area (datacoder.py:111-114) in the grid
+  float amin;        // smallest anchor area (datacoder.py:111-114) in the grid
+  int ax;            // offset of this grid's axis arrays in ssdx_anchors::axes: x0[W] | x1[W] | y0[H] | y1[H]
 };
 // A row range of one feature map: anchors [a_lo, a_lo + n), rows [row0, row0 + nrows) of combos [combo0, combo0 + nb)
 struct ssdx_grid_span {
@@ -54,6 +55,13 @@ struct ssdx_anchors {
   ssdx_grid_span* spans;         // device (n_spans): row ranges of one map, at most kSsdxSpanAnchors anchors each
   int32_t max_span_anchors;      // largest span
   int32_t max_span_combos;       // largest number of shapes of a map
+  // The table itself in separable form: per grid the x extents of its columns and the y extents of its rows, the
+  // very floats of the table (corners(row, col) = (x0[col], y0[row], x1[col], y1[row]) bit for bit), so the encode
+  // kernels rebuild any anchor, its area and its centroid from a few KB of shared memory instead of gathering them
+  // from global memory under a saturated memory system.
+  int32_t n_axes;                // floats in axes
+  float* axes;                   // device
+  int32_t max_map_axes;          // floats of the largest single map's (contiguous) axis arrays
 };
 
 #ifndef SSDX_APT

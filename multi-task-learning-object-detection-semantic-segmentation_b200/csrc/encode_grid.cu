@@ -28,6 +28,8 @@
 //   split : K1 grid (GT chunks, images) computes the per-GT best anchors, K2 grid (row spans of a feature map,
 //           images) the anchor side of its span and writes the span's rows: small batches and large tables
 //           (dense stress: 100k anchors x 256 GT boxes).
+#include <algorithm>
+
 #include "common.cuh"
 #include "encode_common.cuh"
 #include "grid_window.cuh"
@@ -47,20 +49,35 @@ namespace {
 using namespace ssdx_enc;
 
 #ifndef SSDX_GRID_MINB
-#define SSDX_GRID_MINB 2
+#define SSDX_GRID_MINB 4
 #endif
 #ifndef SSDX_GRID_BGROWS
-#define SSDX_GRID_BGROWS 512
+#define SSDX_GRID_BGROWS 256
 #endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kWinCap = 512;                 // windows per round (GT boxes of the round x grids)
 constexpr int kBgRows = SSDX_GRID_BGROWS;    // background rows per bulk store
-constexpr int kPosCap = 1024;                // compacted positives per image (more are encoded in place)
 constexpr int kBestG = 32;                   // GT boxes per CTA of the split driver's K1
 constexpr int kGtTile = 256;                 // GT boxes staged per round by the split driver's K2
 constexpr unsigned short kNone = 0xFFFFu;
-constexpr int kGridFusedMaxA = 12288;        // per-anchor tables of the fused driver: 6 bytes per anchor
+constexpr int kGridFusedMaxA = 32768;        // anchor -> slot table of the fused driver: 2 bytes per anchor
+
+// corners of anchor (row, col) of a grid, the floats of the table (ssdx_anchors::axes)
+__device__ __forceinline__ float4 grid_anchor_box(const ssdx_grid_combo& cb, const float* ax, const int r,
+                                                  const int c) {
+  const float* p = ax + cb.ax;
+  return make_float4(p[c], p[2 * cb.W + r], p[cb.W + c], p[2 * cb.W + cb.H + r]);
+}
+// datacoder.py:111-114, rounded as ssdx_anchors_create rounds the area table
+__device__ __forceinline__ float anchor_area(const float4 b) {
+  return __fmul_rn(__fadd_rn(__fsub_rn(b.w, b.y), 1.0f), __fadd_rn(__fsub_rn(b.z, b.x), 1.0f));
+}
+// datacoder.py:141-144 (cx, cy, w, h), rounded as ssdx_anchors_create rounds enc_cent
+__device__ __forceinline__ float4 anchor_centroid(const float4 b) {
+  return make_float4(__fmul_rn(__fadd_rn(b.z, b.x), 0.5f), __fmul_rn(__fadd_rn(b.w, b.y), 0.5f),
+                     __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+}
 
 // datacoder.py:210-220 for one pair; 0 when the boxes do not intersect (the reference's max(0, .) makes inter 0)
 __device__ __forceinline__ float pair_iou(const float4 ab, const float aa, const float4 gb, const float ga) {
@@ -72,18 +89,29 @@ __device__ __forceinline__ float pair_iou(const float4 ab, const float aa, const
 }
 
 // seed of the GT-side bound: exact IoU of the anchor of this grid nearest to the GT centre
-__device__ __forceinline__ void grid_seed(const ssdx_grid_combo& cb, const float4* __restrict__ corners,
-                                          const float* __restrict__ area, const float4 gb, const float ga,
-                                          u64* s_best_g) {
+__device__ __forceinline__ void grid_seed(const ssdx_grid_combo& cb, const float* ax, const float4 gb,
+                                          const float ga, u64* s_best_g) {
   const float gw = gb.z - gb.x + 1.0f, gh = gb.w - gb.y + 1.0f;
   if (!(gw > 0.0f && gh > 0.0f)) return;
   const float fc = rintf((0.5f * (gb.x + gb.z) - cb.cx0) * cb.inv_dx);
   const float fr = rintf((0.5f * (gb.y + gb.w) - cb.cy0) * cb.inv_dy);
   const int c = (int)fminf(fmaxf(fc, 0.0f), (float)(cb.W - 1));
   const int r = (int)fminf(fmaxf(fr, 0.0f), (float)(cb.H - 1));
-  const int a = cb.off + (r * cb.W + c) * cb.nb;
-  const float iou = pair_iou(__ldg(corners + a), __ldg(area + a), gb, ga);
-  if (iou > 0.0f) atomicMax(s_best_g, pack_best(__float_as_uint(iou), a));
+  const float4 ab = grid_anchor_box(cb, ax, r, c);
+  const float iou = pair_iou(ab, anchor_area(ab), gb, ga);
+  if (iou > 0.0f) atomicMax(s_best_g, pack_best(__float_as_uint(iou), cb.off + (r * cb.W + c) * cb.nb));
+}
+
+// (grid, row, col) of anchor a: the grids of one feature map are consecutive and share H, W, nb
+__device__ __forceinline__ float4 anchor_box_by_index(const ssdx_grid_combo* s_combo, const int nq, const float* ax,
+                                                      const int a) {
+  int q = 0;
+  while (q + s_combo[q].nb < nq && a >= s_combo[q + s_combo[q].nb].off) q += s_combo[q].nb;  // first grid of the map
+  const ssdx_grid_combo& m = s_combo[q];
+  const int rel = a - m.off;
+  const int cell = rel / m.nb, k = rel - cell * m.nb;
+  const int r = cell / m.W, c = cell - r * m.W;
+  return grid_anchor_box(s_combo[q + k], ax, r, c);
 }
 
 __device__ __forceinline__ void atomic_min_u16(unsigned short* p, const unsigned short v) {
@@ -187,43 +215,178 @@ __device__ __forceinline__ void make_windows(const ssdx_grid_combo* s_combo, con
 }
 
 // ------------------------------------------------------------------------------------------ fused driver
+// One CTA per image.  Each warp owns whole GT boxes (g = warp, warp + kWarps, ...): its lanes are the grids, so the
+// seed, the bound t(g), the windows and their prefix sum stay inside the warp (shuffles, no barrier, no shared
+// scratch), the cells of a GT box are walked 32 at a time, and the GT-side arg-max is a warp reduction.  What crosses
+// warps is the anchor side: an anchor reached by windows of several GT boxes.  Anchors with a pair above the
+// threshold are rare (~2 %), so they get a slot in a compact table (s_slot: anchor -> slot, claimed with one 16-bit
+// CAS; per slot the max IoU bits, the cell, the lowest GT index among the maxima) instead of per-anchor tables - the
+// slots double as the list of positives, and the CTA fits four times on an SM.
+//   pass 0: per-slot max IoU, per-GT best anchor | barrier | pass 1: lowest GT index among a slot's maxima | barrier
+//   | closed form (may add slots: anchors that are only some GT's best) | barrier | encode + patch the slots' rows.
+// An image with more positives than slots (kSlots; degenerate inputs) is redone by the exact per-anchor loop
+// grid_fused_overflow.
+constexpr int kSlots = 1024;
+constexpr unsigned kCellDead = 0xFFFFFFFFu;
+// Warp specialisation: kCompWarps warps match, one more warp only feeds the TMA unit with the background rows, a few
+// bulk stores in flight at a time.  (Issued all at once - 75 bulk stores per CTA, four CTAs per SM - the copies back
+// up in the SM's memory-instruction queue and every shared-memory access of the matching warps waits behind them:
+// 74 us per 1024 images, the sum of the match (29 us) and the output stream (45 us) instead of their maximum.)
+#ifndef SSDX_GRID_COMP_WARPS
+#define SSDX_GRID_COMP_WARPS 8
+#endif
+#ifndef SSDX_GRID_INFLIGHT
+#define SSDX_GRID_INFLIGHT 6
+#endif
+constexpr int kCompWarps = SSDX_GRID_COMP_WARPS;
+constexpr int kCompThreads = kCompWarps * 32;
+constexpr int kFThreads = kCompThreads + 32;
+constexpr int kBulkInFlight = SSDX_GRID_INFLIGHT;  // bulk stores of one CTA whose source has not been read yet
+
+__device__ __forceinline__ void comp_barrier() {  // the matching warps only (named barrier 1)
+  asm volatile("bar.sync 1, %0;" ::"n"(kCompThreads) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 __host__ __device__ inline int grid_label_rows(int C) {  // rows per constant label block (multiple of 4)
   int r = ((kBgRows * 16) / (4 * C)) & ~3;
   return r < 4 ? 4 : r;
 }
 __host__ __device__ inline bool grid_bulk_labels(int A, int C) { return ((A * (long long)C) % 4) == 0 && C <= 1024; }
 
-__host__ __device__ inline size_t grid_fused_smem_bytes(int A, int G, int C, int nq) {
+__host__ __device__ inline size_t grid_fused_smem_bytes(int A, int G, int C, int nq, int n_axes) {
   const size_t g = (size_t)(G > 0 ? G : 1);
   size_t n = (size_t)kBgRows * 16;                                                  // bg_off
   n += grid_bulk_labels(A, C) ? (size_t)grid_label_rows(C) * C * 4 : 16;            // bg_lab
-  n += g * 16 + g * 8 + g * 4 + g * 4 + g * 4;                                      // box, best, area, lab, s1a
+  n += g * (16 + 8 + 4 + 4 + 4 + 4);                                                // box, best, area, lab, bcell, s1a
   n = (n + 15) / 16 * 16;
-  n += (size_t)nq * sizeof(ssdx_grid_combo);                                        // grids
-  n += (size_t)kWinCap * 8 + (size_t)(kWinCap + 4) * 4;                             // rect, cnt/start
-  n += (size_t)kPosCap * 4 + 64;                                                    // pos, ctrl + warp sums
-  n += (size_t)((A + 3) / 4 * 4) * 4;                                               // val
-  n += (size_t)((A + 7) / 8 * 8) * 2;                                               // tab
+  n += (size_t)nq * sizeof(ssdx_grid_combo) + (size_t)n_axes * 4;                   // grids, axis arrays
+  n += (size_t)kWinCap * 8;                                                         // window rectangles
+  n += (size_t)kSlots * (4 + 4 + 2) + 64;                                           // slots, ctrl
+  n += (size_t)((A + 7) / 8 * 8) * 2;                                               // anchor -> slot
   return n + 16;
 }
 
-__global__ void __launch_bounds__(kThreads, SSDX_GRID_MINB)
-    ssdx_encode_grid_fused_kernel(const float4* __restrict__ corners, const float* __restrict__ area,
-                                  const float4* __restrict__ anc_cent, const ssdx_grid_combo* __restrict__ combos,
-                                  const int nq, const float4* __restrict__ gt_xyxy,
-                                  const int* __restrict__ gt_label, const int* __restrict__ gt_count, const int A,
-                                  const int Gmax, const int C, const float iou_thr, const float sx, const float sy,
-                                  const float sw, const float sh, float* __restrict__ out_labels,
-                                  float4* __restrict__ out_offsets, int* __restrict__ out_match) {
+// cell code of (grid q, row r, col c): q < 256, r, c < 4096 (ssdx_anchors_create keeps grids within that)
+__device__ __forceinline__ unsigned cell_code(const int q, const int r, const int c) {
+  return ((unsigned)q << 24) | ((unsigned)r << 12) | (unsigned)c;
+}
+
+// slot of anchor a, claimed on first use; -1 when the table is full
+__device__ __forceinline__ int get_slot(unsigned short* s_slot, int* s_nslots, const int cap, const int a) {
+  const unsigned short cur = *(volatile unsigned short*)(s_slot + a);
+  if (cur != kNone) return cur;
+  const int mine = atomicAdd(s_nslots, 1);
+  if (mine >= cap) return -1;
+  const unsigned short prev = atomicCAS(s_slot + a, kNone, (unsigned short)mine);
+  return prev == kNone ? mine : (int)prev;  // lost the race: slot `mine` stays dead (its cell keeps kCellDead)
+}
+
+// Walk the cells of up to 32 windows held one per lane (rectangle rx = r0 | c0 << 16, ry = columns | rows << 16,
+// ry = 0: empty): f(owner lane, row, col) for every cell, 32 cells per round.  All lanes of the warp must call it.
+template <typename F>
+__device__ __forceinline__ void warp_for_each_cell(const int rx, const int ry, const int lane, F f) {
+  const int cnt = (ry & 0xFFFF) * (ry >> 16);
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += u;
+  }
+  const int total = __shfl_sync(kFull, incl, 31);
+  const int excl = incl - cnt;
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    int lo = 0;  // largest lane l with excl(l) <= i: the window cell i belongs to (empty windows share a start)
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int e = __shfl_sync(kFull, excl, (lo + step) & 31);
+      if (e <= i) lo += step;
+    }
+    const int oe = __shfl_sync(kFull, excl, lo);
+    const int ox = __shfl_sync(kFull, rx, lo);
+    const int oy = __shfl_sync(kFull, ry, lo) & 0xFFFF;
+    if (i < total) {
+      const int local = i - oe;
+      const int rr = local / oy, cc = local - rr * oy;
+      f(lo, (ox & 0xFFFF) + rr, (ox >> 16) + cc);
+    }
+  }
+}
+
+// The exact per-anchor loop, for an image that does not fit the slot table: every anchor against every GT box.
+// Reuses s_slot as the anchor -> matched GT table.
+__device__ __noinline__ void grid_fused_overflow(const ssdx_grid_combo* s_combo, const int nq, const float* s_ax,
+                                                 const float4* s_box, const float* s_area, u64* s_best,
+                                                 int* s_s1a, unsigned short* s_tab, const int A, const int G,
+                                                 const float iou_thr) {
+  const int tid = threadIdx.x;
+  const int A8 = (A + 7) / 8 * 8;
+  comp_barrier();
+  for (int i = tid; i < A8 / 8; i += kCompThreads) reinterpret_cast<int4*>(s_tab)[i] = make_int4(-1, -1, -1, -1);
+  for (int g = tid; g < G; g += kCompThreads) s_best[g] = 0ull;
+  comp_barrier();
+  for (int a = tid; a < A; a += kCompThreads) {
+    const float4 ab = anchor_box_by_index(s_combo, nq, s_ax, a);
+    const float aa = anchor_area(ab);
+    float bv = 0.0f;
+    int bg = 0;
+    for (int g = 0; g < G; ++g) {
+      const float iou = pair_iou(ab, aa, s_box[g], s_area[g]);
+      if (iou > bv) {  // strict: ties keep the lower GT index
+        bv = iou;
+        bg = g;
+      }
+      const unsigned bits = __float_as_uint(iou);
+      if (iou > 0.0f && bits >= best_bits(s_best + g)) atomicMax(s_best + g, pack_best(bits, a));
+    }
+    if (bv > iou_thr) s_tab[a] = (unsigned short)bg;
+  }
+  comp_barrier();
+  for (int g = tid; g < G; g += kCompThreads) {
+    const u64 p = s_best[g];
+    s_s1a[g] = ((p >> 32) != 0ull) ? best_anchor(p) : -1;
+  }
+  comp_barrier();
+  for (int g = tid; g < G; g += kCompThreads) {
+    const int a = s_s1a[g];
+    if (a < 0) continue;
+    bool is_max = true;
+    for (int h = g + 1; h < G; ++h) is_max = is_max && (s_s1a[h] != a);
+    if (is_max) {
+      const unsigned short g2 = s_tab[a];
+      s_tab[a] = (g2 != kNone && s_s1a[g2] != a) ? g2 : (unsigned short)g;
+    }
+  }
+  comp_barrier();
+}
+
+// Persistent CTAs: grid = resident CTAs of the device, images handed out through a ticket counter (next_image; the
+// first ticket of a CTA is its block index, the host sets the counter to gridDim.x before the launch).  The producer
+// warp keeps the output stream of the CTA running across images; it draws the tickets and passes them to the
+// matching warps through shared memory.  Per image the two sides meet once (named barrier 2), when the image's
+// background rows are complete and its match is done; the matching warps then patch the positives and go on.
+__global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
+    ssdx_encode_grid_fused_kernel(const ssdx_grid_combo* __restrict__ combos, const int nq,
+                                  const float* __restrict__ axes, const int n_axes,
+                                  const float4* __restrict__ gt_xyxy, const int* __restrict__ gt_label,
+                                  const int* __restrict__ gt_count, const int B, const int A, const int Gmax,
+                                  const int C, const float iou_thr, const float sx, const float sy, const float sw,
+                                  const float sh, float* __restrict__ out_labels, float4* __restrict__ out_offsets,
+                                  int* __restrict__ out_match, int* __restrict__ next_image) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int G = gt_count[b];
-  G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
   const int Gs = Gmax > 0 ? Gmax : 1;
   const bool bulk_lab = grid_bulk_labels(A, C);
   const int lab_rows = grid_label_rows(C);
-  const int A4 = (A + 3) / 4 * 4, A8 = (A + 7) / 8 * 8;
+  const int A8 = (A + 7) / 8 * 8;
 
   float4* bg_off;
   float* bg_lab;
@@ -231,14 +394,16 @@ __global__ void __launch_bounds__(kThreads, SSDX_GRID_MINB)
   u64* s_best;
   float* s_area;
   int* s_lab;
+  unsigned* s_bcell;
   int* s_s1a;
   ssdx_grid_combo* s_combo;
+  float* s_ax;
   int2* s_rect;
-  int* s_cnt;
-  int* s_pos;
+  unsigned* s_cval;
+  unsigned* s_ccell;
+  unsigned short* s_cg;
   int* s_ctrl;
-  unsigned* s_val;
-  unsigned short* s_tab;
+  unsigned short* s_slot;
   {
     unsigned char* p = smem_raw;
     bg_off = (float4*)p;  p += (size_t)kBgRows * 16;
@@ -247,190 +412,351 @@ __global__ void __launch_bounds__(kThreads, SSDX_GRID_MINB)
     s_best = (u64*)p;     p += (size_t)Gs * 8;
     s_area = (float*)p;   p += (size_t)Gs * 4;
     s_lab = (int*)p;      p += (size_t)Gs * 4;
+    s_bcell = (unsigned*)p; p += (size_t)Gs * 4;
     s_s1a = (int*)p;      p += (size_t)Gs * 4;
     p = smem_raw + ((size_t)(p - smem_raw) + 15) / 16 * 16;
     s_combo = (ssdx_grid_combo*)p; p += (size_t)nq * sizeof(ssdx_grid_combo);
+    s_ax = (float*)p;     p += (size_t)n_axes * 4;
     s_rect = (int2*)p;    p += (size_t)kWinCap * 8;
-    s_cnt = (int*)p;      p += (size_t)(kWinCap + 4) * 4;
-    s_pos = (int*)p;      p += (size_t)kPosCap * 4;
+    s_cval = (unsigned*)p;  p += (size_t)kSlots * 4;
+    s_ccell = (unsigned*)p; p += (size_t)kSlots * 4;
+    s_cg = (unsigned short*)p; p += (size_t)kSlots * 2;
     s_ctrl = (int*)p;     p += 64;
-    s_val = (unsigned*)p; p += (size_t)A4 * 4;
-    s_tab = (unsigned short*)p;
+    s_slot = (unsigned short*)p;
   }
-  int* s_wsum = s_ctrl + 4;  // kWarps + 1 ints
+  int* s_nslots = s_ctrl + 0;
+  int* s_overflow = s_ctrl + 1;
+  volatile int* s_ticket = s_ctrl + 2;  // [2]: image of the CTA's k-th round at [k & 1], written by the producer
 
-  // ---- phase 0: constant background blocks, GT staging, tables ----
+  // ---- once per CTA: grids, axis arrays (the table in separable form), constant background blocks, empty tables ----
   PHASE_T0();
-  for (int i = tid; i < kBgRows; i += kThreads) bg_off[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bulk_lab)
-    for (int r = tid; r < lab_rows; r += kThreads) {
-      bg_lab[r * C] = 1.0f;
-      for (int c = 1; c < C; ++c) bg_lab[r * C + c] = 0.0f;
-    }
-  for (int g = tid; g < G; g += kThreads) {
-    const float4 bx = __ldg(gt_xyxy + (size_t)b * Gmax + g);
-    s_box[g] = bx;
-    s_area[g] = gt_area(bx);
-    s_lab[g] = __ldg(gt_label + (size_t)b * Gmax + g);
-    s_best[g] = 0ull;
-  }
-  for (int i = tid; i < nq * (int)(sizeof(ssdx_grid_combo) / 16); i += kThreads)
+  for (int i = tid; i < nq * (int)(sizeof(ssdx_grid_combo) / 16); i += kFThreads)
     reinterpret_cast<int4*>(s_combo)[i] = __ldg(reinterpret_cast<const int4*>(combos) + i);
-  for (int i = tid; i < A4 / 4; i += kThreads) reinterpret_cast<int4*>(s_val)[i] = make_int4(0, 0, 0, 0);
-  for (int i = tid; i < A8 / 8; i += kThreads) reinterpret_cast<int4*>(s_tab)[i] = make_int4(-1, -1, -1, -1);
-  if (tid == 0) s_ctrl[1] = 0;  // number of positives
-  fence_async_smem();           // the background blocks are read by the async proxy
+  for (int i = tid; i < n_axes / 4; i += kFThreads)
+    reinterpret_cast<int4*>(s_ax)[i] = __ldg(reinterpret_cast<const int4*>(axes) + i);
+  for (int i = tid; i < kBgRows; i += kFThreads) bg_off[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bulk_lab) {
+    if (C == 4) {
+      for (int r = tid; r < lab_rows; r += kFThreads)
+        reinterpret_cast<float4*>(bg_lab)[r] = make_float4(1.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int e = tid; e < lab_rows * C; e += kFThreads) bg_lab[e] = (e % C == 0) ? 1.0f : 0.0f;
+    }
+  }
+  for (int i = tid; i < kSlots; i += kFThreads) {
+    s_cval[i] = 0u;
+    s_ccell[i] = kCellDead;
+    s_cg[i] = kNone;
+  }
+  for (int i = tid; i < A8 / 8; i += kFThreads) reinterpret_cast<int4*>(s_slot)[i] = make_int4(-1, -1, -1, -1);
+  if (tid == 0) {
+    *s_nslots = 0;
+    *s_overflow = 0;
+    s_ticket[0] = blockIdx.x;
+  }
+  fence_async_smem();  // the background blocks are read by the async proxy
   __syncthreads();
   PHASE_ADD(0);
 
-  float4* offs = out_offsets + (size_t)b * A;
-  float* labs = out_labels + (size_t)b * A * C;
-  if (warp == kWarps - 1 && lane == 0) {  // background for the whole image, drained by the TMA unit during the match
+  if (warp == kCompWarps) {
+    // =================== producer warp: background rows of every image of this CTA as TMA bulk stores ===================
     const int n_off = (A + kBgRows - 1) / kBgRows;
     const int n_lab = bulk_lab ? (A + lab_rows - 1) / lab_rows : 0;
-    for (int i = 0; i < n_off + n_lab; ++i) {
-      if (i < n_off) {
-        const int r0 = i * kBgRows;
-        bulk_store(offs + r0, bg_off, (unsigned)(min(kBgRows, A - r0) * 16));
-      } else {
-        const int r0 = (i - n_off) * lab_rows;
-        bulk_store(labs + (size_t)r0 * C, bg_lab, (unsigned)(min(lab_rows, A - r0) * C * 4));
-      }
-    }
-    bulk_commit();
-  }
-  __syncwarp();
-
-  if (G > 0) {
-    const float thr_eff = fmaxf(iou_thr, 0.0f);
-    // ---- seeds: nearest anchor of every grid ----
-    for (int w = tid; w < G * nq; w += kThreads) {
-      const int g = w / nq, q = w - g * nq;
-      grid_seed(s_combo[q], corners, area, s_box[g], s_area[g], s_best + g);
-    }
-    __syncthreads();
-    PHASE_ADD(1);
-    // ---- windows -> scan -> cells; pass 0: per-anchor max IoU + GT side, pass 1: lowest GT among the maxima ----
-    const int g_round = max(1, kWinCap / nq);  // GT boxes per round
-    const bool one_round = G <= g_round;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int g0 = 0; g0 < G; g0 += g_round) {
-        const int gn = min(g_round, G - g0);
-        const int n_win = gn * nq;
-        int total;
-        if (pass == 0 || !one_round) {
-          make_windows<0>(s_combo, nq, s_box, s_best, g0, gn, thr_eff, 0, 0, s_cnt, s_rect);
-          __syncthreads();
-          total = block_scan_excl(s_cnt, n_win, s_wsum);
+    const int n_st = n_off + n_lab;
+    auto issue = [&](const int img, const int i0, const int i1) {  // bulk stores [i0, i1) of an image, one group each
+      float4* offs = out_offsets + (size_t)img * A;
+      float* labs = out_labels + (size_t)img * A * C;
+      for (int i = i0; i < i1; ++i) {
+        if (i < n_off) {
+          const int r0 = i * kBgRows;
+          bulk_store(offs + r0, bg_off, (unsigned)(min(kBgRows, A - r0) * 16));
         } else {
-          total = s_cnt[n_win];  // the windows of pass 0 are still in place
+          const int r0 = (i - n_off) * lab_rows;
+          bulk_store(labs + (size_t)r0 * C, bg_lab, (unsigned)(min(lab_rows, A - r0) * C * 4));
         }
-        for (int i = tid; i < total; i += kThreads) {
-          const int w = find_window(s_cnt, n_win, i);
-          const int gl = w / nq, q = w - gl * nq;
-          const int g = g0 + gl;
-          const ssdx_grid_combo& cb = s_combo[q];
-          const int2 rc = s_rect[w];
-          const int local = i - s_cnt[w];
-          const int rr = local / rc.y, cc = local - rr * rc.y;
-          const int a = cb.off + (((rc.x & 0xFFFF) + rr) * cb.W + (rc.x >> 16) + cc) * cb.nb;
-          const float iou = pair_iou(__ldg(corners + a), __ldg(area + a), s_box[g], s_area[g]);
-          const unsigned bits = __float_as_uint(iou);
-          if (pass == 0) {
-            if (iou > iou_thr) atomicMax(s_val + a, bits);
-            if (iou > 0.0f && bits >= best_bits(s_best + g)) atomicMax(s_best + g, pack_best(bits, a));
-          } else {
-            if (iou > iou_thr && bits == s_val[a]) atomic_min_u16(s_tab + a, (unsigned short)g);
+        bulk_commit();
+        bulk_wait_read<kBulkInFlight>();  // at most kBulkInFlight copies of this CTA queued in the SM
+      }
+    };
+    const bool lookahead = n_st >= kBulkInFlight;  // the first stores of the next image go out before this one is waited for
+    int img = blockIdx.x;
+    int head = 0;  // stores of img already issued
+    for (int k = 0; img < B; ++k) {
+      int next = B;
+#ifndef SSDX_GRID_EXP_NOBULK
+      if (lane == 0) {
+        issue(img, head, n_st);
+        next = atomicAdd(next_image, 1);
+        if (next < B && lookahead) {
+          issue(next, 0, kBulkInFlight);
+          bulk_wait<kBulkInFlight>();  // everything but the kBulkInFlight newest groups: image img is complete
+        } else {
+          bulk_wait_all();
+        }
+        s_ticket[(k + 1) & 1] = next;
+      }
+#else
+      if (lane == 0) {
+        next = atomicAdd(next_image, 1);
+        s_ticket[(k + 1) & 1] = next;
+      }
+#endif
+      next = __shfl_sync(kFull, next, 0);
+      head = (next < B && lookahead) ? kBulkInFlight : 0;
+      __syncwarp();
+      asm volatile("bar.sync 2, %0;" ::"n"(kFThreads) : "memory");  // image img: background rows in place
+      img = next;
+    }
+  } else {
+    // =================== matching warps ===================
+    const float thr_eff = fmaxf(iou_thr, 0.0f);
+    int img = blockIdx.x;
+    for (int k = 0; img < B; ++k) {
+      const int b = img;
+      int G = gt_count[b];
+      G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
+      float4* offs = out_offsets + (size_t)b * A;
+      float* labs = out_labels + (size_t)b * A * C;
+      for (int g = tid; g < G; g += kCompThreads) {
+        const float4 bx = __ldg(gt_xyxy + (size_t)b * Gmax + g);
+        s_box[g] = bx;
+        s_area[g] = gt_area(bx);
+        s_lab[g] = __ldg(gt_label + (size_t)b * Gmax + g);
+      }
+      if (out_match)  // (diagnostic output) background everywhere first, the positives overwrite it after a barrier
+        for (int a = tid; a < A; a += kCompThreads) out_match[(size_t)b * A + a] = -1;
+      comp_barrier();
+      PHASE_ADD(6);
+      const int slot_cap = kSlots - G;  // the closed form may add up to G positives of its own (G <= kFusedMaxG)
+      // ---- pass 0: seeds, windows, cells: per-slot max IoU and the GT side ----
+      for (int g = warp; g < G; g += kCompWarps) {
+        const float4 gb = s_box[g];
+        const float ga = s_area[g];
+        u64 best = 0ull;       // this lane's best pair of GT box g: (IoU bits, ~anchor)
+        unsigned bcell = 0u;   // and its cell
+        // seeds: the anchor of every grid nearest to the GT centre
+        const float gw = gb.z - gb.x + 1.0f, gh = gb.w - gb.y + 1.0f;
+        const bool gt_ok = gw > 0.0f && gh > 0.0f;  // an empty or NaN box: every IoU is 0 / NaN and never wins a '>'
+        if (gt_ok)
+          for (int q = lane; q < nq; q += 32) {
+            const ssdx_grid_combo& cb = s_combo[q];
+            const float fc = rintf((0.5f * (gb.x + gb.z) - cb.cx0) * cb.inv_dx);
+            const float fr = rintf((0.5f * (gb.y + gb.w) - cb.cy0) * cb.inv_dy);
+            const int c = (int)fminf(fmaxf(fc, 0.0f), (float)(cb.W - 1));
+            const int r = (int)fminf(fmaxf(fr, 0.0f), (float)(cb.H - 1));
+            const float4 ab = grid_anchor_box(cb, s_ax, r, c);
+            const float iou = pair_iou(ab, anchor_area(ab), gb, ga);
+            const u64 p = pack_best(__float_as_uint(iou), cb.off + (r * cb.W + c) * cb.nb);
+            if (iou > 0.0f && p > best) {
+              best = p;
+              bcell = cell_code(q, r, c);
+            }
+          }
+        const float seed = __uint_as_float(__reduce_max_sync(kFull, (unsigned)(best >> 32)));
+        const float t = fminf(thr_eff, seed);
+        for (int q0 = 0; q0 < nq; q0 += 32) {
+          const int q = q0 + lane;
+          int rx = 0, ry = 0;
+          ssdx_grid_rect rc;
+          if (q < nq && gt_ok && ssdx_grid_window(s_combo[q], gb, t, 0, s_combo[q].H, rc)) {
+            rx = rc.r0 | (rc.c0 << 16);
+            ry = rc.nc | (rc.nr << 16);
+          }
+          if (g * nq + q < kWinCap && q < nq) s_rect[g * nq + q] = make_int2(rx, ry);  // pass 1 walks it again
+          warp_for_each_cell(rx, ry, lane, [&](const int ql, const int r, const int c) {
+            const ssdx_grid_combo& cb = s_combo[q0 + ql];
+            const int a = cb.off + (r * cb.W + c) * cb.nb;
+            const float4 ab = grid_anchor_box(cb, s_ax, r, c);
+            const float iou = pair_iou(ab, anchor_area(ab), gb, ga);
+            const unsigned bits = __float_as_uint(iou);
+            if (iou > iou_thr) {
+              const int slot = get_slot(s_slot, s_nslots, slot_cap, a);
+              if (slot >= 0) {
+                atomicMax(s_cval + slot, bits);
+                s_ccell[slot] = cell_code(q0 + ql, r, c);  // (every writer of a slot writes the same cell)
+              } else {
+                *s_overflow = 1;
+              }
+            }
+            const u64 p = pack_best(bits, a);
+            if (iou > 0.0f && p > best) {
+              best = p;
+              bcell = cell_code(q0 + ql, r, c);
+            }
+          });
+        }
+        // GT side: arg-max over the lanes, ties -> lowest anchor index (largest ~anchor)
+        const unsigned hi = __reduce_max_sync(kFull, (unsigned)(best >> 32));
+        const unsigned lo = __reduce_max_sync(kFull, (unsigned)(best >> 32) == hi ? (unsigned)best : 0u);
+        if ((unsigned)(best >> 32) == hi && (unsigned)best == lo) {  // one lane (distinct anchors), or all when hi == 0
+          s_best[g] = ((u64)hi << 32) | lo;
+          s_bcell[g] = bcell;
+        }
+      }
+      comp_barrier();
+      PHASE_ADD(1);
+
+      // ---- pass 1: lowest GT index among the maxima of a slot (walks the windows of pass 0 again) ----
+      if (*s_overflow == 0) {
+        for (int g = warp; g < G; g += kCompWarps) {
+          const float4 gb = s_box[g];
+          const float ga = s_area[g];
+          const float gw = gb.z - gb.x + 1.0f, gh = gb.w - gb.y + 1.0f;
+          const bool gt_ok = gw > 0.0f && gh > 0.0f;
+          float t = 0.0f;
+          if (G * nq > kWinCap)  // windows beyond the stored ones are rebuilt; the bound may only have grown since
+            t = fminf(thr_eff, __uint_as_float(best_bits(s_best + g)));  // pass 0, the pairs above thr stay inside
+          for (int q0 = 0; q0 < nq; q0 += 32) {
+            const int q = q0 + lane;
+            int rx = 0, ry = 0;
+            if (q < nq) {
+              if (g * nq + q < kWinCap) {
+                const int2 w = s_rect[g * nq + q];
+                rx = w.x;
+                ry = w.y;
+              } else {
+                ssdx_grid_rect rc;
+                if (gt_ok && ssdx_grid_window(s_combo[q], gb, t, 0, s_combo[q].H, rc)) {
+                  rx = rc.r0 | (rc.c0 << 16);
+                  ry = rc.nc | (rc.nr << 16);
+                }
+              }
+            }
+            warp_for_each_cell(rx, ry, lane, [&](const int ql, const int r, const int c) {
+              const ssdx_grid_combo& cb = s_combo[q0 + ql];
+              const int a = cb.off + (r * cb.W + c) * cb.nb;
+              const float4 ab = grid_anchor_box(cb, s_ax, r, c);
+              const float iou = pair_iou(ab, anchor_area(ab), gb, ga);
+              if (iou > iou_thr) {
+                const int slot = s_slot[a];
+                if (__float_as_uint(iou) == s_cval[slot]) atomic_min_u16(s_cg + slot, (unsigned short)g);
+              }
+            });
           }
         }
-        __syncthreads();
       }
-    }
-  }
-  PHASE_ADD(2);
-  if (warp == kWarps - 1 && lane == 0) bulk_wait_all();  // background rows are in place before any patch
-  __syncthreads();
-  PHASE_ADD(3);
-
-  // ---- closed form: only the <= G anchors that are some GT's best anchor need more than g2 ----
-  for (int g = tid; g < G; g += kThreads) {
-    const u64 p = s_best[g];
-    s_s1a[g] = ((p >> 32) != 0ull) ? best_anchor(p) : -1;
-  }
-  __syncthreads();
-  for (int g = tid; g < G; g += kThreads) {
-    const int a = s_s1a[g];
-    if (a < 0) continue;
-    bool is_max = true;  // g == max(S1(a)) ?
-    for (int h = g + 1; h < G; ++h) is_max = is_max && (s_s1a[h] != a);
-    if (is_max) {
-      const unsigned short g2 = s_tab[a];
-      s_tab[a] = (g2 != kNone && s_s1a[g2] != a) ? g2 : (unsigned short)g;
-    }
-  }
-  __syncthreads();
-  PHASE_ADD(4);
-
-  // ---- compact the positives, encode them densely, patch them over the background ----
-  auto emit_positive = [&](const int a, const int g) {
-    st_stream_f4(offs + a, pair_offsets(s_box[g], __ldg(anc_cent + a), sx, sy, sw, sh));
-    if (bulk_lab) {
-      const int lab = s_lab[g];
-      if (C == 4) {
-        const float4 oh = make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f,
-                                      lab == 3 ? 1.f : 0.f);
-        st_stream_f4(reinterpret_cast<float4*>(labs) + a, oh);
-      } else {  // the background row is [1,0,...]; a label outside [0,C) gives an all-zero row (tf.one_hot)
-        labs[(size_t)a * C] = (lab == 0) ? 1.0f : 0.0f;
-        if (lab > 0 && lab < C) labs[(size_t)a * C + lab] = 1.0f;
+      comp_barrier();
+      PHASE_ADD(2);
+      const bool overflow = *s_overflow != 0;
+      if (overflow) {
+        grid_fused_overflow(s_combo, nq, s_ax, s_box, s_area, s_best, s_s1a, s_slot, A, G, iou_thr);
+      } else {
+        // ---- closed form: only the <= G anchors that are some GT's best anchor need more than g2 ----
+        for (int g = tid; g < G; g += kCompThreads) {
+          const u64 p = s_best[g];
+          s_s1a[g] = ((p >> 32) != 0ull) ? best_anchor(p) : -1;
+        }
+        comp_barrier();
+        for (int g = tid; g < G; g += kCompThreads) {
+          const int a = s_s1a[g];
+          if (a < 0) continue;
+          bool is_max = true;  // g == max(S1(a)) ?
+          for (int h = g + 1; h < G; ++h) is_max = is_max && (s_s1a[h] != a);
+          if (is_max) {
+            int slot = s_slot[a];
+            if (slot == kNone) {  // below the threshold, but the best anchor of GT box g: a new positive
+              slot = atomicAdd(s_nslots, 1);  // < kSlots: pass 0 stopped at kSlots - G
+              s_slot[a] = (unsigned short)slot;
+              s_ccell[slot] = s_bcell[g];
+              s_cg[slot] = (unsigned short)g;
+            } else {
+              const unsigned short g2 = s_cg[slot];
+              s_cg[slot] = (s_s1a[g2] != a) ? g2 : (unsigned short)g;
+            }
+          }
+        }
       }
-    }
-  };
-  for (int i = tid; i < A8 / 8; i += kThreads) {
-    const int4 v = reinterpret_cast<const int4*>(s_tab)[i];
-    if ((v.x & v.y & v.z & v.w) == -1) continue;  // 8 background rows
-    const int w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const unsigned m = (k & 1) ? ((unsigned)w[k >> 1] >> 16) : ((unsigned)w[k >> 1] & 0xFFFFu);
-      if (m != kNone) {
-        const int a = i * 8 + k;
-        const int slot = atomicAdd(&s_ctrl[1], 1);
-        if (slot < kPosCap) s_pos[slot] = (a << 8) | (int)m;
-        else emit_positive(a, (int)m);
-      }
-    }
-  }
-  __syncthreads();
-  const int npos = min(s_ctrl[1], kPosCap);
-  for (int s = tid; s < npos; s += kThreads) emit_positive(s_pos[s] >> 8, s_pos[s] & 255);
+      PHASE_ADD(3);
+      asm volatile("bar.sync 2, %0;" ::"n"(kFThreads) : "memory");  // match done, background rows of the image in place
+      PHASE_ADD(4);
 
-  if (!bulk_lab) {  // label rows that cannot be bulk-stored (unaligned image stride): flat coalesced walk
-    const int total = A * C;
-    for (int e = tid; e < total; e += kThreads) {
-      const int a = e / C;
-      const int c = e - a * C;
-      const unsigned short m = s_tab[a];
-      labs[e] = ((m != kNone ? s_lab[m] : 0) == c) ? 1.0f : 0.0f;
-    }
-  }
-  if (out_match)
-    for (int a = tid; a < A; a += kThreads) {
-      const unsigned short m = s_tab[a];
-      out_match[(size_t)b * A + a] = (m != kNone) ? (int)m : -1;
-    }
-  PHASE_ADD(5);
+      // ---- encode the positives densely and patch them over the background ----
+      unsigned short* s_tab = s_slot;  // overflow path only: anchor -> matched GT
+      auto emit_positive = [&](const int a, const float4 ab, const int g) {
+        st_stream_f4(offs + a, pair_offsets(s_box[g], anchor_centroid(ab), sx, sy, sw, sh));
+        if (bulk_lab) {
+          const int lab = s_lab[g];
+          if (C == 4) {
+            const float4 oh = make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f,
+                                          lab == 3 ? 1.f : 0.f);
+            st_stream_f4(reinterpret_cast<float4*>(labs) + a, oh);
+          } else {  // the background row is [1,0,...]; a label outside [0,C) gives an all-zero row (tf.one_hot)
+            labs[(size_t)a * C] = (lab == 0) ? 1.0f : 0.0f;
+            if (lab > 0 && lab < C) labs[(size_t)a * C + lab] = 1.0f;
+          }
+        }
+        if (out_match) out_match[(size_t)b * A + a] = g;
+      };
+      const int n_used = min(*s_nslots, kSlots);
+      if (!overflow) {
+        for (int s = tid; s < n_used; s += kCompThreads) {
+          const unsigned code = s_ccell[s];
+          if (code == kCellDead) continue;
+          const ssdx_grid_combo& cb = s_combo[code >> 24];
+          const int r = (code >> 12) & 0xFFF, c = code & 0xFFF;
+          emit_positive(cb.off + (r * cb.W + c) * cb.nb, grid_anchor_box(cb, s_ax, r, c), s_cg[s]);
+        }
+      } else {
+        for (int a = tid; a < A; a += kCompThreads) {
+          const unsigned short m = s_tab[a];
+          if (m != kNone) emit_positive(a, anchor_box_by_index(s_combo, nq, s_ax, a), (int)m);
+        }
+      }
+      if (!bulk_lab) {  // label rows that cannot be bulk-stored (unaligned image stride): flat coalesced walk
+        const int total = A * C;
+        for (int e = tid; e < total; e += kCompThreads) {
+          const int a = e / C;
+          const int c = e - a * C;
+          int lab = 0;
+          const unsigned short m = s_slot[a];  // slot, or (overflow) the matched GT itself
+          if (m != kNone) lab = s_lab[overflow ? m : s_cg[m]];
+          labs[e] = (lab == c) ? 1.0f : 0.0f;
+        }
+      }
+      const int next = s_ticket[(k + 1) & 1];  // drawn by the producer before the rendezvous
+      comp_barrier();
+      // ---- leave the tables empty for the next image: only what this image used ----
+      if (next < B) {
+        if (!overflow) {
+          for (int s = tid; s < n_used; s += kCompThreads) {
+            const unsigned code = s_ccell[s];
+            if (code != kCellDead) {
+              const ssdx_grid_combo& cb = s_combo[code >> 24];
+              s_slot[cb.off + (((code >> 12) & 0xFFF) * cb.W + (code & 0xFFF)) * cb.nb] = kNone;
+              s_ccell[s] = kCellDead;
+            }
+            s_cval[s] = 0u;
+            s_cg[s] = kNone;
+          }
+        } else {
+          for (int i = tid; i < kSlots; i += kCompThreads) {
+            s_cval[i] = 0u;
+            s_ccell[i] = kCellDead;
+            s_cg[i] = kNone;
+          }
+          for (int i = tid; i < A8 / 8; i += kCompThreads) reinterpret_cast<int4*>(s_slot)[i] = make_int4(-1, -1, -1, -1);
+        }
+        if (tid == 0) {
+          *s_nslots = 0;
+          *s_overflow = 0;
+        }
+      }
+      PHASE_ADD(5);
 #ifdef SSDX_PHASE_TIMERS
-  if (tid == 0) atomicAdd(&g_phase_cycles[24], 1ull);
+      if (tid == 0) atomicAdd(&g_phase_cycles[24], 1ull);
 #endif
+      img = next;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ split driver
 // K1: GT side.  grid (ceil(Gmax / kBestG), B); every (image, GT box) is owned by one CTA, which writes its packed
-// best (IoU bits, ~anchor) - 0 when no anchor overlaps the box.
+// best (IoU bits, ~anchor) - 0 when no anchor overlaps the box.  Dynamic shared memory: grids | axis arrays (when
+// they fit; otherwise the axis arrays are read from global memory).
 __global__ void __launch_bounds__(kThreads)
-    ssdx_encode_grid_best_kernel(const float4* __restrict__ corners, const float* __restrict__ area,
-                                 const ssdx_grid_combo* __restrict__ combos, const int nq,
+    ssdx_encode_grid_best_kernel(const ssdx_grid_combo* __restrict__ combos, const int nq,
+                                 const float* __restrict__ axes, const int n_axes_smem,
                                  const float4* __restrict__ gt_xyxy, const int* __restrict__ gt_count,
                                  const int Gmax, const float iou_thr, u64* __restrict__ gt_best) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -441,15 +767,14 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ int s_cnt[kWinCap + 4];
   __shared__ int s_wsum[kWarps + 1];
   ssdx_grid_combo* s_combo = (ssdx_grid_combo*)smem_raw;
+  float* s_ax = (float*)(s_combo + nq);
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   int G = gt_count[b];
   G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
   const int gc0 = blockIdx.x * kBestG;
   const int gn_cta = min(kBestG, G - gc0);
-  if (gn_cta <= 0) {  // unused slots of a ragged batch: K2 never reads beyond gt_count, nothing to write
-    return;
-  }
+  if (gn_cta <= 0) return;  // unused slots of a ragged batch: K2 never reads beyond gt_count
   for (int g = tid; g < gn_cta; g += kThreads) {
     const float4 bx = __ldg(gt_xyxy + (size_t)b * Gmax + gc0 + g);
     s_box[g] = bx;
@@ -458,11 +783,14 @@ __global__ void __launch_bounds__(kThreads)
   }
   for (int i = tid; i < nq * (int)(sizeof(ssdx_grid_combo) / 16); i += kThreads)
     reinterpret_cast<int4*>(s_combo)[i] = __ldg(reinterpret_cast<const int4*>(combos) + i);
+  for (int i = tid; i < n_axes_smem / 4; i += kThreads)
+    reinterpret_cast<int4*>(s_ax)[i] = __ldg(reinterpret_cast<const int4*>(axes) + i);
+  const float* ax = n_axes_smem > 0 ? s_ax : axes;
   __syncthreads();
   const float thr_eff = fmaxf(iou_thr, 0.0f);
   for (int w = tid; w < gn_cta * nq; w += kThreads) {
     const int g = w / nq, q = w - g * nq;
-    grid_seed(s_combo[q], corners, area, s_box[g], s_area[g], s_best + g);
+    grid_seed(s_combo[q], ax, s_box[g], s_area[g], s_best + g);
   }
   __syncthreads();
   const int g_round = max(1, kWinCap / nq);
@@ -480,10 +808,12 @@ __global__ void __launch_bounds__(kThreads)
       const int2 rc = s_rect[w];
       const int local = i - s_cnt[w];
       const int rr = local / rc.y, cc = local - rr * rc.y;
-      const int a = cb.off + (((rc.x & 0xFFFF) + rr) * cb.W + (rc.x >> 16) + cc) * cb.nb;
-      const float iou = pair_iou(__ldg(corners + a), __ldg(area + a), s_box[g], s_area[g]);
+      const int r = (rc.x & 0xFFFF) + rr, c = (rc.x >> 16) + cc;
+      const float4 ab = grid_anchor_box(cb, ax, r, c);
+      const float iou = pair_iou(ab, anchor_area(ab), s_box[g], s_area[g]);
       const unsigned bits = __float_as_uint(iou);
-      if (iou > 0.0f && bits >= best_bits(s_best + g)) atomicMax(s_best + g, pack_best(bits, a));
+      if (iou > 0.0f && bits >= best_bits(s_best + g))
+        atomicMax(s_best + g, pack_best(bits, cb.off + (r * cb.W + c) * cb.nb));
     }
     __syncthreads();
   }
@@ -491,35 +821,38 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // K2: anchor side of one span (a row range of one feature map) of one image + the span's output rows.
-// grid (n_spans, B).  Dynamic shared memory: combos of the span's map | val (u32 per anchor) | tab (u16) | s1 (u16).
-__host__ __device__ inline size_t grid_span_smem_bytes(int max_span_anchors, int max_span_combos) {
-  const size_t n4 = (size_t)(max_span_anchors + 7) / 8 * 8;
-  return (size_t)max_span_combos * sizeof(ssdx_grid_combo) + n4 * 4 + n4 * 2 + n4 * 2 + n4 * 4 + 16;
+// grid (n_spans, B).  Dynamic shared memory: grids of the span's map | their axis arrays | val (u32 per anchor) |
+// tab (u16) | s1 (u16) | pos (i32).
+__host__ __device__ inline size_t grid_span_smem_bytes(int max_span_anchors, int max_span_combos, int map_axes) {
+  const size_t n8 = (size_t)(max_span_anchors + 7) / 8 * 8;
+  return (size_t)max_span_combos * sizeof(ssdx_grid_combo) + (size_t)map_axes * 4 + n8 * 4 + n8 * 2 + n8 * 2 +
+         n8 * 4 + 16;
 }
 
 __global__ void __launch_bounds__(kThreads)
-    ssdx_encode_grid_span_kernel(const float4* __restrict__ corners, const float* __restrict__ area,
-                                 const float4* __restrict__ anc_cent, const ssdx_grid_combo* __restrict__ combos,
-                                 const ssdx_grid_span* __restrict__ spans, const int max_span_anchors,
-                                 const int max_span_combos, const float4* __restrict__ gt_xyxy,
-                                 const int* __restrict__ gt_label, const int* __restrict__ gt_count, const int A,
-                                 const int Gmax, const int C, const float iou_thr, const float sx, const float sy,
-                                 const float sw, const float sh, const u64* __restrict__ gt_best,
-                                 float* __restrict__ out_labels, float4* __restrict__ out_offsets,
-                                 int* __restrict__ out_match) {
+    ssdx_encode_grid_span_kernel(const ssdx_grid_combo* __restrict__ combos, const ssdx_grid_span* __restrict__ spans,
+                                 const float* __restrict__ axes, const int max_span_anchors,
+                                 const int max_span_combos, const int map_axes_smem,
+                                 const float4* __restrict__ gt_xyxy, const int* __restrict__ gt_label,
+                                 const int* __restrict__ gt_count, const int A, const int Gmax, const int C,
+                                 const float iou_thr, const float sx, const float sy, const float sw,
+                                 const float sh, const u64* __restrict__ gt_best, float* __restrict__ out_labels,
+                                 float4* __restrict__ out_offsets, int* __restrict__ out_match) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float4 s_box[kGtTile];
   __shared__ float s_area[kGtTile];
   __shared__ int2 s_rect[kWinCap];
   __shared__ int s_cnt[kWinCap + 4];
   __shared__ int s_wsum[kWarps + 1];
+  __shared__ int s_lab[kThreads];
   __shared__ int s_npos;
-  const int n4 = (max_span_anchors + 7) / 8 * 8;
+  const int n8 = (max_span_anchors + 7) / 8 * 8;
   ssdx_grid_combo* s_combo = (ssdx_grid_combo*)smem_raw;
-  unsigned* s_val = (unsigned*)(s_combo + max_span_combos);
-  unsigned short* s_tab = (unsigned short*)(s_val + n4);
-  unsigned short* s_s1 = s_tab + n4;     // max(S1(a)) + 1, 0 = empty
-  int* s_pos = (int*)(s_s1 + n4);        // compacted positives: (anchor - a_lo) << 16 | matched GT
+  float* s_ax = (float*)(s_combo + max_span_combos);
+  unsigned* s_val = (unsigned*)(s_ax + map_axes_smem);
+  unsigned short* s_tab = (unsigned short*)(s_val + n8);
+  unsigned short* s_s1 = s_tab + n8;     // max(S1(a)) + 1, 0 = empty
+  int* s_pos = (int*)(s_s1 + n8);        // compacted positives: (anchor - a_lo) << 16 | matched GT
 
   const ssdx_grid_span sp = spans[blockIdx.x];
   const int b = blockIdx.y;
@@ -531,8 +864,18 @@ __global__ void __launch_bounds__(kThreads)
 
   for (int i = tid; i < nq * (int)(sizeof(ssdx_grid_combo) / 16); i += kThreads)
     reinterpret_cast<int4*>(s_combo)[i] = __ldg(reinterpret_cast<const int4*>(combos + sp.combo0) + i);
-  for (int i = tid; i < n4 / 4; i += kThreads) reinterpret_cast<int4*>(s_val)[i] = make_int4(0, 0, 0, 0);
-  for (int i = tid; i < n4 / 8; i += kThreads) {
+  __syncthreads();
+  // axis arrays of this map, rebased so that s_combo[q].ax indexes s_ax
+  const int ax0 = s_combo[0].ax;
+  const ssdx_grid_combo& lastc = s_combo[nq - 1];
+  const int ax_n = lastc.ax + (2 * lastc.W + 2 * lastc.H + 3) / 4 * 4 - ax0;
+  const bool ax_smem = map_axes_smem > 0 && ax_n <= map_axes_smem;
+  if (ax_smem)
+    for (int i = tid; i < ax_n / 4; i += kThreads)
+      reinterpret_cast<int4*>(s_ax)[i] = __ldg(reinterpret_cast<const int4*>(axes + ax0) + i);
+  const float* ax = ax_smem ? (s_ax - ax0) : axes;
+  for (int i = tid; i < n8 / 4; i += kThreads) reinterpret_cast<int4*>(s_val)[i] = make_int4(0, 0, 0, 0);
+  for (int i = tid; i < n8 / 8; i += kThreads) {
     reinterpret_cast<int4*>(s_tab)[i] = make_int4(-1, -1, -1, -1);
     reinterpret_cast<int4*>(s_s1)[i] = make_int4(0, 0, 0, 0);
   }
@@ -574,12 +917,14 @@ __global__ void __launch_bounds__(kThreads)
             const int2 rc = s_rect[w];
             const int local = i - s_cnt[w];
             const int rr = local / rc.y, cc = local - rr * rc.y;
-            const int a = cb.off + (((rc.x & 0xFFFF) + rr) * cb.W + (rc.x >> 16) + cc) * cb.nb;
-            const float iou = pair_iou(__ldg(corners + a), __ldg(area + a), s_box[g], s_area[g]);
+            const int r = (rc.x & 0xFFFF) + rr, c = (rc.x >> 16) + cc;
+            const int al = cb.off + (r * cb.W + c) * cb.nb - sp.a_lo;
+            const float4 ab = grid_anchor_box(cb, ax, r, c);
+            const float iou = pair_iou(ab, anchor_area(ab), s_box[g], s_area[g]);
             if (iou > iou_thr) {
               const unsigned bits = __float_as_uint(iou);
-              if (pass == 0) atomicMax(s_val + (a - sp.a_lo), bits);
-              else if (bits == s_val[a - sp.a_lo]) atomic_min_u16(s_tab + (a - sp.a_lo), (unsigned short)(t0 + g));
+              if (pass == 0) atomicMax(s_val + al, bits);
+              else if (bits == s_val[al]) atomic_min_u16(s_tab + al, (unsigned short)(t0 + g));
             }
           }
           __syncthreads();
@@ -618,7 +963,6 @@ __global__ void __launch_bounds__(kThreads)
       }
     } else {
       // generic class count: flat coalesced walk over the chunk's (n_here * C) floats
-      __shared__ int s_lab[kThreads];
       __syncthreads();
       s_lab[tid] = match >= 0 ? __ldg(gt_label + (size_t)b * Gmax + match) : 0;
       __syncthreads();
@@ -634,12 +978,20 @@ __global__ void __launch_bounds__(kThreads)
   }
   __syncthreads();
   const int npos = s_npos;
+  const int Wm = s_combo[0].W;
   for (int i = tid; i < npos; i += kThreads) {
-    const int pa = sp.a_lo + (s_pos[i] >> 16), pm = s_pos[i] & 0xFFFF;
-    st_stream_f4(out_offsets + row0 + pa,
-                 pair_offsets(__ldg(gt_xyxy + (size_t)b * Gmax + pm), __ldg(anc_cent + pa), sx, sy, sw, sh));
+    const int l = s_pos[i] >> 16, pm = s_pos[i] & 0xFFFF;
+    const int cell = l / nq, k = l - cell * nq;          // the span starts at a row boundary of its map
+    const int r = sp.row0 + cell / Wm, c = cell % Wm;
+    const float4 ab = grid_anchor_box(s_combo[k], ax, r, c);
+    st_stream_f4(out_offsets + row0 + sp.a_lo + l,
+                 pair_offsets(__ldg(gt_xyxy + (size_t)b * Gmax + pm), anchor_centroid(ab), sx, sy, sw, sh));
   }
 }
+
+constexpr int kAxesSmemMax = 12288;  // floats of axis arrays a CTA stages in shared memory (48 KB)
+
+__global__ void ssdx_set_int_kernel(int* p, const int v) { *p = v; }
 
 }  // namespace
 
@@ -650,12 +1002,8 @@ bool ssdx_encode_grid_applies(const ssdx_anchors* anchors, int gmax, int num_cla
 }
 
 bool ssdx_encode_grid_fused_fits(const ssdx_anchors* anchors, int gmax, int num_classes) {
-  return gmax <= kFusedMaxG && anchors->A <= kGridFusedMaxA &&
-         grid_fused_smem_bytes(anchors->A, gmax, num_classes, anchors->n_combos) <= 110 * 1024;
-}
-
-size_t ssdx_encode_grid_workspace_bytes(int batch, int gmax) {
-  return ssdx_align_up((size_t)batch * (size_t)(gmax > 0 ? gmax : 1) * sizeof(u64), 256);
+  return gmax <= kFusedMaxG && anchors->A <= kGridFusedMaxA && anchors->n_axes <= kAxesSmemMax / 2 &&
+         grid_fused_smem_bytes(anchors->A, gmax, num_classes, anchors->n_combos, anchors->n_axes) <= 110 * 1024;
 }
 
 int ssdx_encode_grid_launch(const ssdx_anchors* anchors, const bool fused, const float* gt_xyxy,
@@ -665,34 +1013,43 @@ int ssdx_encode_grid_launch(const ssdx_anchors* anchors, const bool fused, const
   const int A = anchors->A;
   const int nq = anchors->n_combos;
   if (fused) {
-    const size_t smem = grid_fused_smem_bytes(A, gmax, num_classes, nq);
+    const size_t smem = grid_fused_smem_bytes(A, gmax, num_classes, nq, anchors->n_axes);
     SSDX_CUDA(cudaFuncSetAttribute(ssdx_encode_grid_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    ssdx_encode_grid_fused_kernel<<<batch, kThreads, smem, s>>>(
-        anchors->corners, anchors->area, anchors->enc_cent, anchors->combos, nq, (const float4*)gt_xyxy, gt_label,
-        gt_count, A, gmax, num_classes, iou_threshold, std_host[0], std_host[1], std_host[2], std_host[3],
-        out_labels, (float4*)out_offsets, out_match);
+    int per_sm = 0;
+    SSDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssdx_encode_grid_fused_kernel, kFThreads, smem));
+    const int grid = std::min((int)batch, std::max(1, per_sm) * ssdx_sm_count(anchors->device));
+    int* next_image = (int*)workspace;  // ticket counter: the first `grid` images are taken by block index
+    ssdx_set_int_kernel<<<1, 1, 0, s>>>(next_image, grid);
+    ssdx_encode_grid_fused_kernel<<<grid, kFThreads, smem, s>>>(
+        anchors->combos, nq, anchors->axes, anchors->n_axes, (const float4*)gt_xyxy, gt_label, gt_count, batch, A,
+        gmax, num_classes, iou_threshold, std_host[0], std_host[1], std_host[2], std_host[3], out_labels,
+        (float4*)out_offsets, out_match, next_image);
     SSDX_LAUNCH_CHECK("ssdx_encode_grid_fused_kernel");
     return SSDX_OK;
   }
   const int gm = gmax > 0 ? gmax : 1;
   u64* gt_best = (u64*)workspace;
   if (gmax > 0) {
+    const int ax1 = anchors->n_axes <= kAxesSmemMax ? anchors->n_axes : 0;
+    const size_t smem1 = (size_t)nq * sizeof(ssdx_grid_combo) + (size_t)ax1 * 4;
+    SSDX_CUDA(cudaFuncSetAttribute(ssdx_encode_grid_best_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem1));
     dim3 g1((gm + kBestG - 1) / kBestG, batch);
-    ssdx_encode_grid_best_kernel<<<g1, kThreads, (size_t)nq * sizeof(ssdx_grid_combo), s>>>(
-        anchors->corners, anchors->area, anchors->combos, nq, (const float4*)gt_xyxy, gt_count, gm, iou_threshold,
-        gt_best);
+    ssdx_encode_grid_best_kernel<<<g1, kThreads, smem1, s>>>(anchors->combos, nq, anchors->axes, ax1,
+                                                             (const float4*)gt_xyxy, gt_count, gm, iou_threshold,
+                                                             gt_best);
     SSDX_LAUNCH_CHECK("ssdx_encode_grid_best_kernel");
   }
-  const size_t smem2 = grid_span_smem_bytes(anchors->max_span_anchors, anchors->max_span_combos);
+  const int ax2 = anchors->max_map_axes <= kAxesSmemMax ? anchors->max_map_axes : 0;
+  const size_t smem2 = grid_span_smem_bytes(anchors->max_span_anchors, anchors->max_span_combos, ax2);
   SSDX_CUDA(cudaFuncSetAttribute(ssdx_encode_grid_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem2));
   dim3 g2(anchors->n_spans, batch);
   ssdx_encode_grid_span_kernel<<<g2, kThreads, smem2, s>>>(
-      anchors->corners, anchors->area, anchors->enc_cent, anchors->combos, anchors->spans,
-      anchors->max_span_anchors, anchors->max_span_combos, (const float4*)gt_xyxy, gt_label, gt_count, A, gm,
-      num_classes, iou_threshold, std_host[0], std_host[1], std_host[2], std_host[3], gt_best, out_labels,
-      (float4*)out_offsets, out_match);
+      anchors->combos, anchors->spans, anchors->axes, anchors->max_span_anchors, anchors->max_span_combos, ax2,
+      (const float4*)gt_xyxy, gt_label, gt_count, A, gm, num_classes, iou_threshold, std_host[0], std_host[1],
+      std_host[2], std_host[3], gt_best, out_labels, (float4*)out_offsets, out_match);
   SSDX_LAUNCH_CHECK("ssdx_encode_grid_span_kernel");
   return SSDX_OK;
 }
