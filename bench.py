@@ -44,7 +44,12 @@ BYTES_PER_IMAGE = {  # BASELINE.md section 3 (algorithmic / compulsory HBM traff
 WORKLOADS = {
     "roundtrip_b1024": dict(batch=1024, stages=("encode", "decode", "nms")),
     "decode_nms_b64": dict(batch=64, stages=("decode", "nms")),  # BASELINE config 1
+    # BASELINE config 5: detections vs GT, TP/FP flags + per-class counts, 4096 images in total sharded over the ranks,
+    # NCCL all-gather of the (C,3) count tables, AP tail on the global arrays (evaluators.py:65-187)
+    "eval_b4096": dict(batch=4096, stages=("eval",)),
 }
+EVAL_K, EVAL_THR = 200, 0.5
+BYTES_PER_IMAGE["eval"] = 24 * EVAL_K + 20 * G_STD + EVAL_K  # predictions + GT in, TP flags out
 
 
 def measured_peak():
@@ -189,10 +194,12 @@ def reference_arm(args, rank):
         return
     wl = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    sample = max(threads * 16, 512)  # bounded sample per step
     from oracle import c_oracle
 
     c_oracle.build()
+    if args.workload == "eval_b4096":
+        return reference_arm_eval(args, c_oracle, threads)
+    sample = wl["batch"]  # the GPU arm's batch: same config keys, same images per step
     anchors, cent, labels, boxes, counts, scores = cpu_inputs(sample, 1995, wl["stages"])
     times = []
     for i in range(args.warmup + args.steps):
@@ -207,15 +214,266 @@ def reference_arm(args, rank):
         "n_gpus": args.gpus, "gpus_used": 0,  # n_gpus = the N of the launch this line pairs with; the arm is CPU-only
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "stages": list(wl["stages"]), "anchors": A_STD, "gt_per_image": G_STD,
-                   "classes": C_STD, "max_total": K_STD, "images_per_step": sample},
+        "config": roundtrip_config(args, max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} images per step of the {args.workload} workload, C/OpenMP port "
-                                   f"(oracle/ssd_oracle.c), {threads} threads"},
+                                   f"(oracle/ssd_oracle.c, gcc {' '.join(c_oracle.CFLAGS)} -fopenmp), {threads} threads"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def roundtrip_config(args, world):
+    """`config` of the JSON line - the same dict from both arms (the driver compares them): the workload, and how the
+    GPU arm launches it.  Arm-specific facts (oracle check, host threads, sample) live outside `config`."""
+    wl = WORKLOADS[args.workload]
+    B, stages = wl["batch"], wl["stages"]
+    n_pipe = max(1, min(args.pipeline, B))
+    if args.pipeline_split:
+        n_pipe = len(args.pipeline_split.split(","))
+    n_streams = max(1, min(args.pipeline_streams, n_pipe))
+    launch = ("eager" if args.no_graph else "one CUDA graph per step") + (
+        "" if args.no_overlap else (
+            "; NMS candidate selection (ssdx_nms_select) on a second stream, concurrent with encode/decode, joined "
+            "before ssdx_nms_finish" if n_pipe == 1 else
+            f"; {n_pipe} sub-batches of {B // n_pipe} images pipelined on {n_streams} streams"))
+    return {"workload": args.workload, "stages": list(stages), "images_per_gpu": B, "global_batch": B * world,
+            "anchors": A_STD, "gt_per_image": G_STD, "classes": C_STD, "max_total": K_STD, "score_thr": 0.01,
+            "iou_thr": 0.45, "parallelism": f"batch-sharded x{world}, no collective",
+            "l2": "no flush: each step streams %.0f MB (> 126 MB L2)" % (
+                sum(BYTES_PER_IMAGE[s] for s in stages) * B / 1e6),
+            "gpu_launch": launch}
+
+
+def eval_config(world):
+    B = WORKLOADS["eval_b4096"]["batch"]
+    return {"workload": "eval_b4096", "stages": ["eval"], "global_batch": B, "images_per_gpu": B // world,
+            "predictions_per_image": EVAL_K, "gt_per_image": G_STD, "classes": C_STD, "iou_thr": EVAL_THR,
+            "parallelism": f"images sharded x{world}" + (
+                "; ssdx_allgather_counts (ncclAllGather of the (C,3) int64 tables) + all-gather of the TP / confidence "
+                "/ label arrays for the AP tail" if world > 1 else ", no collective"),
+            "l2": "flushed with a 256 MB fill before every timed step (the 17 MB working set would stay in L2)",
+            "gpu_launch": "eager, per-step events"}
+
+
+def reference_arm_eval(args, c_oracle, threads):
+    """BASELINE config 5 on the host: TP flags + counts (C/OpenMP port of evaluators.py:106-157) and the AP tail
+    (NumPy, evaluators.py:159-187) over all 4096 images per step."""
+    from oracle import ssd_oracle as orc
+
+    B = WORKLOADS["eval_b4096"]["batch"]
+    pl, conf, pb, gl, gb, gc = orc.synth_eval(np.random.default_rng(1997), B, EVAL_K, G_STD, C_STD)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        tp, cnt = c_oracle.eval_tp(pl, pb, gb, gl, gc, C_STD, 0, EVAL_THR, nthreads=threads)
+        orc.average_precision_from_tp(tp, conf, pl, {c: int(cnt[c, 2]) for c in range(1, C_STD)})
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    value = B / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "images/sec eval (TP/FP + counts + AP)", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "gpus_used": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": eval_config(max(args.gpus, 1)),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"all {B} images per step: C/OpenMP port of the TP/FP pass ({threads} threads) + "
+                                   "NumPy AP tail (1 thread)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def gpu_arm_eval(args, rank, world, local_rank):
+    """BASELINE config 5: 4096 images of detections vs GT sharded over the ranks (strong scaling), per-class TP/FP/GT
+    counts all-gathered over NCCL (ssdx_allgather_counts), AP on the device from the global flags."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    import __graft_entry__ as entry
+
+    if rank == 0:
+        entry.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.barrier()
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    import ssdseglib
+    from ssdseglib import _dist, _ssdx as sx
+    from oracle import ssd_oracle as orc  # generators (input synthesis) and, after the timed regions, the checker
+
+    B, K, G, C = WORKLOADS["eval_b4096"]["batch"], EVAL_K, G_STD, C_STD
+    pl, conf, pb, gl, gb, gc = orc.synth_eval(np.random.default_rng(1997), B, K, G, C)  # same global batch on every rank
+    lo, hi = _dist.shard_range(B, rank, world)
+    n = hi - lo
+    cuda = f"cuda:{dev}"
+    host = [torch.from_numpy(np.ascontiguousarray(x[lo:hi])).pin_memory() for x in (pl, conf, pb, gl, gb, gc)]
+    d_pl, d_conf, d_pb, d_gl, d_gb, d_gc = [t.to(cuda) for t in host]
+    tp = torch.empty((n, K), dtype=torch.uint8, device=cuda)
+    counts = torch.zeros((C, 3), dtype=torch.int64, device=cuda)
+    gathered = torch.zeros((world, C, 3), dtype=torch.int64, device=cuda)
+    total_counts = torch.zeros((C, 3), dtype=torch.int64, device=cuda)
+    # global flag arrays for the AP tail (rank-major = image-major: the shards are contiguous)
+    sizes = [_dist.shard_range(B, r, world) for r in range(world)]
+    even = all(h - l == n for l, h in sizes)
+    g_tp = torch.empty((B, K), dtype=torch.uint8, device=cuda) if world > 1 else tp
+    g_conf = torch.empty((B, K), dtype=torch.float32, device=cuda) if world > 1 else d_conf
+    g_pl = torch.empty((B, K), dtype=torch.int32, device=cuda) if world > 1 else d_pl
+    ap = torch.empty((C,), dtype=torch.float64, device=cuda)
+    ws_ap = torch.empty(int(sx.lib.ssdx_average_precision_workspace_bytes(B * K, C)), dtype=torch.uint8, device=cuda)
+    comm = _dist.CountsCommunicator(None, dev) if world > 1 else None
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+    assert even or world == 1, "eval_b4096 shards evenly over 1, 2, 4 and 8 ranks"
+
+    def step():
+        counts.zero_()
+        sx.check(sx.lib.ssdx_eval_tp(d_pl.data_ptr(), d_pb.data_ptr(), d_gb.data_ptr(), d_gl.data_ptr(), d_gc.data_ptr(),
+                                     n, K, G, C, 0, EVAL_THR, tp.data_ptr(), counts.data_ptr(), dev, sp))
+        if world > 1:
+            # the one collective of the path: (C,3) int64 per rank, NCCL all-gather on this stream
+            sx.check(sx.lib.ssdx_allgather_counts(comm.handle, counts.data_ptr(), gathered.data_ptr(), C, sp))
+            sx.check(sx.lib.ssdx_sum_counts(gathered.data_ptr(), world, C, total_counts.data_ptr(), dev, sp))
+            # the flags the AP tail integrates, gathered so that every rank holds the global arrays (7.4 MB in all)
+            dist.all_gather_into_tensor(g_tp, tp)
+            dist.all_gather_into_tensor(g_conf, d_conf)
+            dist.all_gather_into_tensor(g_pl, d_pl)
+            cnt = total_counts
+        else:
+            cnt = counts
+        sx.check(sx.lib.ssdx_average_precision(g_tp.data_ptr(), g_conf.data_ptr(), g_pl.data_ptr(), B * K, C,
+                                               cnt.data_ptr(), 0, ap.data_ptr(), ws_ap.data_ptr(), ws_ap.numel(), dev, sp))
+        return cnt
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # the working set (17 MB per rank at N = 1) fits the 126 MB L2: flush it between timed steps with a 256 MB fill
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=cuda)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev_tp = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        evs[k][0].record(stream)
+        counts.zero_()
+        sx.check(sx.lib.ssdx_eval_tp(d_pl.data_ptr(), d_pb.data_ptr(), d_gb.data_ptr(), d_gl.data_ptr(), d_gc.data_ptr(),
+                                     n, K, G, C, 0, EVAL_THR, tp.data_ptr(), counts.data_ptr(), dev, sp))
+        ev_tp[k].record(stream)
+        if world > 1:
+            sx.check(sx.lib.ssdx_allgather_counts(comm.handle, counts.data_ptr(), gathered.data_ptr(), C, sp))
+            sx.check(sx.lib.ssdx_sum_counts(gathered.data_ptr(), world, C, total_counts.data_ptr(), dev, sp))
+            dist.all_gather_into_tensor(g_tp, tp)
+            dist.all_gather_into_tensor(g_conf, d_conf)
+            dist.all_gather_into_tensor(g_pl, d_pl)
+        sx.check(sx.lib.ssdx_average_precision(g_tp.data_ptr(), g_conf.data_ptr(), g_pl.data_ptr(), B * K, C,
+                                               (total_counts if world > 1 else counts).data_ptr(), 0, ap.data_ptr(),
+                                               ws_ap.data_ptr(), ws_ap.numel(), dev, sp))
+        evs[k][1].record(stream)
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    tp_ms = float(np.median([evs[k][0].elapsed_time(ev_tp[k]) for k in range(args.steps)]))
+    total_ms = float(np.sum(step_ms))
+
+    # ---------------- end to end through the public API with host arrays ----------------
+    pg = dist.group.WORLD if dist is not None else None
+    h_np = [t.numpy() for t in host]
+
+    def step_e2e():
+        tp_h, cnt_h = ssdseglib.evaluators.true_positives_and_counts(h_np[0], h_np[2], h_np[3], h_np[4], h_np[5],
+                                                                      EVAL_THR, C, 0, process_group=pg)
+        return tp_h, cnt_h
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        tp_h, cnt_h = step_e2e()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    sampler.stop()
+    h2d = sum(h_np[i].nbytes for i in (0, 2, 3, 4, 5))
+    d2h = tp_h.nbytes + cnt_h.nbytes
+
+    # ---------------- check: ALL images against the oracle (outside the timed regions) ----------------
+    final_counts = step().cpu().numpy()
+    torch.cuda.synchronize(dev)
+    check = "skipped"
+    if rank == 0:
+        from oracle import c_oracle
+
+        ref_tp, ref_cnt = c_oracle.eval_tp(pl, pb, gb, gl, gc, C, 0, EVAL_THR)
+        ref_ap = orc.average_precision_from_tp(ref_tp, conf, pl, {c: int(ref_cnt[c, 2]) for c in range(1, C)})
+        ok = np.array_equal(g_tp.cpu().numpy(), ref_tp) and np.array_equal(final_counts, ref_cnt)
+        ok = ok and np.array_equal(np.asarray(cnt_h), ref_cnt) and np.array_equal(np.asarray(tp_h), ref_tp[lo:hi])
+        ap_h = ap.cpu().numpy()
+        ok = ok and all(abs(ap_h[c] - ref_ap[c]) < 1e-9 for c in range(1, C))
+        check = "pass" if ok else "FAIL"
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_ms, tp_ms], dtype=torch.float64, device=cuda)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms, tp_ms = float(t[0]), float(t[1]), float(t[2])
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_per_step = total_ms / args.steps
+        achieved = BYTES_PER_IMAGE["eval"] * n / (tp_ms / 1e3) / 1e9
+        line = {
+            "metric": "images/sec eval (TP/FP + counts + AP)", "value": B * args.steps / (total_ms / 1e3),
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": eval_config(world), "oracle_check": check + " (all 4096 images: flags, counts, AP)",
+            "roofline": {"bound": "hbm", "kernel": "ssdx_eval_tp_kernel", "stage": "eval", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_IMAGE["eval"] * n,
+                         "note": "instruction-bound: 13 M label-masked IoU pairs over 5,320 B per image",
+                         "stages": {"eval_tp": {"ms": tp_ms}, "collective+ap": {"ms": ms_per_step - tp_ms}}},
+            "e2e": {"value": B * e2e_steps / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "ssdseglib.evaluators.true_positives_and_counts(NumPy in, NumPy out"
+                           + (", process_group=WORLD)" if world > 1 else ")")},
+            "gpu_launches": (3 + (1 if world > 1 else 0)) * args.steps,  # eval_tp, AP keys + AP integrate (+ sum_counts)
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import c_oracle
+
+            threads = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            passes = 0
+            while time.perf_counter() - t0 < 10.0:
+                tpc, cc = c_oracle.eval_tp(pl, pb, gb, gl, gc, C, 0, EVAL_THR, nthreads=threads)
+                orc.average_precision_from_tp(tpc, conf, pl, {c: int(cc[c, 2]) for c in range(1, C)})
+                passes += 1
+            secs = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": passes * B / secs, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": f"{passes} passes over all {B} images ({secs:.1f} s of host work): C/OpenMP "
+                                              f"TP/FP pass on {threads} threads + NumPy AP tail"}
+        print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
+    _dist.close_communicators()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -542,23 +800,13 @@ def gpu_arm(args, rank, world, local_rank):
             pass
         stage_roof = {s: {"ms": stage_ms[s], "gbs": BYTES_PER_IMAGE[s] * B / (stage_ms[s] / 1e3) / 1e9,
                           "frac": BYTES_PER_IMAGE[s] * B / (stage_ms[s] / 1e3) / 1e9 / peak} for s in stages}
-        kernels = {"encode": "ssdx_encode_fused_kernel", "decode": "ssdx_decode_kernel",
+        kernels = {"encode": "ssdx_encode_grid_fused_kernel", "decode": "ssdx_decode_kernel",
                    "nms": "ssdx_nms_select_all_kernel + ssdx_nms_fast_all_kernel"}
         line = {
             "metric": "images/sec encode+decode+NMS", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "stages": list(stages), "images_per_gpu": B, "global_batch": B * world,
-                       "anchors": A_STD, "gt_per_image": G_STD, "classes": C_STD, "max_total": K_STD,
-                       "score_thr": 0.01, "iou_thr": 0.45, "parallelism": f"batch-sharded x{world}, no collective",
-                       "l2": "no flush: each step streams %.0f MB (> 126 MB L2)" % (
-                           sum(BYTES_PER_IMAGE[s] for s in stages) * B / 1e6),
-                       "launch": ("eager" if graph is None else "one CUDA graph per step") + (
-                           "" if args.no_overlap else (
-                               "; NMS candidate selection (ssdx_nms_select) on a second stream, concurrent with "
-                               "encode/decode, joined before ssdx_nms_finish" if n_pipe == 1 else
-                               f"; {n_pipe} sub-batches of {B // n_pipe} images pipelined on {n_streams} streams")),
-                       "oracle_check": check},
+            "config": roundtrip_config(args, world), "oracle_check": check, "graph_captured": graph is not None,
             "roofline": {"bound": "hbm", "kernel": kernels[dom], "stage": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "stages": stage_roof,
@@ -623,7 +871,10 @@ def main():
                    ["--pipeline-split", args.pipeline_split] if args.pipeline_split else []) + (
                    ["--no-numa"] if args.no_numa else [])
         raise SystemExit(subprocess.call(cmd))
-    gpu_arm(args, rank, world, local_rank)
+    if args.workload == "eval_b4096":
+        gpu_arm_eval(args, rank, world, local_rank)
+    else:
+        gpu_arm(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

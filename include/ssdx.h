@@ -47,7 +47,7 @@ extern "C" {
 #define SSDX_ERR_INVALID (-1)   /* bad argument (mirrors the reference's ValueError sites) */
 #define SSDX_ERR_CUDA (-2)      /* CUDA runtime / launch failure */
 #define SSDX_ERR_WORKSPACE (-3) /* caller workspace too small */
-#define SSDX_ERR_NCCL (-4)      /* collective failure (host side, see ssdseglib/_dist.py) */
+#define SSDX_ERR_NCCL (-4)      /* NCCL missing in the process, or a collective / communicator call failed */
 
 typedef struct ssdx_anchors ssdx_anchors; /* opaque, device-resident anchor table */
 typedef void* ssdx_stream;                /* cudaStream_t */
@@ -176,6 +176,27 @@ SSDX_API int ssdx_eval_tp(const int32_t* pred_label, const float* pred_xyxy, con
                  const int32_t* gt_count, int32_t batch, int32_t k, int32_t gmax, int32_t num_classes,
                  int32_t background_label, float iou_threshold, uint8_t* out_tp, int64_t* counts, int device,
                  ssdx_stream stream);
+
+/* ---- the one collective of the path: all-gather of the per-rank (C,3) count tables (BASELINE config 5) ----
+ * Evaluation shards the images over the ranks of one box (evaluators.py:106-157 per shard, no communication); the
+ * (TP, FP, n_gt) tables are then gathered over NCCL so that every rank can form the global counts that
+ * evaluators.py:159-187 integrates.  libssdx binds to the NCCL already loaded in the process (libnccl.so.2, or
+ * $SSDX_NCCL_LIB) at first use - no link-time dependency; without NCCL these four calls return SSDX_ERR_NCCL.
+ *   ssdx_comm_unique_id : rank 0 draws the 128-byte NCCL unique id and hands it to the other ranks out of band
+ *                         (the Python mirror broadcasts it with torch.distributed);
+ *   ssdx_comm_create    : collective over the nranks ranks (ncclCommInitRank), one communicator per (process, device);
+ *   ssdx_allgather_counts: counts (C,3) i64 device -> gathered (nranks,C,3) i64 device, rank-major; stream-ordered
+ *                         (ncclAllGather on `stream`), every rank of the communicator must call it. */
+typedef struct ssdx_comm ssdx_comm;
+SSDX_API int ssdx_nccl_version(int* version);
+SSDX_API int ssdx_comm_unique_id(uint8_t* id128);
+SSDX_API int ssdx_comm_create(const uint8_t* id128, int32_t nranks, int32_t rank, int device, ssdx_comm** out);
+SSDX_API int ssdx_comm_destroy(ssdx_comm* comm);
+SSDX_API int ssdx_allgather_counts(ssdx_comm* comm, const int64_t* counts, int64_t* gathered, int32_t num_classes,
+                                   ssdx_stream stream);
+/* out (C,3) i64 = sum over the nranks tables of gathered (nranks,C,3): the global counts on every rank. */
+SSDX_API int ssdx_sum_counts(const int64_t* gathered, int32_t nranks, int32_t num_classes, int64_t* out, int device,
+                             ssdx_stream stream);
 
 /* ---- average precision: evaluators.py:159-187 (the tail of average_precision_object_detection), SURVEY 8(f) row 4 ----
  * tp (N) u8, confidence (N) f32, label (N) i32 class indices: every prediction of the data set, flattened;

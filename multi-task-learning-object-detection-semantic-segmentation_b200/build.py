@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libssdx.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["capi.cu", "decode.cu", "encode.cu", "encode_grid.cu", "nms.cu", "eval.cu", "seg.cu", "metric.cu", "ap.cu", "loss.cu"]
+SOURCES = ["capi.cu", "decode.cu", "encode.cu", "encode_grid.cu", "nms.cu", "eval.cu", "seg.cu", "metric.cu", "ap.cu", "loss.cu", "comm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -96,7 +96,7 @@ def _compile(out: str, verbose: bool, extra) -> str:
     if any(r[1] != 0 for r in results):
         raise RuntimeError("nvcc failed building " + os.path.basename(out))
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static", "-Xcompiler", "-fPIC",
-           "-o", out] + [r[0] for r in results]
+           "-ldl", "-o", out] + [r[0] for r in results]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

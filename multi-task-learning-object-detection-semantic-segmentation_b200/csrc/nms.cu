@@ -1730,9 +1730,6 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   }
   SSDX_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "ssdx_nms: workspace must be 256-byte aligned");
   const size_t gen_smem = gen_smem_bytes(A, limit);
-  SSDX_CHECK_ARG(gen_smem <= 227 * 1024,
-                 "ssdx_nms: num_anchors=%d with max_per_class=%d needs %zu B of shared memory (limit 232448)", A,
-                 max_per_class, gen_smem);
   SSDX_DEVICE(device);
   cudaStream_t s = (cudaStream_t)stream;
   char* base = (char*)workspace;
@@ -1750,9 +1747,6 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   // one applies.  All paths give identical results.
   const char* force = ssdx_option_nms_path();
   const bool force_generic = force != nullptr && force[0] == 'g';
-  const size_t gen_smem_attr = gen_smem;
-  SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)gen_smem_attr));
   const int num_segments = batch * C;
   const size_t merge_smem = (size_t)C * limit * sizeof(u64);
   const int stage = merge_smem <= 96 * 1024;
@@ -1797,6 +1791,13 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   }
 
   // ---- per-class pipeline ----
+  // (the generic kernel that stands behind it keeps 4 bytes per anchor in shared memory; the merged pipeline above
+  // never hands over to it, so only this pipeline is bounded by that)
+  SSDX_CHECK_ARG(gen_smem <= 227 * 1024,
+                 "ssdx_nms: num_anchors=%d with max_per_class=%d needs %zu B of shared memory (limit 232448)", A,
+                 max_per_class, gen_smem);
+  SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gen_smem));
   // 1. select
   const bool use_fast = !force_generic;
   // first tier of a dense class: ~16 * rank candidates, sized to the per-class cap (a tier that runs dry is refilled

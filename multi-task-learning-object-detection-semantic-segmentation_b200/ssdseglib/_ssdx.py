@@ -60,6 +60,12 @@ SIGNATURES = {
     "ssdx_scale_scores": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int, _vp]),
     "ssdx_eval_tp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, _vp, _vp, C.c_int, _vp]),
+    "ssdx_nccl_version": (C.c_int, [C.POINTER(C.c_int)]),
+    "ssdx_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "ssdx_comm_create": (C.c_int, [C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int, C.POINTER(_vp)]),
+    "ssdx_comm_destroy": (C.c_int, [_vp]),
+    "ssdx_allgather_counts": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp]),
+    "ssdx_sum_counts": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
     "ssdx_average_precision_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "ssdx_average_precision": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, _vp, C.c_size_t,
                                          C.c_int, _vp]),
@@ -85,7 +91,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-SSDX_ERR_INVALID, SSDX_ERR_CUDA, SSDX_ERR_WORKSPACE = -1, -2, -3
+SSDX_ERR_INVALID, SSDX_ERR_CUDA, SSDX_ERR_WORKSPACE, SSDX_ERR_NCCL = -1, -2, -3, -4
 DECODE_YXYX, DECODE_CENTROIDS_MASKED, DECODE_CORNERS_MASKED = 0, 1, 2
 
 
@@ -487,6 +493,9 @@ def eval_tp(pred_label, pred_xyxy, gt_xyxy, gt_label, gt_count, num_classes: int
     torch = _torch()
     B, K = int(pred_label.shape[0]), int(pred_label.shape[1])
     G = int(gt_xyxy.shape[1])
+    if not (int(gt_count.shape[0]) == B and int(gt_xyxy.shape[0]) == B and int(gt_label.shape[0]) == B
+            and int(pred_xyxy.shape[0]) == B):
+        raise ValueError(f"eval_tp: {B} prediction rows but {int(gt_count.shape[0])} ground-truth rows")
     dev = pred_label.device.index
     tp = empty((B, K), np.uint8, dev)
     if counts is None:

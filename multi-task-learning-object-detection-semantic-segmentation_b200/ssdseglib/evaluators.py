@@ -93,11 +93,15 @@ def average_precision_object_detection(
     Raises KeyError for a ground-truth or predicted label that is not in `labels_codes` or is the
     background (the reference's dictionaries do the same)."""
     labels_pred_batch = np.asarray(labels_pred_batch)
-    n = labels_pred_batch.shape[0]
-    lp = labels_pred_batch.reshape(n, -1).astype(np.int32)
-    conf = np.asarray(confidences_pred_batch, dtype=np.float32).reshape(n, -1)
-    bp = np.asarray(boxes_pred_batch, dtype=np.float32).reshape(n, -1, 4)
+    n_pred = labels_pred_batch.shape[0]
+    # the reference zips predictions with paths (evaluators.py:106): the shorter of the two decides
+    n = min(n_pred, len(path_files_labels_boxes))
+    lp = labels_pred_batch.reshape(n_pred, -1).astype(np.int32)[:n]
+    conf = np.asarray(confidences_pred_batch, dtype=np.float32).reshape(n_pred, -1)[:n]
+    bp = np.asarray(boxes_pred_batch, dtype=np.float32).reshape(n_pred, -1, 4)[:n]
     foreground = [l for l in labels_codes if l != label_code_background]
+    if n == 0:
+        return {l: 0.0 for l in foreground}
     gl, gb, gc = read_ground_truth(path_files_labels_boxes[:n])
     valid = np.arange(gl.shape[1])[None, :] < gc[:, None]
     for l in np.unique(gl[valid]):

@@ -16,20 +16,44 @@ LIB = os.path.join(HERE, "_build", "liboracle.so")
 _lib = None
 
 
+CFLAGS = ["-O3", "-march=native", "-ffp-contract=off", "-fno-fast-math"]  # one rounding per fp32 op (no FMA contraction)
+
+
+def _cpu_stamp() -> str:
+    """-march=native code only runs on the CPU it was built for: the library is rebuilt when the host changes
+    (the build container and the GPU box need not have the same CPU)."""
+    import hashlib
+
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1((flags + " ".join(CFLAGS)).encode()).hexdigest()
+
+
 def build(force: bool = False) -> str:
-    """gcc -O2 -fopenmp ... (see Makefile).  Tries the system gcc first (an image-provided $CC may lack
-    libgomp) and falls back to a single-threaded build if no compiler has OpenMP."""
+    """gcc -O3 -march=native -fopenmp -ffp-contract=off ....  Tries the system gcc first (an
+    image-provided $CC may lack libgomp) and falls back to a single-threaded build if no compiler has OpenMP."""
     src = os.path.join(HERE, "ssd_oracle.c")
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
+    stamp_file = LIB + ".stamp"
+    stamp = _cpu_stamp()
+    try:
+        with open(stamp_file) as f:
+            same_host = f.read().strip() == stamp
+    except OSError:
+        same_host = False
+    if not force and same_host and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    base = ["-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-fvisibility=hidden", "-o", LIB, src,
-            "-lm"]
+    base = CFLAGS + ["-fPIC", "-shared", "-fvisibility=hidden", "-o", LIB, src, "-lm"]
     err = ""
     for omp in (["-fopenmp"], []):
         for cc in ("/usr/bin/gcc", "gcc", "cc", os.environ.get("CC") or "gcc"):
             r = subprocess.run([cc] + omp + base, capture_output=True, text=True)
             if r.returncode == 0:
+                with open(stamp_file, "w") as f:
+                    f.write(stamp)
                 return LIB
             err = r.stderr
     raise RuntimeError("could not build oracle/ssd_oracle.c: " + err)
@@ -38,8 +62,7 @@ def build(force: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()
         _lib = C.CDLL(LIB)
     return _lib
 
@@ -93,12 +116,12 @@ def combined_nms(boxes_yxyx, scores, max_per_class, max_total, iou_thr, score_th
     return out, valid, aidx
 
 
-def eval_tp(pred_label, pred_xyxy, gt_xyxy, gt_label, gt_count, num_classes, bg, thr):
+def eval_tp(pred_label, pred_xyxy, gt_xyxy, gt_label, gt_count, num_classes, bg, thr, nthreads=0):
     pl, pb, gb, gl, gc = _i32(pred_label), _f32(pred_xyxy), _f32(gt_xyxy), _i32(gt_label), _i32(gt_count)
     B, K = pl.shape
     G = gb.shape[1]
     tp = np.empty((B, K), np.uint8)
     counts = np.zeros((num_classes, 3), np.int64)
     lib().oracle_eval_tp(_p(pl), _p(pb), _p(gb), _p(gl), _p(gc), B, K, G, int(num_classes), int(bg),
-                         C.c_float(np.float32(thr)), _p(tp), _p(counts), 1)
+                         C.c_float(np.float32(thr)), _p(tp), _p(counts), int(nthreads) or (os.cpu_count() or 1))
     return tp, counts

@@ -203,34 +203,49 @@ EXPORT void oracle_combined_nms(const float* boxes /*B,A,4 yxyx*/, const float* 
 EXPORT void oracle_eval_tp(const int32_t* plab /*B,K*/, const float* pbox /*B,K,4*/, const float* gbox /*B,G,4*/,
                            const int32_t* glab, const int32_t* gcnt, int B, int K, int Gmax, int C, int bg, float thr,
                            uint8_t* tp /*B,K*/, int64_t* counts /*C,3*/, int nthreads) {
-  (void)nthreads;
-  for (int b = 0; b < B; ++b) {
-    const int G = gcnt[b];
-    for (int g = 0; g < G; ++g) {
-      const int l = glab[(size_t)b * Gmax + g];
-      if (l >= 0 && l < C) counts[3 * l + 2] += 1;
-    }
-    for (int k = 0; k < K; ++k) {
-      const int pl = plab[(size_t)b * K + k];
-      uint8_t flag = 0;
-      if (pl != bg) {
-        const float* p = pbox + ((size_t)b * K + k) * 4;
-        const float pa = (p[2] - p[0] + 1.0f) * (p[3] - p[1] + 1.0f);
-        float best = (G == 0) ? 0.0f : -INFINITY;
-        for (int g = 0; g < G; ++g) {
-          const float* t = gbox + ((size_t)b * Gmax + g) * 4;
-          const float ta = (t[2] - t[0] + 1.0f) * (t[3] - t[1] + 1.0f);
-          const float iw = fmax2(0.0f, fmin2(p[2], t[2]) - fmax2(p[0], t[0]) + 1.0f);
-          const float ih = fmax2(0.0f, fmin2(p[3], t[3]) - fmax2(p[1], t[1]) + 1.0f);
-          const float inter = iw * ih;
-          float iou = inter / (pa + ta - inter + 1e-7f);
-          iou = iou * ((glab[(size_t)b * Gmax + g] == pl) ? 1.0f : 0.0f);
-          if (iou > best) best = iou;
-        }
-        flag = best >= thr;
-        if (pl >= 0 && pl < C) counts[3 * pl + (flag ? 0 : 1)] += 1;
+  /* images are independent (evaluators.py:106); the integer counts are summed per thread and added at the end */
+  if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+  {
+    int64_t* local = (int64_t*)calloc((size_t)3 * C, sizeof(int64_t));
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (int b = 0; b < B; ++b) {
+      const int G = gcnt[b];
+      for (int g = 0; g < G; ++g) {
+        const int l = glab[(size_t)b * Gmax + g];
+        if (l >= 0 && l < C) local[3 * l + 2] += 1;
       }
-      tp[(size_t)b * K + k] = flag;
+      for (int k = 0; k < K; ++k) {
+        const int pl = plab[(size_t)b * K + k];
+        uint8_t flag = 0;
+        if (pl != bg) {
+          const float* p = pbox + ((size_t)b * K + k) * 4;
+          const float pa = (p[2] - p[0] + 1.0f) * (p[3] - p[1] + 1.0f);
+          float best = (G == 0) ? 0.0f : -INFINITY;
+          for (int g = 0; g < G; ++g) {
+            const float* t = gbox + ((size_t)b * Gmax + g) * 4;
+            const float ta = (t[2] - t[0] + 1.0f) * (t[3] - t[1] + 1.0f);
+            const float iw = fmax2(0.0f, fmin2(p[2], t[2]) - fmax2(p[0], t[0]) + 1.0f);
+            const float ih = fmax2(0.0f, fmin2(p[3], t[3]) - fmax2(p[1], t[1]) + 1.0f);
+            const float inter = iw * ih;
+            float iou = inter / (pa + ta - inter + 1e-7f);
+            iou = iou * ((glab[(size_t)b * Gmax + g] == pl) ? 1.0f : 0.0f);
+            if (iou > best) best = iou;
+          }
+          flag = best >= thr;
+          if (pl >= 0 && pl < C) local[3 * pl + (flag ? 0 : 1)] += 1;
+        }
+        tp[(size_t)b * K + k] = flag;
+      }
     }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+    for (int i = 0; i < 3 * C; ++i) counts[i] += local[i];
+    free(local);
   }
 }

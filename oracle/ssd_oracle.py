@@ -571,6 +571,40 @@ def average_precision(labels_pred_batch, confidences_pred_batch, boxes_pred_batc
     return ap
 
 
+def average_precision_from_tp(tp, confidences, labels_pred, n_gt_per_label: Dict[int, int]) -> Dict[int, float]:
+    """evaluators.py:159-187 on flat arrays of TP flags (the per-image part, :106-157, already done): per class,
+    argsort(conf)[::-1], precision = cumsum(tp) / rank, recall = cumsum(tp) / n_gt, np.trapz(precision, recall) with
+    no (0, .) sentinel; 0.0 for a class without ground truth or without predictions."""
+    tp = np.asarray(tp).reshape(-1)
+    conf = np.asarray(confidences, dtype=F32).reshape(-1)
+    lab = np.asarray(labels_pred).reshape(-1)
+    ap = {}
+    for l, n_gt in n_gt_per_label.items():
+        sel = lab == l
+        if n_gt == 0 or not sel.any():
+            ap[l] = 0.0
+            continue
+        order = np.argsort(conf[sel])[::-1]
+        t = tp[sel][order].astype(F32)
+        prec = np.cumsum(t) / np.arange(1, len(t) + 1)
+        rec = np.cumsum(t) / n_gt
+        ap[l] = float(np.sum((rec[1:] - rec[:-1]) * (prec[1:] + prec[:-1]) / 2.0))
+    return ap
+
+
+def synth_eval(rng, B, K=200, G=16, C=4, jitter=8.0):
+    """BASELINE config 5 inputs: GT boxes of the config-1 generator; predictions in the NMS output layout - K rows
+    per image = a GT box of the image jittered by N(0, jitter) px, labels U{0..C-1} (0 = background rows), distinct
+    confidences (the tie order of the reference's argsort is unspecified)."""
+    labels, boxes, counts = synth_gt(rng, B, G)
+    pl = rng.integers(0, C, size=(B, K)).astype(np.int32)
+    src = rng.integers(0, G, size=(B, K))
+    pb = (np.take_along_axis(boxes, src[..., None].repeat(4, -1), axis=1)
+          + rng.normal(0, jitter, size=(B, K, 4))).astype(F32)
+    conf = (rng.permutation(B * K).astype(np.float64) / float(B * K)).astype(F32).reshape(B, K)
+    return pl, conf, pb, labels, boxes, counts
+
+
 # --------------------------------------------------------------------------
 # SURVEY.md 8(d) synthetic generators (seeded)
 # --------------------------------------------------------------------------

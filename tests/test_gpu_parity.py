@@ -887,3 +887,194 @@ def test_error_paths_and_workspace(lib, coder):
     assert s.lib.ssdx_encode_workspace_bytes(9600, 2, 4) >= 2 * 9600 * 4 + 2 * 4 * 8
     n = C.c_int(0)
     assert s.lib.ssdx_device_count(C.byref(n)) == 0 and n.value >= 1
+
+
+# ------------------------------------------------------------------------------------------- BASELINE configs, full batch
+def test_encode_stress_config_full_batch(lib, encode_path):
+    """BASELINE config 3 (dense stress: 100,000 anchors x 256 GT boxes, batch 256) - EVERY image against the C oracle:
+    matched indices and labels bit-exact, offsets within 1e-5 relative.  (The 25.6 M-pair IoU matrix per image is
+    what the oracle computes; the device evaluates ~72 k window cells per image on the grid drivers.)"""
+    if encode_path == "tile_fused":
+        pytest.skip("100k anchors do not fit one CTA per image: same launch as tile_tiled")
+    import os
+
+    from oracle import c_oracle
+
+    anchors = orc.anchors_generate(**orc.STRESS_ANCHOR_CFG)
+    rng = np.random.default_rng(1996)
+    B, G = 256, 256
+    labels, boxes, counts = orc.synth_gt(rng, B, G, image_hw=(1000, 1280))
+    c = lib.datacoder.DataEncoderDecoder(4, (1000, 1280), anchors[:, 0], anchors[:, 1], anchors[:, 2], anchors[:, 3])
+    import torch
+
+    gb, gl, gc = (torch.from_numpy(x).cuda() for x in (boxes, labels, counts))
+    for lo in range(0, B, 64):  # 64 images at a time: 64 x 100k x (4 + 4 + 1) floats per chunk on either side
+        L, O, M = c.encode_batch(gb[lo:lo + 64], gl[lo:lo + 64], gc[lo:lo + 64], return_match=True)
+        Lr, Or, Mr = c_oracle.encode_batch(anchors, labels[lo:lo + 64], boxes[lo:lo + 64], counts[lo:lo + 64], 4, 0.5,
+                                           STD, nthreads=os.cpu_count() or 1)
+        assert np.array_equal(M.cpu().numpy(), Mr), f"matched indices differ in images {lo}..{lo + 63}"
+        assert np.array_equal(L.cpu().numpy(), Lr)
+        assert_offsets_close(O.cpu().numpy(), Or)
+
+
+def test_eval_config_full_batch(lib):
+    """BASELINE config 5 inputs (4096 images x 200 detections, 16 GT boxes): TP flags and per-class counts of ALL images
+    against the C oracle, AP at 0.5 / 0.6 / 0.7 (03-...ipynb cell 29) against the NumPy restatement of
+    evaluators.py:159-187."""
+    import torch
+
+    from oracle import c_oracle
+
+    B, K, G, C = 4096, 200, 16, 4
+    pl, conf, pb, gl, gb, gc = orc.synth_eval(np.random.default_rng(1997), B, K, G, C)
+    d = [torch.from_numpy(x).cuda() for x in (pl, pb, gb, gl, gc, conf)]
+    for thr in (0.5, 0.6, 0.7):
+        tp, counts = lib._ssdx.eval_tp(d[0], d[1], d[2], d[3], d[4], C, 0, thr)
+        ref_tp, ref_counts = c_oracle.eval_tp(pl, pb, gb, gl, gc, C, 0, thr)
+        assert np.array_equal(tp.cpu().numpy(), ref_tp) and np.array_equal(counts.cpu().numpy(), ref_counts)
+        ap = lib._ssdx.average_precision(tp.reshape(-1), d[5].reshape(-1), d[0].reshape(-1), counts, C, 0).cpu().numpy()
+        ref_ap = orc.average_precision_from_tp(ref_tp, conf, pl, {c: int(ref_counts[c, 2]) for c in range(1, C)})
+        for c in range(1, C):
+            assert abs(ap[c] - ref_ap[c]) < 1e-9, (thr, c, ap[c], ref_ap[c])
+
+
+def test_encode_decode_centroid_constructor_and_feature_map_inputs(lib, std_anchors):
+    """DataEncoderDecoder built from centroids (datacoder.py:73-89: the corners are then DERIVED, a different fp32
+    table) and from the getters' 'feature-maps' style outputs flattened as notebook 03 cell 6 does."""
+    dbb = lib.boxes.DefaultBoundingBoxes(
+        feature_maps_shapes=((30, 40), (15, 20), (8, 10), (4, 5)),
+        centers_padding_from_borders_percentage=(0.025, 0.05, 0.075, 0.1), boxes_scales=(0.15, 0.95),
+        additional_square_box=True)
+    dbb.rescale_boxes_coordinates((480, 640))
+    cx, cy, w, h = dbb.get_boxes_coordinates_centroids("ssd").T
+    coder = lib.datacoder.DataEncoderDecoder(4, (480, 640), center_x_boxes_default=cx, center_y_boxes_default=cy,
+                                             width_boxes_default=w, height_boxes_default=h, iou_threshold=0.5)
+    derived = np.stack(orc.centroids_to_corners(cx, cy, w, h), 1).astype(np.float32)  # datacoder.py:84-89
+    assert not np.array_equal(derived, std_anchors)  # a few coordinates move by an ulp: not the corner-built table
+    assert np.array_equal(np.stack([coder.xmin_boxes_default, coder.ymin_boxes_default, coder.xmax_boxes_default,
+                                    coder.ymax_boxes_default], 1), derived)
+    rng = np.random.default_rng(8)
+    labels, boxes, counts = orc.synth_gt(rng, 160, 16, integer=True)
+    L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(derived, labels, boxes, counts, 4, 0.5)
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+    cent = np.stack([cx, cy, w, h], 1).astype(np.float32)  # decode uses the centroids as passed (datacoder.py:78-81)
+    assert_coords_close(coder.decode_to_corners(O[5]), orc.decode_to_corners(Or[5], cent, STD), cent[:, 2:])
+    assert_coords_close(coder.decode_to_centroids(O[5]), orc.decode_to_centroids(Or[5], cent, STD), cent[:, 2:])
+    # 'feature-maps' style getters: per-map (H, W, nb, 4) arrays, flattened map-major -> the same 'ssd' table
+    fm = dbb.get_boxes_coordinates_corners("feature-maps")
+    flat = np.concatenate([m.reshape(-1, 4) for m in fm], axis=0)
+    assert np.array_equal(flat, std_anchors)
+    c2 = lib.datacoder.DataEncoderDecoder(4, (480, 640), flat[:, 0], flat[:, 1], flat[:, 2], flat[:, 3])
+    L2, O2, M2 = c2.encode_batch(boxes[:8], labels[:8], counts[:8], return_match=True)
+    Lr2, Or2, Mr2 = encode_ref(std_anchors, labels[:8], boxes[:8], counts[:8], 4, 0.5)
+    assert np.array_equal(M2, Mr2) and np.array_equal(L2, Lr2)
+    assert_offsets_close(O2, Or2)
+
+
+def test_encode_many_positives_overflow_path(lib, coder, std_anchors, encode_path):
+    """More positives per image than the fused grid driver's slot table holds (threshold 0.05: thousands of anchors
+    above it) - the exact per-anchor loop takes over; also G = 256, the most GT boxes one CTA stages."""
+    rng = np.random.default_rng(31)
+    labels, boxes, counts = orc.synth_gt(rng, 150, 16)
+    c = lib.datacoder.DataEncoderDecoder(4, (480, 640), std_anchors[:, 0], std_anchors[:, 1], std_anchors[:, 2],
+                                         std_anchors[:, 3], iou_threshold=0.05)
+    L, O, M = c.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(std_anchors, labels, boxes, counts, 4, 0.05)
+    assert (Mr >= 0).sum(axis=1).max() > 1024
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+    labels, boxes, counts = orc.synth_gt(rng, 150, 256, wh_range=(10.0, 200.0))
+    counts[::3] = rng.integers(0, 257, size=len(counts[::3]))
+    L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(std_anchors, labels, boxes, counts, 4, 0.5)
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
+
+
+# ------------------------------------------------------------------------------------------- the collective (NCCL)
+def test_all_gather_counts_over_nccl(lib, tmp_path):
+    """ssdx_allgather_counts on a real NCCL communicator: one rank per visible GPU (at most 2), launched like the
+    bench; with a single GPU the world has one rank (NCCL still runs the collective on the device)."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    import torch
+
+    world = min(torch.cuda.device_count(), 2)
+    pkg = os.path.dirname(os.path.dirname(os.path.abspath(lib.__file__)))
+    script = tmp_path / "rank.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {pkg!r})
+        import torch, torch.distributed as dist
+        local = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{{local}}"))
+        import ssdseglib
+        from ssdseglib import _dist, _ssdx
+        r, w = dist.get_rank(), dist.get_world_size()
+        ver = _ssdx.C.c_int(0)
+        _ssdx.check(_ssdx.lib.ssdx_nccl_version(_ssdx.C.byref(ver)))
+        assert ver.value >= 20000, ver.value
+        lo, hi = _dist.shard_range(10, r, w)
+        counts = torch.tensor([[r + 1, 10 * (r + 1), hi - lo]] * 4, dtype=torch.int64, device=f"cuda:{{local}}")
+        for _ in range(3):  # the first call creates the communicator (collective), the next ones reuse it
+            g = _dist.all_gather_counts(counts)
+        assert g.is_cuda and g.shape == (w, 4, 3)
+        tot = g.sum(0).cpu()
+        assert tot[0].tolist() == [w * (w + 1) // 2, 10 * w * (w + 1) // 2, 10], tot
+        assert g[r].cpu().tolist() == counts.cpu().tolist()
+        # through the public evaluation entry point: counts summed over the ranks
+        import numpy as np
+        rng = np.random.default_rng(5 + r)
+        pl = rng.integers(0, 4, size=(8, 20)).astype(np.int32)
+        gb = rng.uniform(0, 300, size=(8, 6, 4)).astype(np.float32); gb[..., 2:] += gb[..., :2]
+        pb = np.repeat(gb[:, :1], 20, axis=1) + rng.normal(0, 6, size=(8, 20, 4)).astype(np.float32)
+        gl = rng.integers(1, 4, size=(8, 6)).astype(np.int32); gc = np.full(8, 6, np.int32)
+        tp, c_all = ssdseglib.evaluators.true_positives_and_counts(pl, pb, gl, gb, gc, 0.5, 4, 0,
+                                                                   process_group=dist.group.WORLD)
+        tp1, c_one = ssdseglib.evaluators.true_positives_and_counts(pl, pb, gl, gb, gc, 0.5, 4, 0)
+        mine = torch.from_numpy(np.asarray(c_one)).cuda()
+        dist.all_reduce(mine)
+        assert np.array_equal(np.asarray(c_all), mine.cpu().numpy()) and np.array_equal(tp, tp1)
+        assert torch.cuda.current_device() == local
+        _dist.close_communicators()
+        dist.barrier()
+        if r == 0:
+            print("NCCL_GATHER_OK world", w)
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and f"NCCL_GATHER_OK world {world}" in r.stdout, r.stdout + r.stderr
+
+
+def test_entry_points_leave_the_current_device_alone(lib, std_anchors, golden):
+    """A process that drives two GPUs from one thread: calls on device 1 must not change the thread's current device
+    (every entry point saves and restores it)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    coder1 = lib.datacoder.DataEncoderDecoder(4, (480, 640), std_anchors[:, 0], std_anchors[:, 1], std_anchors[:, 2],
+                                              std_anchors[:, 3], device=1)
+    assert torch.cuda.current_device() == 0
+    rng = np.random.default_rng(2)
+    labels, boxes, counts = orc.synth_gt(rng, 4, 16)
+    gb, gl, gc = (torch.from_numpy(x).to("cuda:1") for x in (boxes, labels, counts))
+    L, O = coder1.encode_batch(gb, gl, gc)
+    assert torch.cuda.current_device() == 0 and L.device.index == 1
+    yx = coder1._decode(O, 0)
+    assert torch.cuda.current_device() == 0
+    nms = lib.layers.NonMaximumSuppression(200, 200, 0.45, 0.01, False)
+    det = nms(yx, L)
+    assert torch.cuda.current_device() == 0 and det.device.index == 1
+    Lr, Or, _ = encode_ref(std_anchors, labels, boxes, counts, 4, 0.5)
+    assert np.array_equal(L.cpu().numpy(), Lr)
