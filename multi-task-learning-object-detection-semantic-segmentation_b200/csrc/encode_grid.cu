@@ -274,6 +274,16 @@ __host__ __device__ inline size_t grid_fused_smem_bytes(int A, int G, int C, int
   return n + 16;
 }
 
+__device__ __forceinline__ float4 one_hot4(const int lab) {  // tf.one_hot(lab, 4): all-zero row outside [0, 4)
+  return make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f, lab == 3 ? 1.f : 0.f);
+}
+// two adjacent 16-byte rows = one 32-byte sector, p 32-byte aligned: one 256-bit store
+__device__ __forceinline__ void st_stream_sector(float4* p, const float4 lo, const float4 hi) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z),
+               "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
+               : "memory");
+}
+
 // cell code of (grid q, row r, col c): q < 256, r, c < 4096 (ssdx_anchors_create keeps grids within that)
 __device__ __forceinline__ unsigned cell_code(const int q, const int r, const int c) {
   return ((unsigned)q << 24) | ((unsigned)r << 12) | (unsigned)c;
@@ -672,20 +682,59 @@ __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
 
       // ---- encode the positives densely and patch them over the background ----
       unsigned short* s_tab = s_slot;  // overflow path only: anchor -> matched GT
+      // A positive row is 16 bytes (offsets; labels when C == 4), half of a 32-byte DRAM sector.  A 16-byte patch
+      // leaves a partially written sector behind, which the memory side completes with a read-modify-write - with
+      // ~360 of them per image the kernel ran 66 us per 1024 images instead of 56.  So the patch is the whole
+      // sector: the positive row and its neighbour a ^ 1 (background, or positive itself - then the lower anchor of
+      // the pair writes both rows), one 32-byte store when the image base is 32-byte aligned.
+      const bool pair_ok = ((((size_t)b * A) & 1) == 0);  // rows a & ~1 and a | 1 share a sector
+      auto matched_gt = [&](const int a) -> int {  // matched GT box of anchor a, -1 = background
+        const unsigned short m = s_slot[a];
+        if (m == kNone) return -1;
+        return overflow ? (int)m : (int)s_cg[m];
+      };
       auto emit_positive = [&](const int a, const float4 ab, const int g) {
-        st_stream_f4(offs + a, pair_offsets(s_box[g], anchor_centroid(ab), sx, sy, sw, sh));
+        const float4 off_a = pair_offsets(s_box[g], anchor_centroid(ab), sx, sy, sw, sh);
+        const int lab_a = s_lab[g];
+        if (out_match) out_match[(size_t)b * A + a] = g;
+        const int nb = a ^ 1;
+        if (!pair_ok || nb >= A) {  // no sector partner: plain 16-byte rows
+          st_stream_f4(offs + a, off_a);
+          if (bulk_lab) {
+            if (C == 4) {
+              st_stream_f4(reinterpret_cast<float4*>(labs) + a, one_hot4(lab_a));
+            } else {  // the background row is [1,0,...]; a label outside [0,C) gives an all-zero row (tf.one_hot)
+              labs[(size_t)a * C] = (lab_a == 0) ? 1.0f : 0.0f;
+              if (lab_a > 0 && lab_a < C) labs[(size_t)a * C + lab_a] = 1.0f;
+            }
+          }
+          return;
+        }
+        const int g_nb = matched_gt(nb);
+        if (g_nb >= 0 && nb < a) return;  // both rows positive: the lower anchor writes the sector
+        float4 off_nb = make_float4(0.f, 0.f, 0.f, 0.f);
+        int lab_nb = 0;
+        if (g_nb >= 0) {
+          off_nb = pair_offsets(s_box[g_nb], anchor_centroid(anchor_box_by_index(s_combo, nq, s_ax, nb)), sx, sy, sw,
+                                sh);
+          lab_nb = s_lab[g_nb];
+          if (out_match) out_match[(size_t)b * A + nb] = g_nb;
+        }
+        const int lo = a & ~1;
+        st_stream_sector(offs + lo, a == lo ? off_a : off_nb, a == lo ? off_nb : off_a);
         if (bulk_lab) {
-          const int lab = s_lab[g];
           if (C == 4) {
-            const float4 oh = make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f,
-                                          lab == 3 ? 1.f : 0.f);
-            st_stream_f4(reinterpret_cast<float4*>(labs) + a, oh);
-          } else {  // the background row is [1,0,...]; a label outside [0,C) gives an all-zero row (tf.one_hot)
-            labs[(size_t)a * C] = (lab == 0) ? 1.0f : 0.0f;
-            if (lab > 0 && lab < C) labs[(size_t)a * C + lab] = 1.0f;
+            st_stream_sector(reinterpret_cast<float4*>(labs) + lo, one_hot4(a == lo ? lab_a : lab_nb),
+                             one_hot4(a == lo ? lab_nb : lab_a));
+          } else {
+            labs[(size_t)a * C] = (lab_a == 0) ? 1.0f : 0.0f;
+            if (lab_a > 0 && lab_a < C) labs[(size_t)a * C + lab_a] = 1.0f;
+            if (g_nb >= 0) {
+              labs[(size_t)nb * C] = (lab_nb == 0) ? 1.0f : 0.0f;
+              if (lab_nb > 0 && lab_nb < C) labs[(size_t)nb * C + lab_nb] = 1.0f;
+            }
           }
         }
-        if (out_match) out_match[(size_t)b * A + a] = g;
       };
       const int n_used = min(*s_nslots, kSlots);
       if (!overflow) {
