@@ -233,10 +233,13 @@ def roundtrip_config(args, world):
     if args.pipeline_split:
         n_pipe = len(args.pipeline_split.split(","))
     n_streams = max(1, min(args.pipeline_streams, n_pipe))
+    nms_split = max(1, min(args.nms_split, B))
     launch = ("eager" if args.no_graph else "one CUDA graph per step") + (
         "" if args.no_overlap else (
-            "; NMS candidate selection (ssdx_nms_select) on a second stream, concurrent with encode/decode, joined "
-            "before ssdx_nms_finish" if n_pipe == 1 else
+            (f"; NMS stage in {nms_split} sub-batches: ssdx_nms_select of one on the step stream while ssdx_nms_finish "
+             "of the previous one runs on a second stream" if nms_split > 1 else
+             "; NMS candidate selection (ssdx_nms_select) on a second stream, concurrent with encode/decode, joined "
+             "before ssdx_nms_finish") if n_pipe == 1 else
             f"; {n_pipe} sub-batches of {B // n_pipe} images pipelined on {n_streams} streams"))
     return {"workload": args.workload, "stages": list(stages), "images_per_gpu": B, "global_batch": B * world,
             "anchors": A_STD, "gt_per_image": G_STD, "classes": C_STD, "max_total": K_STD, "score_thr": 0.01,
@@ -586,6 +589,9 @@ def gpu_arm(args, rank, world, local_rank):
         pipe_bounds = list(zip(edges[:-1], edges[1:]))
     ws_enc_p = [ws_enc] + [torch.empty_like(ws_enc) for _ in range(n_pipe - 1)]
     ws_nms_p = [ws_nms] + [torch.empty_like(ws_nms) for _ in range(n_pipe - 1)]
+    nms_split = max(1, min(args.nms_split, B))
+    nms_bounds = [(B * i // nms_split, B * (i + 1) // nms_split) for i in range(nms_split)]
+    ws_nms_s = [ws_nms] + [torch.empty_like(ws_nms) for _ in range(nms_split - 1)]
     n_streams = max(1, min(args.pipeline_streams, n_pipe))
     pipe_streams = [None, side] + [torch.cuda.Stream(dev) for _ in range(max(0, n_streams - 2))]  # None = step stream
     pipe_streams = pipe_streams[:n_streams]
@@ -632,6 +638,26 @@ def gpu_arm(args, rank, world, local_rank):
         cur = torch.cuda.current_stream(dev)
         if events is not None or not overlap:
             run_range(0, B, sp, ws_enc, ws_nms, events, stream if events is not None else cur)
+            return
+        if n_pipe == 1 and nms_split > 1:
+            # encode and decode over the whole batch, then the NMS in sub-batches: selection of sub-batch j + 1 on the
+            # step stream while sort + suppression of sub-batch j run on the side stream
+            if "encode" in stages:
+                sx.check(sx.lib.ssdx_encode(handle, d_boxes.data_ptr(), d_labels.data_ptr(), d_counts.data_ptr(), B,
+                                            G_STD, C_STD, 0.5, std, o_labels.data_ptr(), o_offsets.data_ptr(), None,
+                                            ws_enc.data_ptr(), ws_enc.numel(), sp))
+            src = o_offsets if "encode" in stages else d_pred_off
+            sx.check(sx.lib.ssdx_decode(dec_layer._anchors.handle, src.data_ptr(), B, std, 0, o_boxes.data_ptr(), sp))
+            for j, (lo, hi) in enumerate(nms_bounds):
+                n = hi - lo
+                sx.check(sx.lib.ssdx_nms_select(d_scores[lo:hi].data_ptr(), None, n, A_STD, C_STD, K_STD, K_STD, 0.01,
+                                                ws_nms_s[j].data_ptr(), ws_nms_s[j].numel(), dev, sp))
+                side.wait_stream(cur)
+                sx.check(sx.lib.ssdx_nms_finish(o_boxes[lo:hi].data_ptr(), d_scores[lo:hi].data_ptr(), None, n, A_STD,
+                                                C_STD, K_STD, K_STD, 0.45, 0.01, o_det[lo:hi].data_ptr(),
+                                                o_valid[lo:hi].data_ptr(), None, ws_nms_s[j].data_ptr(),
+                                                ws_nms_s[j].numel(), dev, side.cuda_stream))
+            cur.wait_stream(side)
             return
         if n_pipe == 1:
             run_range(0, B, sp, ws_enc, ws_nms, None, cur, overlap_side=side)
@@ -817,7 +843,8 @@ def gpu_arm(args, rank, world, local_rank):
                            " -> layers.NonMaximumSuppression (inputs from pinned host memory, detections to pinned host"
                            f" memory, {n_chunks} chunks per step on two streams)",
                     "host_affinity": numa_note},
-            "gpu_launches": kernels_per_step * (1 if args.no_overlap else n_pipe) * args.steps,
+            "gpu_launches": (kernels_per_step * (1 if args.no_overlap else n_pipe)
+                             + (2 * (nms_split - 1) if (not args.no_overlap and n_pipe == 1) else 0)) * args.steps,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -845,7 +872,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-overlap", action="store_true", help="single stream: ssdx_nms instead of select || encode/decode")
-    ap.add_argument("--pipeline", type=int, default=2, help="sub-batches per step pipelined on two streams (1 = off)")
+    ap.add_argument("--pipeline", type=int, default=1, help="sub-batches per step pipelined on two streams (1 = off)")
+    ap.add_argument("--nms-split", type=int, default=2,
+                    help="sub-batches of the NMS stage alone, pipelined on two streams: the candidate selection "
+                         "(memory-bound) of one overlaps the sort + suppression (instruction-bound) of the other")
     ap.add_argument("--pipeline-streams", type=int, default=2)
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the CPU cores next to its GPU")
     ap.add_argument("--pipeline-split", default="", help="comma-separated sub-batch sizes instead of an even split")
@@ -866,7 +896,8 @@ def main():
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload",
                args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
                    ["--no-graph"] if args.no_graph else []) + (["--no-overlap"] if args.no_overlap else []) + [
-                   "--e2e-chunks", str(args.e2e_chunks), "--pipeline", str(args.pipeline),
+                   "--e2e-chunks", str(args.e2e_chunks), "--pipeline", str(args.pipeline), "--nms-split",
+                   str(args.nms_split),
                    "--pipeline-streams", str(args.pipeline_streams)] + (
                    ["--pipeline-split", args.pipeline_split] if args.pipeline_split else []) + (
                    ["--no-numa"] if args.no_numa else [])

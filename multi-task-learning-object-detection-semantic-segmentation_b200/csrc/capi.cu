@@ -134,10 +134,12 @@ bool make_combo(const float* c, const float* area, const GridMap& m, int k, ssdx
 }
 
 bool detect_grids(const float* c, const float* area, size_t A, std::vector<ssdx_grid_combo>& combos,
-                  std::vector<ssdx_grid_span>& spans, std::vector<float>& axes) {
+                  std::vector<ssdx_grid_span>& spans, std::vector<float>& axes,
+                  std::vector<int>* combo_span = nullptr) {
   combos.clear();
   spans.clear();
   axes.clear();
+  if (combo_span) combo_span->clear();
   for (size_t i = 0; i < 4 * A; ++i)
     if (!std::isfinite(c[i])) return false;
   size_t off = 0;
@@ -181,6 +183,11 @@ bool detect_grids(const float* c, const float* area, size_t A, std::vector<ssdx_
       }
       combos.insert(combos.end(), mine.begin(), mine.end());
       const int rps = std::max(1, (int)(kSsdxSpanAnchors / L));
+      if (combo_span)
+        for (int k = 0; k < nb; ++k) {
+          combo_span->push_back((int)spans.size());
+          combo_span->push_back(rps);
+        }
       for (int r = 0; r < H; r += rps) {
         ssdx_grid_span s;
         s.row0 = r; s.nrows = std::min(rps, H - r);
@@ -191,7 +198,11 @@ bool detect_grids(const float* c, const float* area, size_t A, std::vector<ssdx_
       off += (size_t)H * L;
       found = true;
     }
-    if (!found) { combos.clear(); spans.clear(); axes.clear(); return false; }
+    if (!found) {
+      combos.clear(); spans.clear(); axes.clear();
+      if (combo_span) combo_span->clear();
+      return false;
+    }
   }
   return !combos.empty();
 }
@@ -327,7 +338,8 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
   std::vector<ssdx_grid_combo> combos;
   std::vector<ssdx_grid_span> spans;
   std::vector<float> axes;
-  detect_grids(corners_xyxy_host, area.data(), A, combos, spans, axes);
+  std::vector<int> combo_span;
+  detect_grids(corners_xyxy_host, area.data(), A, combos, spans, axes, &combo_span);
   const size_t nq = combos.size(), ns = spans.size(), nax = axes.size();
 
   ssdx_anchors* h = (ssdx_anchors*)calloc(1, sizeof(ssdx_anchors));
@@ -359,7 +371,7 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
   char* base = nullptr;
   const size_t bytes = A * (3 * sizeof(float4) + sizeof(float)) + Ap * (sizeof(float4) + sizeof(float) + sizeof(int)) +
                        n_tiles * (sizeof(float4) + sizeof(float2)) + 64 + nq * sizeof(ssdx_grid_combo) +
-                       ns * sizeof(ssdx_grid_span) + nax * sizeof(float);
+                       ns * sizeof(ssdx_grid_span) + nax * sizeof(float) + nq * sizeof(int2);
   e = cudaMalloc((void**)&base, bytes);
   if (e == cudaSuccess) {
     h->corners = (float4*)base;
@@ -374,6 +386,7 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
     h->combos = (ssdx_grid_combo*)ssdx_align_up((size_t)(h->m_idx + Ap), 32);
     h->spans = (ssdx_grid_span*)(h->combos + nq);
     h->axes = (float*)(h->spans + ns);
+    h->combo_span = (int2*)(h->axes + nax);  // nax is a multiple of 4 floats: 16-byte aligned
     e = cudaMemcpy(h->corners, corners_xyxy_host, A * sizeof(float4), cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) e = cudaMemcpy(h->enc_cent, enc.data(), A * sizeof(float4), cudaMemcpyHostToDevice);
@@ -389,6 +402,8 @@ int ssdx_anchors_create(const float* corners_xyxy_host, const float* centroids_h
   if (e == cudaSuccess && ns)
     e = cudaMemcpy(h->spans, spans.data(), ns * sizeof(ssdx_grid_span), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && nax) e = cudaMemcpy(h->axes, axes.data(), nax * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nq)
+    e = cudaMemcpy(h->combo_span, combo_span.data(), nq * sizeof(int2), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     ssdx_set_error("ssdx_anchors_create: CUDA error: %s", cudaGetErrorString(e));
     if (base) cudaFree(base);

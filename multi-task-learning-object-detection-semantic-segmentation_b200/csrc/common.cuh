@@ -62,6 +62,7 @@ struct ssdx_anchors {
   int32_t n_axes;                // floats in axes
   float* axes;                   // device
   int32_t max_map_axes;          // floats of the largest single map's (contiguous) axis arrays
+  int2* combo_span;              // device (n_combos): (first span of the grid's map, rows per span)
 };
 
 #ifndef SSDX_APT

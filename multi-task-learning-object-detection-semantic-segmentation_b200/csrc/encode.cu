@@ -649,8 +649,10 @@ inline bool use_fused(int A, int gmax, int C, int batch, int sms, int opt) {
 extern "C" size_t ssdx_encode_workspace_bytes(int32_t num_anchors, int32_t batch, int32_t gmax) {
   if (num_anchors <= 0 || batch <= 0 || gmax < 0) return 0;
   const size_t best = ssdx_align_up((size_t)batch * (size_t)(gmax > 0 ? gmax : 1) * sizeof(u64), 256);
-  const size_t g2 = ssdx_align_up((size_t)batch * (size_t)num_anchors * sizeof(int), 256);
-  return best + g2;
+  // the larger of: matched GT per anchor (tile drivers, 4 bytes per anchor) and the hit lists of the split grid driver
+  // (12 bytes per anchor, encode_grid.cu)
+  const size_t per_anchor = ssdx_align_up((size_t)batch * (((size_t)num_anchors * 12 + 7) / 8 * 8), 256);
+  return best + per_anchor;
 }
 
 extern "C" int ssdx_encode(const ssdx_anchors* anchors, const float* gt_xyxy, const int32_t* gt_label,

@@ -55,7 +55,6 @@ using namespace ssdx_enc;
 #define SSDX_GRID_BGROWS 256
 #endif
 constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kWinCap = 512;                 // windows per round (GT boxes of the round x grids)
 constexpr int kBgRows = SSDX_GRID_BGROWS;    // background rows per bulk store
 constexpr int kBestG = 32;                   // GT boxes per CTA of the split driver's K1
@@ -128,89 +127,6 @@ __device__ __forceinline__ void atomic_max_u16(unsigned short* p, const unsigned
     const unsigned short prev = atomicCAS(p, old, v);
     if (prev == old) break;
     old = prev;
-  }
-}
-
-// Exclusive prefix sum of s[0..n) in place, n <= kWinCap; s[n] = total (also returned).  Called by all threads, the
-// counts must be complete (barrier) before the call; ends with a barrier.
-__device__ __forceinline__ int block_scan_excl(int* s, const int n, int* s_wsum) {
-  constexpr int P = kWinCap / kThreads;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int base = tid * P;
-  int v[P];
-  int sum = 0;
-#pragma unroll
-  for (int k = 0; k < P; ++k) {
-    v[k] = (base + k < n) ? s[base + k] : 0;
-    sum += v[k];
-  }
-  int incl = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int u = __shfl_up_sync(kFull, incl, d);
-    if (lane >= d) incl += u;
-  }
-  if (lane == 31) s_wsum[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    const int w = lane < kWarps ? s_wsum[lane] : 0;
-    int wi = w;
-#pragma unroll
-    for (int d = 1; d < kWarps; d <<= 1) {
-      const int u = __shfl_up_sync(kFull, wi, d);
-      if (lane >= d) wi += u;
-    }
-    if (lane < kWarps) s_wsum[lane] = wi - w;
-    if (lane == kWarps - 1) s_wsum[kWarps] = wi;
-  }
-  __syncthreads();
-  int run = s_wsum[warp] + incl - sum;
-#pragma unroll
-  for (int k = 0; k < P; ++k) {
-    if (base + k < n) s[base + k] = run;
-    run += v[k];
-  }
-  const int total = s_wsum[kWarps];
-  if (tid == 0) s[n] = total;
-  __syncthreads();
-  return total;
-}
-
-// largest w in [0, n) with s_start[w] <= i  (s_start is non-decreasing, s_start[0] = 0 <= i < s_start[n])
-__device__ __forceinline__ int find_window(const int* s_start, const int n, const int i) {
-  int lo = 0, hi = n;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (s_start[mid] <= i) lo = mid;
-    else hi = mid;
-  }
-  return lo;
-}
-
-// Windows of one round: GT boxes [0, gn) of the staged tile x grids [0, nq).  Window w = g * nq + q.
-//   T_MODE 0: t(g) = min(thr_eff, current GT-side best)   (fused driver, K1)
-//   T_MODE 1: t(g) = thr_eff                              (K2: the GT side is already final)
-template <int T_MODE>
-__device__ __forceinline__ void make_windows(const ssdx_grid_combo* s_combo, const int nq, const float4* s_box,
-                                             const u64* s_best, const int g_first, const int gn,
-                                             const float thr_eff, const int row_lo_rel, const int nrows_clip,
-                                             int* s_cnt, int2* s_rect) {
-  const int n_win = gn * nq;
-  for (int w = threadIdx.x; w < n_win; w += kThreads) {
-    const int gl = w / nq, q = w - gl * nq;
-    const int g = g_first + gl;
-    const ssdx_grid_combo& cb = s_combo[q];
-    float t = thr_eff;
-    if (T_MODE == 0) t = fminf(t, __uint_as_float(best_bits(s_best + g)));
-    ssdx_grid_rect r;
-    const int row_lo = nrows_clip > 0 ? row_lo_rel : 0;
-    const int row_hi = nrows_clip > 0 ? row_lo_rel + nrows_clip : cb.H;
-    int cnt = 0;
-    if (ssdx_grid_window(cb, s_box[g], t, row_lo, row_hi, r)) {
-      cnt = r.nr * r.nc;
-      s_rect[w] = make_int2(r.r0 | (r.c0 << 16), r.nc);
-    }
-    s_cnt[w] = cnt;
   }
 }
 
@@ -300,9 +216,11 @@ __device__ __forceinline__ int get_slot(unsigned short* s_slot, int* s_nslots, c
 }
 
 // Walk the cells of up to 32 windows held one per lane (rectangle rx = r0 | c0 << 16, ry = columns | rows << 16,
-// ry = 0: empty): f(owner lane, row, col) for every cell, 32 cells per round.  All lanes of the warp must call it.
+// ry = 0: empty; tag = anything the owner wants passed along): f(tag of the owning lane, row, col) for every cell,
+// 32 cells per round.  All lanes of the warp must call it.
 template <typename F>
-__device__ __forceinline__ void warp_for_each_cell(const int rx, const int ry, const int lane, F f) {
+__device__ __forceinline__ void warp_for_each_cell_tagged(const int rx, const int ry, const int tag, const int lane,
+                                                          F f) {
   const int cnt = (ry & 0xFFFF) * (ry >> 16);
   int incl = cnt;
 #pragma unroll
@@ -323,12 +241,17 @@ __device__ __forceinline__ void warp_for_each_cell(const int rx, const int ry, c
     const int oe = __shfl_sync(kFull, excl, lo);
     const int ox = __shfl_sync(kFull, rx, lo);
     const int oy = __shfl_sync(kFull, ry, lo) & 0xFFFF;
+    const int ot = __shfl_sync(kFull, tag, lo);
     if (i < total) {
       const int local = i - oe;
       const int rr = local / oy, cc = local - rr * oy;
-      f(lo, (ox & 0xFFFF) + rr, (ox >> 16) + cc);
+      f(ot, (ox & 0xFFFF) + rr, (ox >> 16) + cc);
     }
   }
+}
+template <typename F>
+__device__ __forceinline__ void warp_for_each_cell(const int rx, const int ry, const int lane, F f) {
+  warp_for_each_cell_tagged(rx, ry, lane, lane, f);  // tag = owning lane
 }
 
 // The exact per-anchor loop, for an image that does not fit the slot table: every anchor against every GT box.
@@ -378,11 +301,12 @@ __device__ __noinline__ void grid_fused_overflow(const ssdx_grid_combo* s_combo,
   comp_barrier();
 }
 
-// Persistent CTAs: grid = resident CTAs of the device, images handed out through a ticket counter (next_image; the
-// first ticket of a CTA is its block index, the host sets the counter to gridDim.x before the launch).  The producer
-// warp keeps the output stream of the CTA running across images; it draws the tickets and passes them to the
-// matching warps through shared memory.  Per image the two sides meet once (named barrier 2), when the image's
-// background rows are complete and its match is done; the matching warps then patch the positives and go on.
+// Persistent CTAs: grid = resident CTAs of the device, CTA c takes images c, c + gridDim.x, ...  (Measured against a
+// ticket counter zeroed by a memset node before the launch: 62.8 us static, 66.2 us with tickets per 1024 images -
+// every image writes the same number of bytes, so there is little to balance and the extra stream operation costs
+// more than it saves.)  The producer warp keeps the output stream of the CTA running across images.  Per image the
+// two sides meet once (named barrier 2), when the image's background rows are complete and its match is done; the
+// matching warps then patch the positives and go on.
 __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
     ssdx_encode_grid_fused_kernel(const ssdx_grid_combo* __restrict__ combos, const int nq,
                                   const float* __restrict__ axes, const int n_axes,
@@ -390,7 +314,7 @@ __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
                                   const int* __restrict__ gt_count, const int B, const int A, const int Gmax,
                                   const int C, const float iou_thr, const float sx, const float sy, const float sw,
                                   const float sh, float* __restrict__ out_labels, float4* __restrict__ out_offsets,
-                                  int* __restrict__ out_match, int* __restrict__ next_image) {
+                                  int* __restrict__ out_match) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Gs = Gmax > 0 ? Gmax : 1;
@@ -436,7 +360,6 @@ __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
   }
   int* s_nslots = s_ctrl + 0;
   int* s_overflow = s_ctrl + 1;
-  volatile int* s_ticket = s_ctrl + 2;  // [2]: image of the CTA's k-th round at [k & 1], written by the producer
 
   // ---- once per CTA: grids, axis arrays (the table in separable form), constant background blocks, empty tables ----
   PHASE_T0();
@@ -462,7 +385,6 @@ __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
   if (tid == 0) {
     *s_nslots = 0;
     *s_overflow = 0;
-    s_ticket[0] = blockIdx.x;
   }
   fence_async_smem();  // the background blocks are read by the async proxy
   __syncthreads();
@@ -491,27 +413,19 @@ __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
     const bool lookahead = n_st >= kBulkInFlight;  // the first stores of the next image go out before this one is waited for
     int img = blockIdx.x;
     int head = 0;  // stores of img already issued
-    for (int k = 0; img < B; ++k) {
-      int next = B;
+    while (img < B) {
+      const int next = img + gridDim.x;
 #ifndef SSDX_GRID_EXP_NOBULK
       if (lane == 0) {
         issue(img, head, n_st);
-        next = atomicAdd(next_image, 1);
         if (next < B && lookahead) {
           issue(next, 0, kBulkInFlight);
           bulk_wait<kBulkInFlight>();  // everything but the kBulkInFlight newest groups: image img is complete
         } else {
           bulk_wait_all();
         }
-        s_ticket[(k + 1) & 1] = next;
-      }
-#else
-      if (lane == 0) {
-        next = atomicAdd(next_image, 1);
-        s_ticket[(k + 1) & 1] = next;
       }
 #endif
-      next = __shfl_sync(kFull, next, 0);
       head = (next < B && lookahead) ? kBulkInFlight : 0;
       __syncwarp();
       asm volatile("bar.sync 2, %0;" ::"n"(kFThreads) : "memory");  // image img: background rows in place
@@ -521,7 +435,7 @@ __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
     // =================== matching warps ===================
     const float thr_eff = fmaxf(iou_thr, 0.0f);
     int img = blockIdx.x;
-    for (int k = 0; img < B; ++k) {
+    while (img < B) {
       const int b = img;
       int G = gt_count[b];
       G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
@@ -762,7 +676,7 @@ __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
           labs[e] = (lab == c) ? 1.0f : 0.0f;
         }
       }
-      const int next = s_ticket[(k + 1) & 1];  // drawn by the producer before the rendezvous
+      const int next = img + gridDim.x;
       comp_barrier();
       // ---- leave the tables empty for the next image: only what this image used ----
       if (next < B) {
@@ -800,25 +714,53 @@ __global__ void __launch_bounds__(kFThreads, SSDX_GRID_MINB)
 }
 
 // ------------------------------------------------------------------------------------------ split driver
+// Small batches and large tables.  The (GT box, grid) windows of a CTA are numbered w = g * nq + q and walked by its
+// warps 32 windows at a time (one per lane; the cells of the 32 windows are spread over the lanes by
+// warp_for_each_cell), so the warps run independently: no block-wide scan, barriers only between the passes.
+__device__ __forceinline__ unsigned fast_div_magic(const int d) { return 0xFFFFFFFFu / (unsigned)d + 1u; }
+// n / d for n * d < 2^32 (window numbers: n < 2^16 * 2^8)
+__device__ __forceinline__ int fast_div(const int n, const unsigned magic, const int d) {
+  return d == 1 ? n : (int)__umulhi((unsigned)n, magic);
+}
+
 // K1: GT side.  grid (ceil(Gmax / kBestG), B); every (image, GT box) is owned by one CTA, which writes its packed
 // best (IoU bits, ~anchor) - 0 when no anchor overlaps the box.  Dynamic shared memory: grids | axis arrays (when
 // they fit; otherwise the axis arrays are read from global memory).
+// Hit lists (K1 -> K2): every pair above the threshold that K1 meets is appended to the list of the span its anchor
+// lies in, so that K2 does not have to search the GT boxes again.  The lists of image b live in 12 * A bytes of the
+// workspace; span s owns the bytes [12 * a_lo, 12 * (a_lo + n)) of them: a 64-bit counter, then 64-bit entries
+// (anchor - a_lo) << 48 | GT << 32 | IoU bits - room for ~1.5 hits per anchor of the span.  A list that overflows is
+// ignored by K2, which then searches that span itself.
+__host__ __device__ inline size_t span_list_offset(const int a_lo) { return ((size_t)12 * a_lo + 7) / 8 * 8; }
+__host__ __device__ inline size_t span_list_stride(const int A) { return ((size_t)12 * A + 7) / 8 * 8; }  // per image
+__host__ __device__ inline int span_list_capacity(const int a_lo, const int n) {
+  const long long bytes = (long long)12 * (a_lo + n) - (long long)span_list_offset(a_lo) - 8;
+  return bytes < 8 ? 0 : (int)(bytes / 8);
+}
+
+__global__ void ssdx_encode_grid_zero_lists_kernel(const ssdx_grid_span* __restrict__ spans, const int n_spans,
+                                                   const int B, const int A, unsigned char* __restrict__ lists) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_spans * B) return;
+  const int b = i / n_spans, s = i - b * n_spans;
+  *reinterpret_cast<u64*>(lists + (size_t)b * span_list_stride(A) + span_list_offset(spans[s].a_lo)) = 0ull;
+}
+
 __global__ void __launch_bounds__(kThreads)
     ssdx_encode_grid_best_kernel(const ssdx_grid_combo* __restrict__ combos, const int nq,
                                  const float* __restrict__ axes, const int n_axes_smem,
+                                 const ssdx_grid_span* __restrict__ spans, const int2* __restrict__ combo_span,
                                  const float4* __restrict__ gt_xyxy, const int* __restrict__ gt_count,
-                                 const int Gmax, const float iou_thr, u64* __restrict__ gt_best) {
+                                 const int A, const int Gmax, const float iou_thr, u64* __restrict__ gt_best,
+                                 unsigned char* __restrict__ lists) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float4 s_box[kBestG];
   __shared__ float s_area[kBestG];
   __shared__ u64 s_best[kBestG];
-  __shared__ int2 s_rect[kWinCap];
-  __shared__ int s_cnt[kWinCap + 4];
-  __shared__ int s_wsum[kWarps + 1];
   ssdx_grid_combo* s_combo = (ssdx_grid_combo*)smem_raw;
   float* s_ax = (float*)(s_combo + nq);
   const int b = blockIdx.y;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int G = gt_count[b];
   G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
   const int gc0 = blockIdx.x * kBestG;
@@ -837,35 +779,46 @@ __global__ void __launch_bounds__(kThreads)
   const float* ax = n_axes_smem > 0 ? s_ax : axes;
   __syncthreads();
   const float thr_eff = fmaxf(iou_thr, 0.0f);
-  for (int w = tid; w < gn_cta * nq; w += kThreads) {
-    const int g = w / nq, q = w - g * nq;
+  const unsigned magic = fast_div_magic(nq);
+  const int n_win = gn_cta * nq;
+  for (int w = tid; w < n_win; w += kThreads) {
+    const int g = fast_div(w, magic, nq), q = w - g * nq;
     grid_seed(s_combo[q], ax, s_box[g], s_area[g], s_best + g);
   }
   __syncthreads();
-  const int g_round = max(1, kWinCap / nq);
-  for (int g0 = 0; g0 < gn_cta; g0 += g_round) {
-    const int gn = min(g_round, gn_cta - g0);
-    const int n_win = gn * nq;
-    make_windows<0>(s_combo, nq, s_box, s_best, g0, gn, thr_eff, 0, 0, s_cnt, s_rect);
-    __syncthreads();
-    const int total = block_scan_excl(s_cnt, n_win, s_wsum);
-    for (int i = tid; i < total; i += kThreads) {
-      const int w = find_window(s_cnt, n_win, i);
-      const int gl = w / nq, q = w - gl * nq;
-      const int g = g0 + gl;
-      const ssdx_grid_combo& cb = s_combo[q];
-      const int2 rc = s_rect[w];
-      const int local = i - s_cnt[w];
-      const int rr = local / rc.y, cc = local - rr * rc.y;
-      const int r = (rc.x & 0xFFFF) + rr, c = (rc.x >> 16) + cc;
+  for (int w0 = warp * 32; w0 < n_win; w0 += kThreads) {
+    const int w = w0 + lane;
+    int rx = 0, ry = 0, tag = 0;
+    if (w < n_win) {
+      const int g = fast_div(w, magic, nq), q = w - g * nq;
+      tag = (g << 8) | q;
+      ssdx_grid_rect rc;
+      const float t = fminf(thr_eff, __uint_as_float(best_bits(s_best + g)));
+      if (ssdx_grid_window(s_combo[q], s_box[g], t, 0, s_combo[q].H, rc)) {
+        rx = rc.r0 | (rc.c0 << 16);
+        ry = rc.nc | (rc.nr << 16);
+      }
+    }
+    warp_for_each_cell_tagged(rx, ry, tag, lane, [&](const int tg, const int r, const int c) {
+      const int g = tg >> 8;
+      const ssdx_grid_combo& cb = s_combo[tg & 255];
       const float4 ab = grid_anchor_box(cb, ax, r, c);
       const float iou = pair_iou(ab, anchor_area(ab), s_box[g], s_area[g]);
       const unsigned bits = __float_as_uint(iou);
-      if (iou > 0.0f && bits >= best_bits(s_best + g))
-        atomicMax(s_best + g, pack_best(bits, cb.off + (r * cb.W + c) * cb.nb));
-    }
-    __syncthreads();
+      const int a = cb.off + (r * cb.W + c) * cb.nb;
+      if (iou > 0.0f && bits >= best_bits(s_best + g)) atomicMax(s_best + g, pack_best(bits, a));
+      if (iou > iou_thr) {  // anchor side: hand the pair to the span of the anchor
+        const int2 cs = __ldg(combo_span + (tg & 255));
+        const ssdx_grid_span sp = spans[cs.x + r / cs.y];
+        unsigned char* reg = lists + (size_t)b * span_list_stride(A) + span_list_offset(sp.a_lo);
+        const u64 pos = atomicAdd(reinterpret_cast<u64*>(reg), 1ull);
+        if (pos < (u64)span_list_capacity(sp.a_lo, sp.n))
+          reinterpret_cast<u64*>(reg)[1 + pos] =
+              ((u64)(unsigned)(a - sp.a_lo) << 48) | ((u64)(unsigned)(gc0 + g) << 32) | (u64)bits;
+      }
+    });
   }
+  __syncthreads();
   for (int g = tid; g < gn_cta; g += kThreads) gt_best[(size_t)b * Gmax + gc0 + g] = s_best[g];
 }
 
@@ -885,14 +838,12 @@ __global__ void __launch_bounds__(kThreads)
                                  const float4* __restrict__ gt_xyxy, const int* __restrict__ gt_label,
                                  const int* __restrict__ gt_count, const int A, const int Gmax, const int C,
                                  const float iou_thr, const float sx, const float sy, const float sw,
-                                 const float sh, const u64* __restrict__ gt_best, float* __restrict__ out_labels,
+                                 const float sh, const u64* __restrict__ gt_best,
+                                 const unsigned char* __restrict__ lists, float* __restrict__ out_labels,
                                  float4* __restrict__ out_offsets, int* __restrict__ out_match) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ float4 s_box[kGtTile];
   __shared__ float s_area[kGtTile];
-  __shared__ int2 s_rect[kWinCap];
-  __shared__ int s_cnt[kWinCap + 4];
-  __shared__ int s_wsum[kWarps + 1];
   __shared__ int s_lab[kThreads];
   __shared__ int s_npos;
   const int n8 = (max_span_anchors + 7) / 8 * 8;
@@ -905,7 +856,7 @@ __global__ void __launch_bounds__(kThreads)
 
   const ssdx_grid_span sp = spans[blockIdx.x];
   const int b = blockIdx.y;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int G = gt_count[b];
   G = G < 0 ? 0 : (G > Gmax ? Gmax : G);
   const int nq = sp.nb;
@@ -913,6 +864,12 @@ __global__ void __launch_bounds__(kThreads)
 
   for (int i = tid; i < nq * (int)(sizeof(ssdx_grid_combo) / 16); i += kThreads)
     reinterpret_cast<int4*>(s_combo)[i] = __ldg(reinterpret_cast<const int4*>(combos + sp.combo0) + i);
+  for (int i = tid; i < n8 / 4; i += kThreads) reinterpret_cast<int4*>(s_val)[i] = make_int4(0, 0, 0, 0);
+  for (int i = tid; i < n8 / 8; i += kThreads) {
+    reinterpret_cast<int4*>(s_tab)[i] = make_int4(-1, -1, -1, -1);
+    reinterpret_cast<int4*>(s_s1)[i] = make_int4(0, 0, 0, 0);
+  }
+  if (tid == 0) s_npos = 0;
   __syncthreads();
   // axis arrays of this map, rebased so that s_combo[q].ax indexes s_ax
   const int ax0 = s_combo[0].ax;
@@ -923,13 +880,6 @@ __global__ void __launch_bounds__(kThreads)
     for (int i = tid; i < ax_n / 4; i += kThreads)
       reinterpret_cast<int4*>(s_ax)[i] = __ldg(reinterpret_cast<const int4*>(axes + ax0) + i);
   const float* ax = ax_smem ? (s_ax - ax0) : axes;
-  for (int i = tid; i < n8 / 4; i += kThreads) reinterpret_cast<int4*>(s_val)[i] = make_int4(0, 0, 0, 0);
-  for (int i = tid; i < n8 / 8; i += kThreads) {
-    reinterpret_cast<int4*>(s_tab)[i] = make_int4(-1, -1, -1, -1);
-    reinterpret_cast<int4*>(s_s1)[i] = make_int4(0, 0, 0, 0);
-  }
-  if (tid == 0) s_npos = 0;
-  __syncthreads();
   // S1: GT boxes whose best anchor (IoU > 0) lies in this span
   for (int g = tid; g < G; g += kThreads) {
     const u64 p = best[g];
@@ -939,34 +889,52 @@ __global__ void __launch_bounds__(kThreads)
     }
   }
 
-  if (G > 0) {
+  // the pairs above the threshold, as K1 listed them for this span
+  const u64* list = reinterpret_cast<const u64*>(lists + (size_t)b * span_list_stride(A) + span_list_offset(sp.a_lo));
+  const u64 n_list = (G > 0) ? list[0] : 0ull;
+  const bool listed = n_list <= (u64)span_list_capacity(sp.a_lo, sp.n);
+  if (G > 0 && listed) {
+    const int n = (int)n_list;
+    for (int i = tid; i < n; i += kThreads) {  // per-anchor max IoU
+      const u64 e = __ldg(list + 1 + i);
+      atomicMax(s_val + (int)(e >> 48), (unsigned)e);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kThreads) {  // lowest GT index among the maxima (L1 / L2 hit)
+      const u64 e = __ldg(list + 1 + i);
+      const int al = (int)(e >> 48);
+      if ((unsigned)e == s_val[al]) atomic_min_u16(s_tab + al, (unsigned short)((e >> 32) & 0xFFFFu));
+    }
+  } else if (G > 0) {  // the list overflowed: search the span's pairs here
     const float thr_eff = fmaxf(iou_thr, 0.0f);
-    const int g_round = max(1, kWinCap / nq);
-    for (int pass = 0; pass < 2; ++pass) {
+    const unsigned magic = fast_div_magic(nq);
+    for (int pass = 0; pass < 2; ++pass) {  // 0: per-anchor max IoU, 1: lowest GT index among the maxima
       for (int t0 = 0; t0 < G; t0 += kGtTile) {  // GT tile staged in shared memory
         const int tn = min(kGtTile, G - t0);
         __syncthreads();
-        for (int g = tid; g < tn; g += kThreads) {
-          const float4 bx = __ldg(gt_xyxy + (size_t)b * Gmax + t0 + g);
-          s_box[g] = bx;
-          s_area[g] = gt_area(bx);
-        }
+        if (pass == 0 || G > kGtTile)
+          for (int g = tid; g < tn; g += kThreads) {
+            const float4 bx = __ldg(gt_xyxy + (size_t)b * Gmax + t0 + g);
+            s_box[g] = bx;
+            s_area[g] = gt_area(bx);
+          }
         __syncthreads();
-        for (int g0 = 0; g0 < tn; g0 += g_round) {
-          const int gn = min(g_round, tn - g0);
-          const int n_win = gn * nq;
-          make_windows<1>(s_combo, nq, s_box, nullptr, g0, gn, thr_eff, sp.row0, sp.nrows, s_cnt, s_rect);
-          __syncthreads();
-          const int total = block_scan_excl(s_cnt, n_win, s_wsum);
-          for (int i = tid; i < total; i += kThreads) {
-            const int w = find_window(s_cnt, n_win, i);
-            const int gl = w / nq, q = w - gl * nq;
-            const int g = g0 + gl;
-            const ssdx_grid_combo& cb = s_combo[q];
-            const int2 rc = s_rect[w];
-            const int local = i - s_cnt[w];
-            const int rr = local / rc.y, cc = local - rr * rc.y;
-            const int r = (rc.x & 0xFFFF) + rr, c = (rc.x >> 16) + cc;
+        const int n_win = tn * nq;
+        for (int w0 = warp * 32; w0 < n_win; w0 += kThreads) {
+          const int w = w0 + lane;
+          int rx = 0, ry = 0, tag = 0;
+          if (w < n_win) {
+            const int g = fast_div(w, magic, nq), q = w - g * nq;
+            tag = (g << 8) | q;
+            ssdx_grid_rect rc;  // the GT side is final (K1): only pairs above the threshold matter here
+            if (ssdx_grid_window(s_combo[q], s_box[g], thr_eff, sp.row0, sp.row0 + sp.nrows, rc)) {
+              rx = rc.r0 | (rc.c0 << 16);
+              ry = rc.nc | (rc.nr << 16);
+            }
+          }
+          warp_for_each_cell_tagged(rx, ry, tag, lane, [&](const int tg, const int r, const int c) {
+            const int g = tg >> 8;
+            const ssdx_grid_combo& cb = s_combo[tg & 255];
             const int al = cb.off + (r * cb.W + c) * cb.nb - sp.a_lo;
             const float4 ab = grid_anchor_box(cb, ax, r, c);
             const float iou = pair_iou(ab, anchor_area(ab), s_box[g], s_area[g]);
@@ -975,8 +943,7 @@ __global__ void __launch_bounds__(kThreads)
               if (pass == 0) atomicMax(s_val + al, bits);
               else if (bits == s_val[al]) atomic_min_u16(s_tab + al, (unsigned short)(t0 + g));
             }
-          }
-          __syncthreads();
+          });
         }
       }
     }
@@ -1006,9 +973,7 @@ __global__ void __launch_bounds__(kThreads)
     if (C == 4) {
       if (l < sp.n) {
         const int lab = match >= 0 ? __ldg(gt_label + (size_t)b * Gmax + match) : 0;
-        const float4 oh = make_float4(lab == 0 ? 1.f : 0.f, lab == 1 ? 1.f : 0.f, lab == 2 ? 1.f : 0.f,
-                                      lab == 3 ? 1.f : 0.f);
-        st_stream_f4(reinterpret_cast<float4*>(out_labels) + row0 + sp.a_lo + l, oh);
+        st_stream_f4(reinterpret_cast<float4*>(out_labels) + row0 + sp.a_lo + l, one_hot4(lab));
       }
     } else {
       // generic class count: flat coalesced walk over the chunk's (n_here * C) floats
@@ -1040,8 +1005,6 @@ __global__ void __launch_bounds__(kThreads)
 
 constexpr int kAxesSmemMax = 12288;  // floats of axis arrays a CTA stages in shared memory (48 KB)
 
-__global__ void ssdx_set_int_kernel(int* p, const int v) { *p = v; }
-
 }  // namespace
 
 // ---- host side (called by ssdx_encode) ----
@@ -1065,29 +1028,38 @@ int ssdx_encode_grid_launch(const ssdx_anchors* anchors, const bool fused, const
     const size_t smem = grid_fused_smem_bytes(A, gmax, num_classes, nq, anchors->n_axes);
     SSDX_CUDA(cudaFuncSetAttribute(ssdx_encode_grid_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    int per_sm = 0;
-    SSDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssdx_encode_grid_fused_kernel, kFThreads, smem));
+    static thread_local size_t cached_smem = 0;  // resident CTAs per SM for this shared-memory size
+    static thread_local int cached_per_sm = 0;
+    if (cached_smem != smem || cached_per_sm == 0) {
+      SSDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, ssdx_encode_grid_fused_kernel, kFThreads,
+                                                              smem));
+      cached_smem = smem;
+    }
+    const int per_sm = cached_per_sm;
     const int grid = std::min((int)batch, std::max(1, per_sm) * ssdx_sm_count(anchors->device));
-    int* next_image = (int*)workspace;  // ticket counter: the first `grid` images are taken by block index
-    ssdx_set_int_kernel<<<1, 1, 0, s>>>(next_image, grid);
     ssdx_encode_grid_fused_kernel<<<grid, kFThreads, smem, s>>>(
         anchors->combos, nq, anchors->axes, anchors->n_axes, (const float4*)gt_xyxy, gt_label, gt_count, batch, A,
         gmax, num_classes, iou_threshold, std_host[0], std_host[1], std_host[2], std_host[3], out_labels,
-        (float4*)out_offsets, out_match, next_image);
+        (float4*)out_offsets, out_match);
     SSDX_LAUNCH_CHECK("ssdx_encode_grid_fused_kernel");
     return SSDX_OK;
   }
   const int gm = gmax > 0 ? gmax : 1;
   u64* gt_best = (u64*)workspace;
+  unsigned char* lists = (unsigned char*)workspace + ssdx_align_up((size_t)batch * gm * sizeof(u64), 256);
   if (gmax > 0) {
+    const int nz = anchors->n_spans * batch;
+    ssdx_encode_grid_zero_lists_kernel<<<(nz + 255) / 256, 256, 0, s>>>(anchors->spans, anchors->n_spans, batch, A,
+                                                                        lists);
+    SSDX_LAUNCH_CHECK("ssdx_encode_grid_zero_lists_kernel");
     const int ax1 = anchors->n_axes <= kAxesSmemMax ? anchors->n_axes : 0;
     const size_t smem1 = (size_t)nq * sizeof(ssdx_grid_combo) + (size_t)ax1 * 4;
     SSDX_CUDA(cudaFuncSetAttribute(ssdx_encode_grid_best_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem1));
     dim3 g1((gm + kBestG - 1) / kBestG, batch);
-    ssdx_encode_grid_best_kernel<<<g1, kThreads, smem1, s>>>(anchors->combos, nq, anchors->axes, ax1,
-                                                             (const float4*)gt_xyxy, gt_count, gm, iou_threshold,
-                                                             gt_best);
+    ssdx_encode_grid_best_kernel<<<g1, kThreads, smem1, s>>>(anchors->combos, nq, anchors->axes, ax1, anchors->spans,
+                                                             anchors->combo_span, (const float4*)gt_xyxy, gt_count,
+                                                             A, gm, iou_threshold, gt_best, lists);
     SSDX_LAUNCH_CHECK("ssdx_encode_grid_best_kernel");
   }
   const int ax2 = anchors->max_map_axes <= kAxesSmemMax ? anchors->max_map_axes : 0;
@@ -1098,7 +1070,7 @@ int ssdx_encode_grid_launch(const ssdx_anchors* anchors, const bool fused, const
   ssdx_encode_grid_span_kernel<<<g2, kThreads, smem2, s>>>(
       anchors->combos, anchors->spans, anchors->axes, anchors->max_span_anchors, anchors->max_span_combos, ax2,
       (const float4*)gt_xyxy, gt_label, gt_count, A, gm, num_classes, iou_threshold, std_host[0], std_host[1],
-      std_host[2], std_host[3], gt_best, out_labels, (float4*)out_offsets, out_match);
+      std_host[2], std_host[3], gt_best, lists, out_labels, (float4*)out_offsets, out_match);
   SSDX_LAUNCH_CHECK("ssdx_encode_grid_span_kernel");
   return SSDX_OK;
 }

@@ -985,6 +985,14 @@ def test_encode_many_positives_overflow_path(lib, coder, std_anchors, encode_pat
     assert (Mr >= 0).sum(axis=1).max() > 1024
     assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
     assert_offsets_close(O, Or)
+    # 64 GT boxes at threshold 0.05: more pairs above the threshold than the split driver's hit lists hold
+    labels, boxes, counts = orc.synth_gt(rng, 20, 64)
+    L, O, M = c.encode_batch(boxes, labels, counts, return_match=True)
+    Lr, Or, Mr = encode_ref(std_anchors, labels, boxes, counts, 4, 0.05)
+    iou = orc.iou_matrix(std_anchors, boxes[0])
+    assert (iou > 0.05).sum() > 1.5 * 9600
+    assert np.array_equal(M, Mr) and np.array_equal(L, Lr)
+    assert_offsets_close(O, Or)
     labels, boxes, counts = orc.synth_gt(rng, 150, 256, wh_range=(10.0, 200.0))
     counts[::3] = rng.integers(0, 257, size=len(counts[::3]))
     L, O, M = coder.encode_batch(boxes, labels, counts, return_match=True)
