@@ -453,7 +453,9 @@ def gpu_arm_eval(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "ssdseglib.evaluators.true_positives_and_counts(NumPy in, NumPy out"
                            + (", process_group=WORLD)" if world > 1 else ")")},
-            "gpu_launches": (3 + (1 if world > 1 else 0)) * args.steps,  # eval_tp, AP keys + AP integrate (+ sum_counts)
+            # eval_tp + the seven kernels of ssdx_average_precision (sample, bucket, columns, offsets, scatter, terms, sum)
+            # (+ sum_counts after the all-gather)
+            "gpu_launches": (8 + (1 if world > 1 else 0)) * args.steps,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -736,9 +738,13 @@ def gpu_arm(args, rank, world, local_rank):
     copy_stream = torch.cuda.Stream(dev)
     h_det = torch.empty((B, K_STD, 6), dtype=torch.float32).pin_memory()
 
-    def step_e2e():
+    # Double-buffered across steps: the copies of step i + 1 are enqueued (copy stream) before the compute of step i
+    # (step stream), so PCIe stays busy while the GPU works; the host waits for step i's detections before it
+    # reuses that step's pinned result buffer.
+    h_det2 = [h_det, torch.empty_like(h_det).pin_memory()]
+
+    def e2e_stage():
         staged = []
-        copy_stream.wait_stream(stream)
         with torch.cuda.stream(copy_stream):
             for lo, hi in bounds:
                 gb = h_boxes[lo:hi].to(f"cuda:{dev}", non_blocking=True)
@@ -749,6 +755,9 @@ def gpu_arm(args, rank, world, local_rank):
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 staged.append((gb, gl, gc, sc, po, ev))
+        return staged
+
+    def e2e_compute(staged, out_host):
         for (lo, hi), (gb, gl, gc, sc, po, ev) in zip(bounds, staged):
             stream.wait_event(ev)
             for t in (gb, gl, gc, sc, po):
@@ -760,23 +769,65 @@ def gpu_arm(args, rank, world, local_rank):
                 off = po
             yx = dec_layer(off)
             det = nms_layer(yx, sc)
-            h_det[lo:hi].copy_(det, non_blocking=True)  # device -> host read of the chunk's result
-        stream.synchronize()
-        return h_det
+            out_host[lo:hi].copy_(det, non_blocking=True)  # device -> host read of the chunk's result
+        done = torch.cuda.Event()
+        done.record(stream)
+        return done
+
+    def run_e2e(n_steps):
+        staged = e2e_stage()
+        out = None
+        for i in range(n_steps):
+            nxt = e2e_stage() if i + 1 < n_steps else None
+            done = e2e_compute(staged, h_det2[i & 1])
+            done.synchronize()  # step i's detections are on the host
+            out = h_det2[i & 1]
+            staged = nxt
+        return out
 
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        det_host = step_e2e()
+    det_host = run_e2e(e2e_steps)
     e1.record(stream)
     barrier()
     e2e_wall = time.perf_counter() - t0
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)
+
+    # two more end-to-end figures through the public API (NumPy in, NumPy out), as the reference uses the path:
+    # (a) the training-data pipeline: GT boxes -> encoded targets back on the host (datacoder.py:302-347, cell 8);
+    # (b) the inference tail: raw head outputs -> detections (models.py:402-414) in one call
+    e2e_more = {}
+    if "encode" in stages:
+        n_more = max(2, min(e2e_steps, 5))
+        np_in = (boxes, labels, counts)
+        coder.encode_batch(*np_in)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_more):
+            enc_l, enc_o = coder.encode_batch(*np_in)
+        t_enc = (time.perf_counter() - t0) / n_more
+        e2e_more["encode_numpy_in_numpy_out"] = {
+            "value": B / t_enc, "unit": "images/s", "ms_per_step": 1e3 * t_enc,
+            "h2d_bytes_per_step": int(boxes.nbytes + labels.nbytes + counts.nbytes),
+            "d2h_bytes_per_step": int(enc_l.nbytes + enc_o.nbytes),
+            "api": "DataEncoderDecoder.encode_batch(NumPy) -> (labels, offsets) NumPy"}
+        h_off_np = o_offsets.cpu().numpy()
+        h_log_np = torch.log(d_scores.clamp_min(1e-30)).cpu().numpy()
+        nms_layer.call_on_offsets_and_logits(dec_layer, h_off_np, h_log_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_more):
+            det_np = nms_layer.call_on_offsets_and_logits(dec_layer, h_off_np, h_log_np)
+        t_tail = (time.perf_counter() - t0) / n_more
+        e2e_more["inference_tail_numpy_in_numpy_out"] = {
+            "value": B / t_tail, "unit": "images/s", "ms_per_step": 1e3 * t_tail,
+            "h2d_bytes_per_step": int(h_off_np.nbytes + h_log_np.nbytes), "d2h_bytes_per_step": int(det_np.nbytes),
+            "api": "NonMaximumSuppression.call_on_offsets_and_logits(decode_layer, offsets, logits) NumPy -> NumPy"}
+        del h_off_np, h_log_np
     sampler.stop()
 
     h2d = h_scores.numel() * 4 + (h_boxes.numel() * 4 + h_labels.numel() * 4 + h_counts.numel() * 4
@@ -841,8 +892,9 @@ def gpu_arm(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "ssdseglib.datacoder.DataEncoderDecoder.encode_batch -> layers.DecodeBoxesCentroidsOffsets"
                            " -> layers.NonMaximumSuppression (inputs from pinned host memory, detections to pinned host"
-                           f" memory, {n_chunks} chunks per step on two streams)",
-                    "host_affinity": numa_note},
+                           f" memory, {n_chunks} chunks per step on two streams, copies of step i + 1 under the compute"
+                           " of step i)",
+                    "host_affinity": numa_note, "more": e2e_more},
             "gpu_launches": (kernels_per_step * (1 if args.no_overlap else n_pipe)
                              + (2 * (nms_split - 1) if (not args.no_overlap and n_pipe == 1) else 0)) * args.steps,
             "clocks": sampler.summary(),
@@ -871,9 +923,12 @@ def main():
     ap.add_argument("--workload", default="roundtrip_b1024", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph per step")
-    ap.add_argument("--no-overlap", action="store_true", help="single stream: ssdx_nms instead of select || encode/decode")
+    ap.add_argument("--overlap", action="store_true",
+                    help="multi-stream forms of the step (--pipeline / --nms-split, or the NMS candidate selection on a "
+                         "second stream).  Default: one stream - since encode became bandwidth-bound every "
+                         "overlapped form measured slower (211 us single stream, 217-277 us overlapped)")
     ap.add_argument("--pipeline", type=int, default=1, help="sub-batches per step pipelined on two streams (1 = off)")
-    ap.add_argument("--nms-split", type=int, default=2,
+    ap.add_argument("--nms-split", type=int, default=1,
                     help="sub-batches of the NMS stage alone, pipelined on two streams: the candidate selection "
                          "(memory-bound) of one overlaps the sort + suppression (instruction-bound) of the other")
     ap.add_argument("--pipeline-streams", type=int, default=2)
@@ -881,6 +936,7 @@ def main():
     ap.add_argument("--pipeline-split", default="", help="comma-separated sub-batch sizes instead of an even split")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks per step of the end-to-end leg (copy/compute overlap)")
     args = ap.parse_args()
+    args.no_overlap = not args.overlap
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -895,7 +951,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload",
                args.workload] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (
-                   ["--no-graph"] if args.no_graph else []) + (["--no-overlap"] if args.no_overlap else []) + [
+                   ["--no-graph"] if args.no_graph else []) + (["--overlap"] if args.overlap else []) + [
                    "--e2e-chunks", str(args.e2e_chunks), "--pipeline", str(args.pipeline), "--nms-split",
                    str(args.nms_split),
                    "--pipeline-streams", str(args.pipeline_streams)] + (

@@ -246,6 +246,14 @@ def to_device(x: Any, np_dtype, device: Optional[int] = None, tag: str = "x") ->
 def from_device(t, kind: str):
     """Mirror the input kind on the way out."""
     if kind == "numpy":
+        if t.numel() * t.element_size() >= (1 << 16):
+            # device -> pinned host block (torch's caching host allocator hands freed blocks out again) at PCIe rate;
+            # the returned array owns the block through its base tensor, so consecutive calls never alias
+            torch = _torch()
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device.index).synchronize()
+            return h.numpy()
         return t.cpu().numpy()
     if kind == "torch_cpu":
         return t.cpu()

@@ -1,10 +1,17 @@
-"""Prediction post-processing - mirror of the reference's `ssdseglib/layers.py` (decode + NMS) over libssdx.
+"""Prediction post-processing - mirror of the reference's `ssdseglib/layers.py` over libssdx.
 
-`DecodeBoxesCentroidsOffsets` and `NonMaximumSuppression` keep the reference's constructor arguments, `call`
-signature, output layout and `get_config` (layers.py:4-177).  They are plain callables (TensorFlow/Keras is not a
-dependency of this package); `call` accepts NumPy arrays, torch tensors or DLPack objects and mirrors the input
-kind on return.  `SegmentationSuppression` and `Split` belong to the Keras model graph and are not part of this
-path.
+`DecodeBoxesCentroidsOffsets`, `NonMaximumSuppression` and `SegmentationSuppression` keep the reference's constructor
+arguments, `call` signature, output layout and `get_config` (layers.py:4-212).  TensorFlow/Keras is not a dependency
+of this package:
+
+  * without TensorFlow the three names are plain callables: `call` accepts NumPy arrays, torch tensors or DLPack
+    objects and mirrors the input kind on return;
+  * when `tensorflow` is importable they are `tf.keras.layers.Layer` subclasses registered under the reference's
+    names (`keras_layers.py`), usable on symbolic tensors inside `tf.keras.Model` exactly where `models.py:378-417`
+    puts them; non-TensorFlow inputs still go to the plain implementation, which stays available as
+    `PlainDecodeBoxesCentroidsOffsets` / `PlainNonMaximumSuppression` / `PlainSegmentationSuppression`.
+
+`Split` (a `tf.split` wrapper inside the Keras model graph) is not part of this path.
 """
 from __future__ import annotations
 
@@ -269,3 +276,18 @@ class SegmentationSuppression(_Layer):
 
     def get_config(self):
         return {}
+
+
+# ---- Keras-graph form (only when TensorFlow is importable; see keras_layers.py) ----
+PlainDecodeBoxesCentroidsOffsets = DecodeBoxesCentroidsOffsets
+PlainNonMaximumSuppression = NonMaximumSuppression
+PlainSegmentationSuppression = SegmentationSuppression
+try:  # pragma: no cover - TensorFlow is absent from the build and test images
+    import tensorflow as _tf
+except Exception:
+    _tf = None
+if _tf is not None:  # pragma: no cover
+    from .keras_layers import make_keras_layers
+
+    DecodeBoxesCentroidsOffsets, NonMaximumSuppression, SegmentationSuppression = make_keras_layers(
+        _tf, PlainDecodeBoxesCentroidsOffsets, PlainNonMaximumSuppression, PlainSegmentationSuppression)

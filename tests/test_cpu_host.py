@@ -335,3 +335,104 @@ def test_grid_windows_random_tables(ssdseglib):
         boxes = boxes[0] + np.float32(rng.uniform(-0.3, 0.3) * hw[1] * rng.integers(0, 2))
         _windows_cover(ssdseglib, anchors, boxes, rng.choice([0.0, 0.1, 0.5, 0.7], size=12).astype(np.float32))
     assert done >= 30
+
+
+# ------------------------------------------------------------------------------- Keras-graph form of the layers
+def _stub_tensorflow():
+    """A minimal stand-in for the parts of TensorFlow keras_layers.py touches (TensorFlow itself is not installable
+    in the build / test images): Layer with Keras' call protocol, register_keras_serializable, numpy_function."""
+    import types
+
+    registry = {}
+
+    class Layer:
+        def __init__(self, name=None, trainable=True, **kwargs):
+            assert not kwargs, kwargs
+            self.name, self.trainable = name, trainable
+
+        def __call__(self, *args, **kwargs):
+            return self.call(*args, **kwargs)
+
+    class FakeTensor:
+        def __init__(self, value):
+            self.value = np.asarray(value)
+            self.shape = self.value.shape
+
+        def set_shape(self, shape):
+            self.static_shape = tuple(shape)
+
+    def register(package="Custom", name=None):
+        def deco(cls):
+            registry[name or cls.__name__] = cls
+            return cls
+        return deco
+
+    def numpy_function(func, inp, Tout, name=None):
+        return FakeTensor(func(*[t.value for t in inp]))
+
+    tf = types.SimpleNamespace(
+        keras=types.SimpleNamespace(layers=types.SimpleNamespace(Layer=Layer),
+                                    saving=types.SimpleNamespace(register_keras_serializable=register)),
+        is_tensor=lambda x: isinstance(x, FakeTensor), numpy_function=numpy_function, float32="float32")
+    return tf, registry, FakeTensor
+
+
+def test_keras_layer_forms_mirror_the_reference_contract(ssdseglib):
+    """models.py:378-417 constructs the layers with keyword arguments + name=, sets .trainable, calls them on graph
+    tensors and relies on get_config / the registered names for save + load_model (layers.py:4,83-93,95,170-177,179)."""
+    from ssdseglib import keras_layers
+
+    tf, registry, FakeTensor = _stub_tensorflow()
+    calls = []
+
+    class PlainNms:
+        def __init__(self, *a):
+            self.args = a
+
+        def call(self, boxes, probs):
+            calls.append((boxes.dtype, probs.dtype, boxes.shape))
+            return np.zeros((boxes.shape[0], self.args[1], 6), np.float32)
+
+        def call_on_logits(self, boxes, logits):
+            return "logits-path"
+
+    class PlainDecode:
+        def __init__(self, *a):
+            self.args = a
+
+        def call(self, off):
+            return off * 2
+
+    Dec, Nms, Seg = keras_layers.make_keras_layers(tf, PlainDecode, PlainNms, lambda: None)
+    assert set(registry) == {"DecodeBoxesCentroidsOffsets", "NonMaximumSuppression", "SegmentationSuppression"}
+    assert issubclass(Nms, tf.keras.layers.Layer) and issubclass(Dec, tf.keras.layers.Layer)
+    nms = Nms(max_number_of_boxes_per_class=4, max_number_of_boxes_per_sample=10, boxes_iou_threshold=0.025,
+              labels_probability_threshold=0.725, suppress_background_boxes=False, name="output-object-detection")
+    nms.trainable = False
+    assert nms.get_config() == {"max_number_of_boxes_per_class": 4, "max_number_of_boxes_per_sample": 10,
+                                "boxes_iou_threshold": 0.025, "labels_probability_threshold": 0.725,
+                                "suppress_background_boxes": False}
+    assert Nms(**nms.get_config()).get_config() == nms.get_config()  # from_config round trip
+    out = nms(boxes_corners_coordinates=FakeTensor(np.zeros((3, 50, 4), np.float64)),
+              labels_probabilities=FakeTensor(np.zeros((3, 50, 4), np.float64)))
+    assert isinstance(out, FakeTensor) and out.static_shape == (3, 10, 6)
+    assert calls == [(np.dtype("float32"), np.dtype("float32"), (3, 50, 4))]  # fp32 host arrays reach the C-ABI path
+    assert Nms(4, 10, 0.1, 0.5, True)(FakeTensor(np.zeros((2, 5, 4))), FakeTensor(np.zeros((2, 5, 4)))).static_shape \
+        == (None, 6)
+    # non-TensorFlow inputs bypass the graph machinery; the extra entry points stay reachable
+    assert isinstance(nms(np.zeros((2, 5, 4), np.float32), np.zeros((2, 5, 4), np.float32)), np.ndarray)
+    assert nms.call_on_logits(None, None) == "logits-path"
+    cx = np.arange(5, dtype=np.float32)
+    dec = Dec(center_x_boxes_default=cx, center_y_boxes_default=cx, width_boxes_default=cx, height_boxes_default=cx,
+              standard_deviation_center_x_offsets=0.1, standard_deviation_center_y_offsets=0.1,
+              standard_deviation_width_offsets=0.2, standard_deviation_height_offsets=0.2, name="decode-output-boxes")
+    cfg = dec.get_config()
+    assert list(cfg) == ["center_x_boxes_default", "center_y_boxes_default", "width_boxes_default",
+                         "height_boxes_default", "standard_deviation_center_x_offsets",
+                         "standard_deviation_center_y_offsets", "standard_deviation_width_offsets",
+                         "standard_deviation_height_offsets"] and cfg["center_x_boxes_default"] is cx
+    y = dec(FakeTensor(np.ones((2, 5, 4))))
+    assert y.static_shape == (2, 5, 4) and np.all(y.value == 2.0)
+    assert Seg(name="segmentation-suppression").get_config() == {}
+    # the package itself: plain callables here (no TensorFlow), aliases always present
+    assert ssdseglib.layers.NonMaximumSuppression is ssdseglib.layers.PlainNonMaximumSuppression
