@@ -188,6 +188,25 @@ def run_cpu_sample(stages, sample_images, seed, threads, target_seconds=10.0, ma
     return sample_images * passes / total, total, passes
 
 
+def cpu_config0(c_oracle, threads):
+    """BASELINE config 0: the reference CPU path's own runnable case - encode of 8 synthetic images x 16 GT boxes
+    (3 foreground classes) against the SSDLite-MobileNetV2 anchor set - on one core and on all cores of this host."""
+    from oracle import ssd_oracle as orc
+
+    anchors = orc.anchors_generate(**orc.STD_ANCHOR_CFG)
+    labels, boxes, counts = orc.synth_gt(np.random.default_rng(1993), 8, G_STD)
+    out = {"workload": "encode, 8 images x 16 GT boxes, 9600 anchors (C port of datacoder.py:205-300)"}
+    for name, nt in (("one_core", 1), ("all_cores", threads)):
+        c_oracle.encode_batch(anchors, labels, boxes, counts, C_STD, 0.5, STD, nthreads=nt)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 0.5:
+            c_oracle.encode_batch(anchors, labels, boxes, counts, C_STD, 0.5, STD, nthreads=nt)
+            reps += 1
+        out[name] = {"images_per_s": 8 * reps / (time.perf_counter() - t0), "threads": nt}
+    return out
+
+
 def reference_arm(args, rank):
     """`--impl reference`: the host-CPU port of the reference path, all host threads, bounded sample per step."""
     if rank != 0:
@@ -904,10 +923,14 @@ def gpu_arm(args, rank, world, local_rank):
             threads = os.cpu_count() or 1
             sample = 1024
             v, secs, passes = run_cpu_sample(stages, sample, 1995, threads)
+            from oracle import c_oracle
+
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
                                     "sample": f"{passes} passes over {sample} images of the {args.workload} workload "
                                               f"({secs:.1f} s of host work), C/OpenMP port of the reference "
-                                              f"(oracle/ssd_oracle.c), {threads} threads"}
+                                              f"(oracle/ssd_oracle.c, gcc {' '.join(c_oracle.CFLAGS)} -fopenmp), "
+                                              f"{threads} threads",
+                                    "config0": cpu_config0(c_oracle, threads)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

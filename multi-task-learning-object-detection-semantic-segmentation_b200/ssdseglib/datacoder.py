@@ -149,12 +149,27 @@ class DataEncoderDecoder:
         lab, off = self.encode_batch(boxes[None], labels[None])
         return lab[0], off[0]
 
+    def _encode_np(self, path_file_labels_boxes, augment_with_horizontal_flip):
+        """Body of the `tf.numpy_function` inside `read_and_encode`: path (bytes / str / 0-d array), flip flag
+        (bool / np.bool_) -> (labels (A, num_classes), offsets (A, 4)) float32.  Re-entrant: `tf.data` calls it from
+        several threads (03-...ipynb cell 8, num_parallel_calls=AUTOTUNE)."""
+        path = path_file_labels_boxes
+        if isinstance(path, np.ndarray):
+            path = path.item()
+        if isinstance(path, bytes):
+            path = path.decode()
+        lab, off = self._encode_ground_truth_labels_boxes(str(path), bool(augment_with_horizontal_flip))
+        return np.ascontiguousarray(lab, np.float32), np.ascontiguousarray(off, np.float32)
+
     def read_and_encode(self, path_file_image: str, path_file_mask: str, path_file_labels_boxes: str):
         """(image, {'output-mask', 'output-labels', 'output-boxes'}) as datacoder.py:302-347.
 
-        Only the box side runs here.  PNG decoding / one-hot mask / image flip (datacoder.py:325-342) are
-        image I/O outside this library: they are delegated to TensorFlow when it is importable, otherwise
-        this method raises."""
+        Usable exactly where the reference uses it - as the function of `tf.data.Dataset.map` (graph mode, symbolic
+        string tensors) or eagerly with Python strings.  PNG decoding, the one-hot mask and the image flip
+        (datacoder.py:325-342) are TensorFlow image ops and stay TensorFlow ops; the flip coin is the reference's
+        `tf.random.uniform(...) >= 0.5` (:337); the box side (:344, datacoder.py:177-300) runs on the GPU through a
+        `tf.numpy_function` with the static shapes (A, num_classes) / (A, 4) restored.  Without TensorFlow this method
+        raises: use `read_labels_boxes(_batch)` + `encode_batch` for the box targets."""
         try:
             import tensorflow as tf  # noqa: F401
         except ImportError as e:
@@ -163,11 +178,16 @@ class DataEncoderDecoder:
         image = tf.cast(tf.image.decode_png(tf.io.read_file(path_file_image), channels=3), tf.float32)
         mask = tf.image.decode_png(tf.io.read_file(path_file_mask), channels=1)
         mask = tf.squeeze(tf.one_hot(mask, depth=self.num_classes, dtype=tf.float32), axis=2)
-        flip = bool(self.augmentation_horizontal_flip and np.random.uniform() >= 0.5)
-        if flip:
-            image = tf.image.flip_left_right(image)
-            mask = tf.image.flip_left_right(mask)
-        labels, boxes = self._encode_ground_truth_labels_boxes(path_file_labels_boxes, flip)
+        if self.augmentation_horizontal_flip:
+            flip = tf.random.uniform(shape=[], minval=0, maxval=1) >= 0.5
+            image = tf.cond(flip, lambda: tf.image.flip_left_right(image), lambda: image)
+            mask = tf.cond(flip, lambda: tf.image.flip_left_right(mask), lambda: mask)
+        else:
+            flip = tf.constant(False)
+        labels, boxes = tf.numpy_function(self._encode_np, [path_file_labels_boxes, flip], [tf.float32, tf.float32],
+                                          name="ssdx_encode")
+        labels.set_shape((self.num_anchors, self.num_classes))
+        boxes.set_shape((self.num_anchors, 4))
         return image, {'output-mask': mask, 'output-labels': labels, 'output-boxes': boxes}
 
     # ------------------------------------------------------------------ decode

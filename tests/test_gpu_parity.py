@@ -195,6 +195,9 @@ def test_encode_per_image_file_api(lib, coder, std_anchors, tmp_path, golden):
     L, O = coder._encode_ground_truth_labels_boxes(str(p), False)
     assert np.array_equal(L, g["cfg0_labels"][0])
     assert_offsets_close(O, g["cfg0_offsets"][0])
+    # the body of the tf.numpy_function inside read_and_encode: bytes path + NumPy flag, as TensorFlow hands them over
+    Ln, On = coder._encode_np(np.array(str(p).encode()), np.bool_(False))
+    assert Ln.dtype == np.float32 and np.array_equal(Ln, L) and np.array_equal(On, O)
     Lf, Of = coder._encode_ground_truth_labels_boxes(str(p), True)
     Lr, Or, _ = orc.encode_image(std_anchors, g["cfg0_gt_labels"][0],
                                  orc.flip_boxes_horizontal(g["cfg0_gt_boxes"][0], 640), 4, 0.5, STD)
