@@ -1,7 +1,8 @@
 // Per-class confidence-filtered NMS + cross-class merge
 // (reference: layers.py:127-168 -> tf.image.combined_non_max_suppression, q = 1, clip_boxes = False).
 //
-// Pipeline (4 launches, stream-ordered, all state in the caller's workspace):
+// Per-class pipeline (max_per_class < max_total; 4 launches, stream-ordered, all state in the caller's workspace;
+// caps of at most 32 boxes per class take the one-warp-per-segment kernel of section 2w instead of steps 2-4):
 //   1. select  : one CTA per (image, class group).  Scores are read coalesced (128-bit when C == 4).
 //                A 1/16 sample of the anchors gives, per class, the key of its m-th largest sample
 //                (warp-level bisection, REDUX only); a second pass appends every candidate with
@@ -22,7 +23,7 @@
 //                lower anchor), keeps max_total rows and writes [label, prob, xmin, ymin, xmax, ymax]
 //                (layers.py:155-162), zero padding, valid counts and source anchor indices.
 //
-// Merged pipeline (2 launches + 2 gated fallbacks), used when max_per_class >= max_total (the per-class cap can
+// Merged pipeline (2 launches, no fallback behind it), used when max_per_class >= max_total (the per-class cap can
 // then never bind before the image has max_total rows), C <= 256 and A <= 2^24:
 //   The K = max_total output rows are the first K boxes selected when the candidates of ALL classes are visited in
 //   one descending order (score, then lower class, then lower anchor) and each one is tested only against the
@@ -33,9 +34,10 @@
 //                    streaming pass with a single compare per score; ~400 composites
 //                    (score key << 32 | ~class << 24 | ~anchor) per image.
 //   2m. fast_all   : one CTA per image: register bitonic sort, blocked greedy suppression with a class-equality
-//                    test on the rare overlapping pairs, adaptive refills, rows written in place.  An image whose list
-//                    overflowed or whose refills failed (massive score ties) is handed to the exact per-class
-//                    generic kernel + a merge over the handed-over images only.
+//                    test on the rare overlapping pairs, rows written in place.  A list that runs dry - or that
+//                    overflowed, or that holds thousands of equal scores - is refilled in bands of the full 64-bit
+//                    composite order (score key, class, anchor), narrowed down to a single composite if need be:
+//                    the kernel never hands an image over to the generic kernel.
 //
 // IoU follows TF's IOU(): min/max-normalised corners, area = (y1-y0)*(x1-x0), 0 if either area <= 0,
 // inter / ((area_i + area_j) - inter) with IEEE division, suppressed iff IoU > iou_thr (strict).
