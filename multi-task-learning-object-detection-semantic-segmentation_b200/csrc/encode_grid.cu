@@ -807,11 +807,25 @@ __global__ void __launch_bounds__(kThreads)
       const unsigned bits = __float_as_uint(iou);
       const int a = cb.off + (r * cb.W + c) * cb.nb;
       if (iou > 0.0f && bits >= best_bits(s_best + g)) atomicMax(s_best + g, pack_best(bits, a));
-      if (iou > iou_thr) {  // anchor side: hand the pair to the span of the anchor
+      // anchor side: hand the pair to the span of the anchor.  The lanes of a round mostly hit the same one or two
+      // spans: one atomicAdd per (round, span) reserves the slots of all its lanes.
+      const bool hit = iou > iou_thr;
+      int span_idx = -1;
+      if (hit) {
         const int2 cs = __ldg(combo_span + (tg & 255));
-        const ssdx_grid_span sp = spans[cs.x + r / cs.y];
+        span_idx = cs.x + r / cs.y;
+      }
+      const unsigned active = __activemask();
+      const unsigned peers = __match_any_sync(active, span_idx);
+      if (hit) {
+        const ssdx_grid_span sp = spans[span_idx];
         unsigned char* reg = lists + (size_t)b * span_list_stride(A) + span_list_offset(sp.a_lo);
-        const u64 pos = atomicAdd(reinterpret_cast<u64*>(reg), 1ull);
+        const int leader = __ffs(peers) - 1;
+        const int my_rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+        u64 base = 0ull;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(reinterpret_cast<u64*>(reg), (u64)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const u64 pos = base + (u64)my_rank;
         if (pos < (u64)span_list_capacity(sp.a_lo, sp.n))
           reinterpret_cast<u64*>(reg)[1 + pos] =
               ((u64)(unsigned)(a - sp.a_lo) << 48) | ((u64)(unsigned)(gc0 + g) << 32) | (u64)bits;
@@ -823,12 +837,11 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // K2: anchor side of one span (a row range of one feature map) of one image + the span's output rows.
-// grid (n_spans, B).  Dynamic shared memory: grids of the span's map | their axis arrays | val (u32 per anchor) |
-// tab (u16) | s1 (u16) | pos (i32).
+// grid (n_spans, B).  Dynamic shared memory: grids of the span's map | their axis arrays | val (u32 per anchor; reused
+// as the list of positives once the matches are final) | tab (u16) | s1 (u16).
 __host__ __device__ inline size_t grid_span_smem_bytes(int max_span_anchors, int max_span_combos, int map_axes) {
   const size_t n8 = (size_t)(max_span_anchors + 7) / 8 * 8;
-  return (size_t)max_span_combos * sizeof(ssdx_grid_combo) + (size_t)map_axes * 4 + n8 * 4 + n8 * 2 + n8 * 2 +
-         n8 * 4 + 16;
+  return (size_t)max_span_combos * sizeof(ssdx_grid_combo) + (size_t)map_axes * 4 + n8 * 4 + n8 * 2 + n8 * 2 + 16;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -852,7 +865,7 @@ __global__ void __launch_bounds__(kThreads)
   unsigned* s_val = (unsigned*)(s_ax + map_axes_smem);
   unsigned short* s_tab = (unsigned short*)(s_val + n8);
   unsigned short* s_s1 = s_tab + n8;     // max(S1(a)) + 1, 0 = empty
-  int* s_pos = (int*)(s_s1 + n8);        // compacted positives: (anchor - a_lo) << 16 | matched GT
+  int* s_pos = (int*)s_val;              // compacted positives: (anchor - a_lo) << 16 | matched GT (s_val is dead by then)
 
   const ssdx_grid_span sp = spans[blockIdx.x];
   const int b = blockIdx.y;
