@@ -436,3 +436,24 @@ def test_keras_layer_forms_mirror_the_reference_contract(ssdseglib):
     assert Seg(name="segmentation-suppression").get_config() == {}
     # the package itself: plain callables here (no TensorFlow), aliases always present
     assert ssdseglib.layers.NonMaximumSuppression is ssdseglib.layers.PlainNonMaximumSuppression
+
+
+def test_nccl_binding_is_optional_and_fails_cleanly(ssdseglib):
+    """libssdx binds NCCL at first use with dlopen (no link dependency): asking for the version either works (a
+    libnccl.so.2 is loadable in this process) or returns SSDX_ERR_NCCL with a message - never a crash; a NULL
+    communicator is an invalid argument."""
+    sx = ssdseglib._ssdx
+    needed = subprocess.run(["readelf", "-d", os.path.join(PKG, "lib", "libssdx.so")], capture_output=True,
+                            text=True).stdout
+    assert "libnccl" not in needed  # no DT_NEEDED entry for NCCL
+    ver = ctypes.c_int(-1)
+    st = sx.lib.ssdx_nccl_version(ctypes.byref(ver))
+    assert st in (0, sx.SSDX_ERR_NCCL)
+    if st == 0:
+        assert ver.value >= 20000
+    else:
+        assert b"NCCL" in sx.lib.ssdx_last_error()
+    assert sx.lib.ssdx_allgather_counts(None, None, None, 4, None) == sx.SSDX_ERR_INVALID
+    with pytest.raises(ValueError):
+        sx.set_option("encode_path", "no-such-path")
+    sx.set_option("encode_path", "auto")
