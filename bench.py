@@ -823,7 +823,8 @@ def gpu_arm(args, rank, world, local_rank):
     if "encode" in stages:
         n_more = max(2, min(e2e_steps, 5))
         np_in = (boxes, labels, counts)
-        coder.encode_batch(*np_in)
+        for _ in range(3):  # the pinned result blocks come from torch's caching host allocator: two generations of them
+            enc_l, enc_o = coder.encode_batch(*np_in)  # are alive at a time, both must exist before the timed calls
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_more):
@@ -836,7 +837,8 @@ def gpu_arm(args, rank, world, local_rank):
             "api": "DataEncoderDecoder.encode_batch(NumPy) -> (labels, offsets) NumPy"}
         h_off_np = o_offsets.cpu().numpy()
         h_log_np = torch.log(d_scores.clamp_min(1e-30)).cpu().numpy()
-        nms_layer.call_on_offsets_and_logits(dec_layer, h_off_np, h_log_np)
+        for _ in range(2):
+            nms_layer.call_on_offsets_and_logits(dec_layer, h_off_np, h_log_np)
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_more):
