@@ -273,8 +273,8 @@ def eval_config(world):
     return {"workload": "eval_b4096", "stages": ["eval"], "global_batch": B, "images_per_gpu": B // world,
             "predictions_per_image": EVAL_K, "gt_per_image": G_STD, "classes": C_STD, "iou_thr": EVAL_THR,
             "parallelism": f"images sharded x{world}" + (
-                "; ssdx_allgather_counts (ncclAllGather of the (C,3) int64 tables) + all-gather of the TP / confidence "
-                "/ label arrays for the AP tail" if world > 1 else ", no collective"),
+                "; ssdx_allgather_eval: the (C,3) int64 count tables and the TP / confidence / label arrays for the AP "
+                "tail in one NCCL launch (ncclGroupStart/End)" if world > 1 else ", no collective"),
             "l2": "flushed with a 256 MB fill before every timed step (the 17 MB working set would stay in L2)",
             "gpu_launch": "eager, per-step events"}
 
@@ -363,12 +363,11 @@ def gpu_arm_eval(args, rank, world, local_rank):
                                      n, K, G, C, 0, EVAL_THR, tp.data_ptr(), counts.data_ptr(), dev, sp))
         if world > 1:
             # the one collective of the path: (C,3) int64 per rank, NCCL all-gather on this stream
-            sx.check(sx.lib.ssdx_allgather_counts(comm.handle, counts.data_ptr(), gathered.data_ptr(), C, sp))
+            # and the flags the AP tail integrates (7.4 MB in all), in the same NCCL launch
+            sx.check(sx.lib.ssdx_allgather_eval(comm.handle, counts.data_ptr(), gathered.data_ptr(), C, tp.data_ptr(),
+                                                d_conf.data_ptr(), d_pl.data_ptr(), n * K, g_tp.data_ptr(),
+                                                g_conf.data_ptr(), g_pl.data_ptr(), sp))
             sx.check(sx.lib.ssdx_sum_counts(gathered.data_ptr(), world, C, total_counts.data_ptr(), dev, sp))
-            # the flags the AP tail integrates, gathered so that every rank holds the global arrays (7.4 MB in all)
-            dist.all_gather_into_tensor(g_tp, tp)
-            dist.all_gather_into_tensor(g_conf, d_conf)
-            dist.all_gather_into_tensor(g_pl, d_pl)
             cnt = total_counts
         else:
             cnt = counts
@@ -399,11 +398,10 @@ def gpu_arm_eval(args, rank, world, local_rank):
                                      n, K, G, C, 0, EVAL_THR, tp.data_ptr(), counts.data_ptr(), dev, sp))
         ev_tp[k].record(stream)
         if world > 1:
-            sx.check(sx.lib.ssdx_allgather_counts(comm.handle, counts.data_ptr(), gathered.data_ptr(), C, sp))
+            sx.check(sx.lib.ssdx_allgather_eval(comm.handle, counts.data_ptr(), gathered.data_ptr(), C, tp.data_ptr(),
+                                                d_conf.data_ptr(), d_pl.data_ptr(), n * K, g_tp.data_ptr(),
+                                                g_conf.data_ptr(), g_pl.data_ptr(), sp))
             sx.check(sx.lib.ssdx_sum_counts(gathered.data_ptr(), world, C, total_counts.data_ptr(), dev, sp))
-            dist.all_gather_into_tensor(g_tp, tp)
-            dist.all_gather_into_tensor(g_conf, d_conf)
-            dist.all_gather_into_tensor(g_pl, d_pl)
         sx.check(sx.lib.ssdx_average_precision(g_tp.data_ptr(), g_conf.data_ptr(), g_pl.data_ptr(), B * K, C,
                                                (total_counts if world > 1 else counts).data_ptr(), 0, ap.data_ptr(),
                                                ws_ap.data_ptr(), ws_ap.numel(), dev, sp))

@@ -194,6 +194,12 @@ SSDX_API int ssdx_comm_create(const uint8_t* id128, int32_t nranks, int32_t rank
 SSDX_API int ssdx_comm_destroy(ssdx_comm* comm);
 SSDX_API int ssdx_allgather_counts(ssdx_comm* comm, const int64_t* counts, int64_t* gathered, int32_t num_classes,
                                    ssdx_stream stream);
+/* Everything a rank needs for the global AP tail (evaluators.py:159-187) in ONE NCCL launch (ncclGroupStart/End): the
+ * count tables as above plus the TP flags, confidences and labels of every rank's n_local predictions (the same n_local
+ * on every rank), rank-major = image-major for contiguous shards: all_tp / all_confidence / all_label (nranks * n_local). */
+SSDX_API int ssdx_allgather_eval(ssdx_comm* comm, const int64_t* counts, int64_t* gathered_counts, int32_t num_classes,
+                                 const uint8_t* tp, const float* confidence, const int32_t* label, int64_t n_local,
+                                 uint8_t* all_tp, float* all_confidence, int32_t* all_label, ssdx_stream stream);
 /* out (C,3) i64 = sum over the nranks tables of gathered (nranks,C,3): the global counts on every rank. */
 SSDX_API int ssdx_sum_counts(const int64_t* gathered, int32_t nranks, int32_t num_classes, int64_t* out, int device,
                              ssdx_stream stream);

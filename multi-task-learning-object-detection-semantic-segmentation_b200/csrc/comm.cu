@@ -22,6 +22,7 @@ typedef struct {
 } ncclUniqueId;
 typedef int ncclResult_t;            // 0 = ncclSuccess
 constexpr int kNcclInt64 = 4;        // ncclDataType_t::ncclInt64
+constexpr int kNcclUint8 = 1, kNcclInt32 = 2, kNcclFloat32 = 7;
 
 struct NcclApi {
   void* lib = nullptr;
@@ -29,6 +30,8 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*GetVersion)(int*) = nullptr;
 };
@@ -48,9 +51,11 @@ void load_nccl() {
   a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
   a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
+  a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
   a.GetVersion = (decltype(a.GetVersion))dlsym(h, "ncclGetVersion");
-  if (a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather) g_nccl = a;
+  if (a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GroupStart && a.GroupEnd) g_nccl = a;
 }
 
 const NcclApi* nccl() {
@@ -159,6 +164,31 @@ int ssdx_allgather_counts(ssdx_comm* comm, const int64_t* counts, int64_t* gathe
   const ncclResult_t r = a->AllGather(counts, gathered, (size_t)num_classes * 3, kNcclInt64, comm->comm,
                                       (cudaStream_t)stream);
   if (r != 0) return nccl_fail("ncclAllGather", r);
+  return SSDX_OK;
+}
+
+int ssdx_allgather_eval(ssdx_comm* comm, const int64_t* counts, int64_t* gathered_counts, int32_t num_classes,
+                        const uint8_t* tp, const float* confidence, const int32_t* label, int64_t n_local,
+                        uint8_t* all_tp, float* all_confidence, int32_t* all_label, ssdx_stream stream) {
+  SSDX_CHECK_ARG(comm != nullptr && counts != nullptr && gathered_counts != nullptr && num_classes >= 1,
+                 "ssdx_allgather_eval: bad argument");
+  SSDX_CHECK_ARG(n_local >= 0 && (n_local == 0 || (tp && confidence && label && all_tp && all_confidence && all_label)),
+                 "ssdx_allgather_eval: prediction arrays are NULL");
+  const NcclApi* a = nccl();
+  SSDX_NCCL_REQUIRED(a);
+  SSDX_DEVICE(comm->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  ncclResult_t r = a->GroupStart();  // the four gathers leave as one NCCL launch
+  if (r != 0) return nccl_fail("ncclGroupStart", r);
+  ncclResult_t first = a->AllGather(counts, gathered_counts, (size_t)num_classes * 3, kNcclInt64, comm->comm, s);
+  if (n_local > 0) {
+    if (first == 0) first = a->AllGather(tp, all_tp, (size_t)n_local, kNcclUint8, comm->comm, s);
+    if (first == 0) first = a->AllGather(confidence, all_confidence, (size_t)n_local, kNcclFloat32, comm->comm, s);
+    if (first == 0) first = a->AllGather(label, all_label, (size_t)n_local, kNcclInt32, comm->comm, s);
+  }
+  r = a->GroupEnd();
+  if (first != 0) return nccl_fail("ncclAllGather", first);
+  if (r != 0) return nccl_fail("ncclGroupEnd", r);
   return SSDX_OK;
 }
 

@@ -62,6 +62,26 @@ class CountsCommunicator:
                                                            counts.shape[0], self._sx.stream_ptr(self.device)))
         return out
 
+    def all_gather_eval(self, counts, tp, confidence, label):
+        """Everything the global AP tail needs in one NCCL launch (`ssdx_allgather_eval`): counts (C, 3) int64 ->
+        (world, C, 3); tp uint8 / confidence float32 / label int32, each with the same number of elements on every
+        rank -> flat (world * n) arrays, rank-major."""
+        torch = self._sx._torch()
+        counts, tp = counts.contiguous(), tp.contiguous().view(-1)
+        confidence, label = confidence.contiguous().view(-1), label.contiguous().view(-1)
+        assert tp.dtype == torch.uint8 and confidence.dtype == torch.float32 and label.dtype == torch.int32
+        n = tp.numel()
+        assert confidence.numel() == n and label.numel() == n
+        dev = counts.device
+        g_counts = torch.empty((self.world,) + tuple(counts.shape), dtype=torch.int64, device=dev)
+        g_tp = torch.empty(self.world * n, dtype=torch.uint8, device=dev)
+        g_conf = torch.empty(self.world * n, dtype=torch.float32, device=dev)
+        g_label = torch.empty(self.world * n, dtype=torch.int32, device=dev)
+        self._sx.check(self._sx.lib.ssdx_allgather_eval(
+            self.handle, counts.data_ptr(), g_counts.data_ptr(), counts.shape[0], tp.data_ptr(), confidence.data_ptr(),
+            label.data_ptr(), n, g_tp.data_ptr(), g_conf.data_ptr(), g_label.data_ptr(), self._sx.stream_ptr(self.device)))
+        return g_counts, g_tp, g_conf, g_label
+
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
             self._sx.lib.ssdx_comm_destroy(self.handle)

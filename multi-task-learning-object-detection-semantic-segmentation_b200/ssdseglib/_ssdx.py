@@ -66,6 +66,7 @@ SIGNATURES = {
     "ssdx_comm_destroy": (C.c_int, [_vp]),
     "ssdx_allgather_counts": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp]),
     "ssdx_sum_counts": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, C.c_int, _vp]),
+    "ssdx_allgather_eval": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "ssdx_average_precision_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "ssdx_average_precision": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, _vp, C.c_size_t,
                                          C.c_int, _vp]),

@@ -1053,6 +1053,18 @@ def test_all_gather_counts_over_nccl(lib, tmp_path):
         dist.all_reduce(mine)
         assert np.array_equal(np.asarray(c_all), mine.cpu().numpy()) and np.array_equal(tp, tp1)
         assert torch.cuda.current_device() == local
+        # the grouped gather of the AP inputs against torch.distributed's all-gathers
+        comm = _dist.CountsCommunicator(None, local)
+        n = 1000
+        tpf = torch.from_numpy((rng.uniform(size=n) < 0.3).astype(np.uint8)).cuda()
+        cf = torch.from_numpy(rng.uniform(size=n).astype(np.float32)).cuda()
+        lb = torch.from_numpy(rng.integers(0, 4, size=n).astype(np.int32)).cuda()
+        gc_, gt_, gf_, gl_ = comm.all_gather_eval(counts, tpf, cf, lb)
+        for mine, got in ((tpf, gt_), (cf, gf_), (lb, gl_), (counts.view(-1), gc_.view(-1))):
+            ref = torch.empty(w * mine.numel(), dtype=mine.dtype, device=mine.device)
+            dist.all_gather_into_tensor(ref, mine.contiguous())
+            assert torch.equal(ref, got)
+        comm.close()
         _dist.close_communicators()
         dist.barrier()
         if r == 0:

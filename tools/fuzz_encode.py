@@ -1,7 +1,7 @@
 """GPU box: randomized differential test of the encode drivers (one CTA per image / anchor-tiled) against the C oracle:
 random anchor subsets and synthetic grids, GT counts (incl. 0 and ragged), integer coordinates (exact IoU ties),
 duplicated GT boxes, GT boxes equal to anchors, thresholds, class counts, out-of-range labels.
-usage: python tools/fuzz_encode.py [cases] [seed]"""
+usage: python tools/fuzz_encode.py [cases] [seed] [encode_path]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multi-task-learning-object-detection-semantic-segmentation_b200"))
@@ -87,4 +87,6 @@ def run(cases: int, seed: int, verbose: bool = True) -> int:
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 3:  # pin one encode driver: grid_fused | grid_split | tile_fused | tile_tiled
+        ssdseglib._ssdx.set_option("encode_path", sys.argv[3])
     sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 200, int(sys.argv[2]) if len(sys.argv) > 2 else 0) else 0)
