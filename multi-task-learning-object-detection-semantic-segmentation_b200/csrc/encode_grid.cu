@@ -20,14 +20,19 @@
 // centre in every grid.  On the reference configuration (9600 anchors, 16 GT boxes) the windows hold ~250 cells per
 // image for ~200 pairs above the threshold - the 153,600-pair matrix is never looked at.
 //
+// The anchors themselves are rebuilt from per-grid axis arrays x0[W] | x1[W] | y0[H] | y1[H] (the very floats of the
+// table) held in shared memory: corners, area and centroid of any cell, bit for bit, without a global read.
+//
 // Drivers:
-//   fused : one CTA per image (batch >= number of SMs, A small enough for per-anchor tables in shared memory).  The
-//           constant background rows of the whole image leave as TMA bulk stores at the start (as in encode.cu);
-//           seeds -> windows -> block scan -> cells (pass 0: per-anchor max IoU and per-GT best anchor; pass 1:
-//           lowest GT index among the maxima) -> closed form -> the positives are patched over the background.
-//   split : K1 grid (GT chunks, images) computes the per-GT best anchors, K2 grid (row spans of a feature map,
-//           images) the anchor side of its span and writes the span's rows: small batches and large tables
-//           (dense stress: 100k anchors x 256 GT boxes).
+//   fused : persistent, warp-specialised CTAs, one image at a time per CTA (tables up to 32768 anchors / 256 GT
+//           boxes).  A producer warp streams the constant background rows of the image as TMA bulk stores, a few in
+//           flight at a time; the matching warps own whole GT boxes (lanes = grids: seed, bound, windows and their
+//           prefix sum stay inside the warp), the few anchors with a pair above the threshold claim slots of a
+//           compact table (pass 0: slot max IoU + per-GT best; pass 1: lowest GT index among a slot's maxima), then
+//           the closed form, and the positives are patched over the background as whole 32-byte sectors.
+//   split : K1 grid (32 GT boxes, image) walks the windows once: per-GT best pairs + a hit list per row span of a
+//           feature map; K2 grid (span, image) reduces its list, applies the closed form and writes the span's rows:
+//           larger tables (dense stress: 100k anchors x 256 GT boxes).
 #include <algorithm>
 
 #include "common.cuh"
