@@ -44,6 +44,23 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigne
                "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                : "memory");
 }
+// the same with an L2 eviction policy (createpolicy.fractional.L2::evict_first / evict_last)
+__device__ __forceinline__ void bulk_store_hint(void* gdst, const void* ssrc, unsigned bytes, unsigned long long pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(
+                   __cvta_generic_to_global(gdst)),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
