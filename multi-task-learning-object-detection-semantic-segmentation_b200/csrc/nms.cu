@@ -1149,14 +1149,17 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   const size_t box_row0 = (size_t)b * A;
   const float* img_scores = scores + (size_t)b * A * C;
   const u64* lst = lists + (size_t)b * kCap;
+  PHASE_T0();
   for (int i = tid; i < n; i += kFastThreads) s_list[i] = lst[i];  // (n = 0 after an overflow: refill right away)
   if (tid == 0) s_nsel = 0;
   __syncthreads();
+  PHASE_ADD(10);  // list load
 
   int n_sel = 0;
   while (true) {
     // ---- sort the current tier (merged order) ----
     fast_sort(s_list, s_tmp, n, tid);
+    PHASE_ADD(11);  // sort
     if (span == 0ull) {  // band that held the lower half of this tier -> width expected to hold the refill target
       const u64 c_mid = (n >= 2) ? s_list[n >> 1] : 0ull;
       const u64 c_bot = (n >= 2) ? s_list[n - 1] : 0ull;
@@ -1179,6 +1182,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
         s_chbox[tid] = make_hbox(nb);
       }
       __syncthreads();
+      PHASE_ADD(12);  // box gather
       for (int base = 0; base < gn && n_sel < K; base += kBlk) {
         const int m = min(kBlk, gn - base);
         const int ci = tid >> 2, part = tid & 3;
@@ -1243,6 +1247,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
           if (part == 0) s_row[ci] = ((u64)hi << 32) | (u64)lo;
         }
         __syncthreads();
+        PHASE_ADD(13);  // pair tests
         if (warp == kFastThreads / 32 - 1) {  // the arbiter favours the highest warp id: keep the serial part there
           const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
           const u64 ra = s_row[lane], rb = s_row[lane + 32];
@@ -1292,6 +1297,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
           if (lane == 0) s_nsel = n_sel + min(room, n_lo + __popc(kept_hi));
         }
         __syncthreads();
+        PHASE_ADD(14);  // block resolve
         n_sel = s_nsel;
       }
     }
@@ -1372,6 +1378,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
       }
     }
     __syncthreads();
+    PHASE_ADD(15);  // refill scans
   }
   __syncthreads();
   // ---- rows, already in merge order: [label, prob, xmin, ymin, xmax, ymax] (layers.py:155-162), zero padding ----
@@ -1393,6 +1400,10 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   if (out_idx)
     for (int e = n_sel + tid; e < K; e += kFastThreads) out_idx[(size_t)b * K + e] = -1;
   if (out_valid && tid == 0) out_valid[b] = n_sel;
+  PHASE_ADD(16);  // rows
+#ifdef SSDX_PHASE_TIMERS
+  if (tid == 0) atomicAdd(&g_phase_cycles[18], 1ull);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ 3. generic path
