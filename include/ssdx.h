@@ -59,7 +59,7 @@ SSDX_API int ssdx_device_count(int* count);
 /* Process-level dispatch override; every path of an entry point gives identical results, the options exist for tests
  * and tuning runs.  key "encode_path": "auto" | "grid_fused" | "grid_split" (closed-form windows, anchor tables that
  * are unions of regular grids) | "tile_fused" | "tile_tiled" (tile match, any anchor table);
- * key "nms_path": "auto" | "perclass" | "pcta" | "generic".  A forced path that cannot serve a call (table is not a
+ * key "nms_path": "auto" | "perclass" | "pcta" | "generic" | "blocked".  A forced path that cannot serve a call (table is not a
  * grid, shapes too large for one CTA per image) falls back to the automatic choice for that call. */
 SSDX_API int ssdx_set_option(const char* key, const char* value);
 

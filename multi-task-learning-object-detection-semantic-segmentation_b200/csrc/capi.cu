@@ -35,8 +35,9 @@ static std::atomic<int> g_encode_path(SSDX_ENC_AUTO);
 static std::atomic<int> g_nms_path(0);
 int ssdx_option_encode_path() { return g_encode_path.load(std::memory_order_relaxed); }
 const char* ssdx_option_nms_path() {
-  static const char* const names[4] = {nullptr, "perclass", "pcta", "generic"};
-  return names[g_nms_path.load(std::memory_order_relaxed) & 3];
+  static const char* const names[5] = {nullptr, "perclass", "pcta", "generic", "blocked"};
+  const int i = g_nms_path.load(std::memory_order_relaxed);
+  return names[(i >= 0 && i < 5) ? i : 0];
 }
 
 int ssdx_sm_count(int device) {
@@ -225,8 +226,8 @@ int ssdx_set_option(const char* key, const char* value) {
         return SSDX_OK;
       }
   } else if (strcmp(key, "nms_path") == 0) {
-    static const char* const v[4] = {"auto", "perclass", "pcta", "generic"};
-    for (int i = 0; i < 4; ++i)
+    static const char* const v[5] = {"auto", "perclass", "pcta", "generic", "blocked"};
+    for (int i = 0; i < 5; ++i)
       if (strcmp(value, v[i]) == 0) {
         g_nms_path.store(i);
         return SSDX_OK;

@@ -72,6 +72,7 @@ constexpr int kMergeThreads = 256;
 #endif
 constexpr int kAllRank = SSDX_ALL_RANK;       // merged select: threshold at the 26th largest sample => ~416 +- 80 listed
 constexpr int kAllRefillTarget = 384;
+constexpr int kChunkTiles = 36;  // 32 x 32 tiles of the lower triangle of a 256-candidate chunk
 
 #ifdef SSDX_PHASE_TIMERS
 static __device__ unsigned long long g_phase_cycles[32];
@@ -133,6 +134,17 @@ __device__ __forceinline__ HBox make_hbox(const float4 n) {
 }
 __device__ __forceinline__ bool hboxes_may_overlap(const HBox a, const HBox b) {
   return __hbgt2(a.mx, b.mn) && __hbgt2(b.mx, a.mn);
+}
+// Prefilter copy with the class folded in: boxes of class c are shifted by (2 * (c & 15), 2 * (c >> 4)) before the
+// directed roundings (fp32 add and fp16 conversion both round minima down and maxima up), so that boxes of the same
+// class keep "exact overlap implies prefilter overlap" while boxes of different classes inside the usual [-0.5, 1.5]
+// range never pass it.  Pairs that pass are still decided by the class test and the exact fp32 IoU.
+__device__ __forceinline__ HBox make_hbox_cls(const float4 n, const int cls) {
+  const float oy = (float)(2 * (cls & 15)), ox = (float)(2 * (cls >> 4));
+  HBox h;
+  h.mn = __halves2half2(__float2half_rd(__fadd_rd(n.x, oy)), __float2half_rd(__fadd_rd(n.y, ox)));
+  h.mx = __halves2half2(__float2half_ru(__fadd_ru(n.z, oy)), __float2half_ru(__fadd_ru(n.w, ox)));
+  return h;
 }
 // exact TF IoU test for a pair that overlaps
 __device__ __forceinline__ bool iou_exceeds_overlapping(const float4 a, const float aa, const float4 b, const float ab,
@@ -200,7 +212,7 @@ __device__ __forceinline__ int bitonic_sort_desc(u64* v, const int n, const int 
 // shared-memory exchange (double-buffered: one barrier per such stage).  9 barriers instead of 45 for 512 keys.
 template <int EPT>
 __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64* buf1,
-                                                  const int tid) {
+                                                  const int tid, const bool active = true) {
   constexpr int N = 256 * EPT;
   int flip = 0;
 #pragma unroll
@@ -223,59 +235,70 @@ __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64*
           }
         }
       } else if (j < 32) {
+        if (active) {  // (whole warps are active or not)
 #pragma unroll
-        for (int r = 0; r < EPT; ++r) {
-          const int e = r * 256 + tid;
-          const u64 p = __shfl_xor_sync(0xFFFFFFFFu, v[r], j);
-          const bool take_max = (((e & j) == 0) == ((e & k) == 0));
-          v[r] = ((v[r] > p) == take_max) ? v[r] : p;  // keys are distinct or equal: one compare, one select
+          for (int r = 0; r < EPT; ++r) {
+            const int e = r * 256 + tid;
+            const u64 p = __shfl_xor_sync(0xFFFFFFFFu, v[r], j);
+            const bool take_max = (((e & j) == 0) == ((e & k) == 0));
+            v[r] = ((v[r] > p) == take_max) ? v[r] : p;  // keys are distinct or equal: one compare, one select
+          }
         }
       } else {
         u64* buf = flip ? buf1 : buf0;
         flip ^= 1;
+        if (active) {
 #pragma unroll
-        for (int r = 0; r < EPT; ++r) buf[r * 256 + tid] = v[r];
+          for (int r = 0; r < EPT; ++r) buf[r * 256 + tid] = v[r];
+        }
         __syncthreads();
+        if (active) {
 #pragma unroll
-        for (int r = 0; r < EPT; ++r) {
-          const int e = r * 256 + tid;
-          const u64 p = buf[e ^ j];
-          const bool take_max = (((e & j) == 0) == ((e & k) == 0));
-          v[r] = ((v[r] > p) == take_max) ? v[r] : p;
+          for (int r = 0; r < EPT; ++r) {
+            const int e = r * 256 + tid;
+            const u64 p = buf[e ^ j];
+            const bool take_max = (((e & j) == 0) == ((e & k) == 0));
+            v[r] = ((v[r] > p) == take_max) ? v[r] : p;
+          }
         }
       }
     }
   }
 }
 
-// sort s_list[0..n) descending for the fast kernel (256 threads); uniform control flow
+// sort s_list[0..n) descending for the fast kernels (threads 0..255 hold the keys; the threads of a wider CTA pass
+// active = false and only take part in the barriers); uniform control flow
 __device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n,
-                                          const int tid) {
+                                          const int tid, const bool active = true) {
   if (n <= 256) {
     u64 v[1];
-    v[0] = (tid < n) ? s_list[tid] : 0ull;
+    v[0] = (active && tid < n) ? s_list[tid] : 0ull;
     __syncthreads();
-    bitonic_sort_regs<1>(v, s_list, s_tmp, tid);
+    bitonic_sort_regs<1>(v, s_list, s_tmp, tid, active);
     __syncthreads();
-    s_list[tid] = v[0];
+    if (active) s_list[tid] = v[0];
   } else if (n <= 512) {
     u64 v[2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) v[r] = (r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
+    for (int r = 0; r < 2; ++r) v[r] = (active && r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
     __syncthreads();
-    bitonic_sort_regs<2>(v, s_list, s_tmp, tid);
+    bitonic_sort_regs<2>(v, s_list, s_tmp, tid, active);
     __syncthreads();
+    if (active) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) s_list[r * 256 + tid] = v[r];
+      for (int r = 0; r < 2; ++r) s_list[r * 256 + tid] = v[r];
+    }
   } else {
     u64 v[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) v[r] = (r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
+    for (int r = 0; r < 4; ++r) v[r] = (active && r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
     __syncthreads();
-    bitonic_sort_regs<4>(v, s_list, s_tmp, tid);
+    bitonic_sort_regs<4>(v, s_list, s_tmp, tid, active);
     __syncthreads();
+    if (active) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) s_list[r * 256 + tid] = v[r];
+      for (int r = 0; r < 4; ++r) s_list[r * 256 + tid] = v[r];
+    }
   }
   __syncthreads();
 }
@@ -964,15 +987,15 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
 
 // ------------------------------------------------------------------------------------------ 1m. merged select
 // info per image: [0] listed candidates (may exceed kCap), [1] threshold key (every candidate with key >= it is listed)
-template <bool VEC4, bool LOGITS>
-__global__ void __launch_bounds__(kSelThreads)
+template <bool VEC4, bool LOGITS, int NT>  // NT threads per image: 256, or 512 / 1024 when the batch leaves SMs idle
+__global__ void __launch_bounds__(NT)
     ssdx_nms_select_all_kernel(const float* __restrict__ scores, const float* __restrict__ cscale, const int A,
                                const int C, const float score_thr, const int all_rank, u64* __restrict__ lists,
                                int* __restrict__ info) {
   constexpr bool logits = LOGITS;
   // LOGITS (VEC4 only): `scores` holds raw logits, the probabilities are ssdx_softmax4 of each row, computed as
   // the rows are read (never written to memory)
-  __shared__ unsigned s_max[kSelThreads];  // per-thread maximum of the sampled keys
+  __shared__ unsigned s_max[NT];  // per-thread maximum of the sampled keys
   __shared__ unsigned s_T;
   __shared__ int s_cnt;
   const int b = blockIdx.x;
@@ -984,7 +1007,7 @@ __global__ void __launch_bounds__(kSelThreads)
   // ---- sample: every 16th anchor (jittered), all classes; each thread keeps the largest key it sees ----
   {
     unsigned kmax = 0u;  // 0 = no candidate
-    for (int k = tid; k < NS; k += kSelThreads) {
+    for (int k = tid; k < NS; k += NT) {
       int a = k * kSampleStride + ((k * 7) & (kSampleStride - 1));
       a = a < A ? a : A - 1;
       if (VEC4) {
@@ -1007,11 +1030,11 @@ __global__ void __launch_bounds__(kSelThreads)
   //      above it (usually just that many: the top keys of a sample sit in different threads), so ~16 * kAllRank
   //      candidates get listed.  One warp bisects over the 256 maxima held in registers. ----
   if (tid < 32) {
-    unsigned v[kSelThreads / 32];
+    unsigned v[NT / 32];
     int nz = 0;
     unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll
-    for (int r = 0; r < kSelThreads / 32; ++r) {
+    for (int r = 0; r < NT / 32; ++r) {
       v[r] = s_max[r * 32 + lane];
       nz += v[r] != 0u;
       kmax = max(kmax, v[r]);
@@ -1028,7 +1051,7 @@ __global__ void __launch_bounds__(kSelThreads)
         const unsigned mid = lo + ((hi - lo) >> 1);
         int cnt = 0;
 #pragma unroll
-        for (int r = 0; r < kSelThreads / 32; ++r) cnt += v[r] >= mid;
+        for (int r = 0; r < NT / 32; ++r) cnt += v[r] >= mid;
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
         if (cnt >= all_rank) {
           lo = mid;
@@ -1053,18 +1076,18 @@ __global__ void __launch_bounds__(kSelThreads)
   if (VEC4) {
     constexpr int kBatch = 8;  // independent 128-bit streaming loads in flight per thread
     const float4 cf4 = class_factor4(cscale);
-    for (int a0 = tid; a0 < A; a0 += kSelThreads * kBatch) {
+    for (int a0 = tid; a0 < A; a0 += NT * kBatch) {
       float4 sb[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const int a = a0 + u * kSelThreads;
+        const int a = a0 + u * NT;
         sb[u] = (a < A) ? __ldcs(reinterpret_cast<const float4*>(img) + a)
                         : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
       if (logits) {
 #pragma unroll
         for (int u = 0; u < kBatch; ++u)
-          if (a0 + u * kSelThreads < A) sb[u] = ssdx_softmax4(sb[u]);
+          if (a0 + u * NT < A) sb[u] = ssdx_softmax4(sb[u]);
       }
       unsigned hits = 0u;  // bit 4*u + c
 #pragma unroll
@@ -1078,7 +1101,7 @@ __global__ void __launch_bounds__(kSelThreads)
       while (hits != 0u) {  // the score is re-read (L1/L2 hit) instead of indexing the register batch dynamically
         const int bit = __ffs(hits) - 1;
         hits &= hits - 1u;
-        const int a = a0 + (bit >> 2) * kSelThreads, c = bit & 3;
+        const int a = a0 + (bit >> 2) * NT, c = bit & 3;
         float s;
         if (logits) {
           const float4 p = ssdx_softmax4(__ldg(reinterpret_cast<const float4*>(img) + a));
@@ -1092,7 +1115,7 @@ __global__ void __launch_bounds__(kSelThreads)
     }
   } else {
     const int total = A * C;  // flat coalesced walk
-    for (int e = tid; e < total; e += kSelThreads) {
+    for (int e = tid; e < total; e += NT) {
       const float s = cscale ? __fmul_rn(__ldcs(img + e), __ldg(cscale + e % C)) : __ldcs(img + e);
       if (s >= t_lo) {
         const int a = e / C;
@@ -1109,14 +1132,19 @@ __global__ void __launch_bounds__(kSelThreads)
 }
 
 // ------------------------------------------------------------------------------------------ 2m. merged fast path
-template <int MAXSEL, int MINB, bool LOGITS>  // MAXSEL >= K; MINB resident CTAs per SM (7 * 148 >= 1024: one wave at
-                                              // batch 1024); LOGITS: `scores` holds raw logits of 4 classes
-__global__ void __launch_bounds__(kFastThreads, MINB)
+// MAXSEL >= K; MINB resident CTAs per SM (7 * 148 >= 1024: one wave at batch 1024); LOGITS: `scores` holds raw logits
+// of 4 classes.  ALGO 1 (default): the sorted candidates are taken in chunks of up to 256; a chunk is tested against
+// the boxes kept by earlier chunks and against itself as 32 x 32 tiles of a lower-triangular bit matrix (all warps,
+// no barrier inside), then one warp resolves the chunk 64 candidates at a time from the bit rows.  ALGO 0
+// (ssdx_set_option("nms_path", "blocked")): 64 candidates at a time, each against the kept boxes, two barriers per 64.
+template <int MAXSEL, int MINB, bool LOGITS, int ALGO, int NT>
+__global__ void __launch_bounds__(NT, MINB)
     ssdx_nms_fast_all_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                              const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                              const int K, const float iou_thr, const float score_thr, float* __restrict__ out,
                              int* __restrict__ out_valid, int* __restrict__ out_idx) {
   constexpr bool logits = LOGITS;
+  static_assert(ALGO == 1 || NT == kFastThreads, "the blocked form runs 256 threads");
   __shared__ u64 s_list[kCap];
   __shared__ u64 s_tmp[kCap];  // second exchange buffer of the sort; the candidate arrays below alias it
   __shared__ float4 s_sbox[MAXSEL];
@@ -1124,8 +1152,12 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   __shared__ u64 s_pick[MAXSEL];
   __shared__ unsigned char s_scls[MAXSEL];
   __shared__ HBox s_shbox[MAXSEL];  // prefilter copies of the kept boxes
-  __shared__ u64 s_row[kBlk];  // per candidate of the block: earlier candidates (j < i) that suppress it
-  __shared__ int s_sup[kBlk];
+  __shared__ u64 s_row[ALGO == 0 ? kBlk : 1];  // per candidate of the block: earlier candidates (j < i) that suppress it
+  __shared__ int s_sup[ALGO == 0 ? kBlk : 1];
+  // ALGO 1: tile (g, jb), jb <= g, at index g (g + 1) / 2 + jb: bit jj of word `lane` = candidate 32 jb + jj of the
+  // chunk suppresses candidate 32 g + lane (same class, IoU > threshold, earlier in the order)
+  __shared__ unsigned s_tile[ALGO == 1 ? kChunkTiles * 32 : 1];
+  __shared__ unsigned char s_supb[ALGO == 1 ? kFastThreads : 1];  // suppressed by a box kept in an earlier chunk / beyond m
   __shared__ int s_nsel, s_n;
   float4* s_cbox = reinterpret_cast<float4*>(s_tmp);                              // [kFastThreads]
   float* s_carea = reinterpret_cast<float*>(s_cbox + kFastThreads);               // [kFastThreads]
@@ -1150,15 +1182,16 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   const float* img_scores = scores + (size_t)b * A * C;
   const u64* lst = lists + (size_t)b * kCap;
   PHASE_T0();
-  for (int i = tid; i < n; i += kFastThreads) s_list[i] = lst[i];  // (n = 0 after an overflow: refill right away)
+  for (int i = tid; i < n; i += NT) s_list[i] = lst[i];  // (n = 0 after an overflow: refill right away)
   if (tid == 0) s_nsel = 0;
   __syncthreads();
   PHASE_ADD(10);  // list load
 
   int n_sel = 0;
+  int seen = 0;  // candidates consumed so far (ALGO 1: sizes the chunks after the first from the keep rate)
   while (true) {
     // ---- sort the current tier (merged order) ----
-    fast_sort(s_list, s_tmp, n, tid);
+    fast_sort(s_list, s_tmp, n, tid, tid < kFastThreads);
     PHASE_ADD(11);  // sort
     if (span == 0ull) {  // band that held the lower half of this tier -> width expected to hold the refill target
       const u64 c_mid = (n >= 2) ? s_list[n >> 1] : 0ull;
@@ -1170,135 +1203,319 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
                                                                                          : per * (2ull * kAllRefillTarget));
     }
 
-    for (int g0 = 0; g0 < n && n_sel < K; g0 += kFastThreads) {
-      const int gn = min(kFastThreads, n - g0);
-      __syncthreads();  // s_tmp (sort buffer / previous candidate arrays) is free
-      if (tid < gn) {   // gather the boxes of the next 256 sorted candidates
-        const u64 cp = s_list[g0 + tid];
-        const float4 nb = normalise_box(ssdx_load_box(boxes, box_row0, comp_all_idx(cp)));
-        s_cbox[tid] = nb;
-        s_carea[tid] = box_area(nb);
-        s_ccls[tid] = (unsigned char)comp_all_cls(cp);
-        s_chbox[tid] = make_hbox(nb);
-      }
-      __syncthreads();
-      PHASE_ADD(12);  // box gather
-      for (int base = 0; base < gn && n_sel < K; base += kBlk) {
-        const int m = min(kBlk, gn - base);
-        const int ci = tid >> 2, part = tid & 3;
+    if constexpr (ALGO == 1) {
+      for (int g0 = 0; g0 < n && n_sel < K;) {
+        // chunk size: what the keep rate seen so far asks for (+ 1/8 + 8), whole warps, at most one per thread
+        int want = K - n_sel;
+        if (seen > 0) want = (int)(((long long)want * seen + n_sel - 1) / n_sel);  // (n_sel >= 1 once seen > 0)
+        else want += want >> 3;
+        want += (want >> 3) + 8;
+        const int m = min(min(kFastThreads, n - g0), (want + 31) & ~31);
+        const int R = (m + 31) >> 5;  // row groups of 32 candidates
+        const int n_sel0 = n_sel;
+        __syncthreads();  // s_tmp (sort buffer / previous candidate arrays) is free
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ai = 0.f;
+        int cls = 0;
+        HBox hb;
+        hb.mn = __float2half2_rn(INFINITY);  // overlaps nothing
+        hb.mx = __float2half2_rn(-INFINITY);
+        if (tid < m) {  // gather the boxes of the next m sorted candidates
+          const u64 cp = s_list[g0 + tid];
+          bi = normalise_box(ssdx_load_box(boxes, box_row0, comp_all_idx(cp)));
+          ai = box_area(bi);
+          cls = comp_all_cls(cp);
+          hb = make_hbox_cls(bi, cls);
+          s_cbox[tid] = bi;
+          s_carea[tid] = ai;
+          s_ccls[tid] = (unsigned char)cls;
+        }
+        if (tid < kFastThreads) {
+          s_chbox[tid] = hb;
+          s_supb[tid] = (unsigned char)(tid >= m);
+        }
+        __syncthreads();
+        PHASE_ADD(12);  // box gather
+        // ---- (a) against the boxes kept by earlier chunks: candidate = tid % (32 R), kept boxes strided over the
+        //      256 / (32 R) thread groups, newest first ----
+        if (n_sel0 > 0) {
+          const int rows = 32 * R, parts = NT / rows;
+          const int ci = tid % rows, part = tid / rows;
+          if (part < parts && ci < m) {
+            const float4 b = s_cbox[ci];
+            const float a = s_carea[ci];
+            const unsigned c = s_ccls[ci];
+            const HBox h = s_chbox[ci];
+            bool hit = false;
+            if (a > 0.0f) {  // a box without area is never suppressed
+              int sidx = n_sel0 - 1 - part;
+              for (; sidx >= 3 * parts && !hit; sidx -= 4 * parts) {
+                const HBox h0 = s_shbox[sidx], h1 = s_shbox[sidx - parts], h2 = s_shbox[sidx - 2 * parts],
+                           h3 = s_shbox[sidx - 3 * parts];
+                const bool o0 = hboxes_may_overlap(h, h0), o1 = hboxes_may_overlap(h, h1),
+                           o2 = hboxes_may_overlap(h, h2), o3 = hboxes_may_overlap(h, h3);
+                if (o0 | o1 | o2 | o3) {
+                  hit = (o0 && s_scls[sidx] == c && iou_exceeds(b, a, s_sbox[sidx], s_sarea[sidx], iou_thr)) ||
+                        (o1 && s_scls[sidx - parts] == c &&
+                         iou_exceeds(b, a, s_sbox[sidx - parts], s_sarea[sidx - parts], iou_thr)) ||
+                        (o2 && s_scls[sidx - 2 * parts] == c &&
+                         iou_exceeds(b, a, s_sbox[sidx - 2 * parts], s_sarea[sidx - 2 * parts], iou_thr)) ||
+                        (o3 && s_scls[sidx - 3 * parts] == c &&
+                         iou_exceeds(b, a, s_sbox[sidx - 3 * parts], s_sarea[sidx - 3 * parts], iou_thr));
+                }
+              }
+              for (; sidx >= 0 && !hit; sidx -= parts) {
+                if (hboxes_may_overlap(h, s_shbox[sidx]) && s_scls[sidx] == c)
+                  hit = iou_exceeds(b, a, s_sbox[sidx], s_sarea[sidx], iou_thr);
+              }
+            }
+            if (hit) s_supb[ci] = 1;  // (several parts may store the same value)
+          }
+        }
+        // ---- (b) the chunk against itself: tiles t = g (g + 1) / 2 + jb of the lower triangle, dealt to the warps ----
         {
-          bool hit = false;
-          float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
-          float ai = 0.f;
-          unsigned cls = 0u;
-          HBox hi_box = make_hbox(bi);
-          if (ci < m) {
-            bi = s_cbox[base + ci];
-            ai = s_carea[base + ci];
-            cls = s_ccls[base + ci];
-            hi_box = s_chbox[base + ci];
-          }
-          if (ai > 0.0f) {  // a box without area is never suppressed
-            // kept boxes of every class, newest first; the class test and the exact IoU only for overlapping pairs
-            int s = n_sel - 1 - part;
-            for (; s >= 12 && !hit; s -= 16) {
-              const HBox h0 = s_shbox[s], h1 = s_shbox[s - 4], h2 = s_shbox[s - 8], h3 = s_shbox[s - 12];
-              const bool o0 = hboxes_may_overlap(hi_box, h0), o1 = hboxes_may_overlap(hi_box, h1),
-                         o2 = hboxes_may_overlap(hi_box, h2), o3 = hboxes_may_overlap(hi_box, h3);
-              if (o0 | o1 | o2 | o3) {
-                hit = (o0 && s_scls[s] == cls && iou_exceeds(bi, ai, s_sbox[s], s_sarea[s], iou_thr)) ||
-                      (o1 && s_scls[s - 4] == cls && iou_exceeds(bi, ai, s_sbox[s - 4], s_sarea[s - 4], iou_thr)) ||
-                      (o2 && s_scls[s - 8] == cls && iou_exceeds(bi, ai, s_sbox[s - 8], s_sarea[s - 8], iou_thr)) ||
-                      (o3 && s_scls[s - 12] == cls && iou_exceeds(bi, ai, s_sbox[s - 12], s_sarea[s - 12], iou_thr));
-              }
-            }
-            for (; s >= 0 && !hit; s -= 4) {
-              if (hboxes_may_overlap(hi_box, s_shbox[s]) && s_scls[s] == cls)
-                hit = iou_exceeds(bi, ai, s_sbox[s], s_sarea[s], iou_thr);
-            }
-          }
-          const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
-          if (part == 0) s_sup[ci] = (ci >= m) || (((bal >> (lane & 28)) & 0xFu) != 0u);
-          // earlier candidates j < ci of the same class that suppress ci; this thread tests j = 4*jj + part
-          unsigned lo = 0u, hi = 0u;
-          if (ai > 0.0f && part < ci) {
+          const int ntiles = R * (R + 1) / 2;
+          for (int t = warp; t < ntiles; t += NT / 32) {
+            int g = 0;
+            while ((g + 1) * (g + 2) / 2 <= t) ++g;
+            const int jb = t - g * (g + 1) / 2;
+            const int i = 32 * g + lane;
+            const HBox me = s_chbox[i];  // (rows beyond m overlap nothing)
+            const HBox* col = s_chbox + 32 * jb;  // (columns beyond m overlap nothing either)
             unsigned ov = 0u;
-            const int nj = (ci - part + 3) >> 2;  // number of jj with 4*jj + part < ci
-            const int nj4 = (nj + 3) & ~3;        // stale slots beyond m / ci are masked below
-            for (int j0 = 0; j0 < nj4; j0 += 4) {
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                ov |= (unsigned)hboxes_may_overlap(hi_box, s_chbox[base + 4 * (j0 + jj) + part]) << (j0 + jj);
+            for (int jj = 0; jj < 32; ++jj) {  // both packed compares unconditionally, one predicated OR per pair
+              const HBox o = col[jj];
+              if ((__hgt2_mask(me.mx, o.mn) & __hgt2_mask(o.mx, me.mn)) == 0xFFFFFFFFu) ov |= 1u << jj;
             }
-            if (nj < 16) ov &= (1u << nj) - 1u;
-            while (ov) {  // class + exact test for the few overlapping pairs
-              const int jj = __ffs(ov) - 1;
-              ov &= ov - 1u;
-              const int j = 4 * jj + part;
-              if (s_ccls[base + j] == cls && iou_exceeds(bi, ai, s_cbox[base + j], s_carea[base + j], iou_thr)) {
-                if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
+            if (jb == g) ov &= (1u << lane) - 1u;  // earlier candidates only
+            unsigned keep = 0u;
+            if (ov != 0u) {  // class + exact test for the few overlapping pairs
+              const float4 b = s_cbox[i];
+              const float a = s_carea[i];
+              const unsigned c = s_ccls[i];
+              if (a > 0.0f) {
+                while (ov) {
+                  const int jj = __ffs(ov) - 1;
+                  ov &= ov - 1u;
+                  const int j = 32 * jb + jj;
+                  if (s_ccls[j] == c && iou_exceeds(b, a, s_cbox[j], s_carea[j], iou_thr)) keep |= 1u << jj;
+                }
               }
             }
+            s_tile[t * 32 + lane] = keep;
           }
-          lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 1);
-          hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 1);
-          lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 2);
-          hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 2);
-          if (part == 0) s_row[ci] = ((u64)hi << 32) | (u64)lo;
         }
         __syncthreads();
         PHASE_ADD(13);  // pair tests
-        if (warp == kFastThreads / 32 - 1) {  // the arbiter favours the highest warp id: keep the serial part there
+        // ---- (c) one warp decides the chunk, 64 candidates at a time (the arbiter favours the highest warp id) ----
+        if (warp == NT / 32 - 1) {
           const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
-          const u64 ra = s_row[lane], rb = s_row[lane + 32];
-          const unsigned a_lo = (unsigned)ra & lt;
-          const unsigned b_lo = (unsigned)rb, b_hi = (unsigned)(rb >> 32) & lt;
-          unsigned supp_lo = __ballot_sync(0xFFFFFFFFu, s_sup[lane] != 0);
-          unsigned supp_hi = __ballot_sync(0xFFFFFFFFu, s_sup[lane + 32] != 0);
-          unsigned kept_lo = 0u, kept_hi = 0u;
-          // fix-point: the lowest undecided candidate is decided in every round
-          while ((kept_lo | supp_lo) != 0xFFFFFFFFu || (kept_hi | supp_hi) != 0xFFFFFFFFu) {
-            const bool und_a = !((kept_lo | supp_lo) & me), und_b = !((kept_hi | supp_hi) & me);
-            const bool a_hit = (a_lo & kept_lo) != 0u;
-            const bool b_hit = ((b_lo & kept_lo) | (b_hi & kept_hi)) != 0u;
-            const bool a_free = (a_lo & ~supp_lo) == 0u;
-            const bool b_free = ((b_lo & ~supp_lo) | (b_hi & ~supp_hi)) == 0u;
-            const unsigned nk_lo = __ballot_sync(0xFFFFFFFFu, und_a && !a_hit && a_free);
-            const unsigned ns_lo = __ballot_sync(0xFFFFFFFFu, und_a && a_hit);
-            const unsigned nk_hi = __ballot_sync(0xFFFFFFFFu, und_b && !b_hit && b_free);
-            const unsigned ns_hi = __ballot_sync(0xFFFFFFFFu, und_b && b_hit);
-            kept_lo |= nk_lo;
-            supp_lo |= ns_lo;
-            kept_hi |= nk_hi;
-            supp_hi |= ns_hi;
-          }
-          const int room = K - n_sel;
-          const int n_lo = __popc(kept_lo);
-          if (kept_lo & me) {
-            const int r = __popc(kept_lo & lt);
-            if (r < room) {
-              s_sbox[n_sel + r] = s_cbox[base + lane];
-              s_sarea[n_sel + r] = s_carea[base + lane];
-              s_scls[n_sel + r] = s_ccls[base + lane];
-              s_shbox[n_sel + r] = s_chbox[base + lane];
-              s_pick[n_sel + r] = s_list[g0 + base + lane];
+          unsigned keptw[8];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) keptw[w] = 0u;
+          int ns = n_sel0;
+#pragma unroll
+          for (int sb = 0; sb < 4; ++sb) {
+            if (64 * sb < m && ns < K) {  // (uniform)
+              const int ga = 2 * sb, gb = 2 * sb + 1;
+              const int ta = ga * (ga + 1) / 2, tb = gb * (gb + 1) / 2;
+              const int ia = 64 * sb + lane, ib = ia + 32;
+              const bool has_b = gb < R;
+              bool sa = s_supb[ia] != 0, sbb = !has_b || s_supb[ib] != 0;
+#pragma unroll
+              for (int w = 0; w < 2 * sb; ++w) {  // suppressed by a box kept earlier in this chunk
+                sa |= (s_tile[(ta + w) * 32 + lane] & keptw[w]) != 0u;
+                if (has_b) sbb |= (s_tile[(tb + w) * 32 + lane] & keptw[w]) != 0u;
+              }
+              const unsigned a_lo = s_tile[(ta + ga) * 32 + lane];  // (diagonal tile: bits below the lane only)
+              const unsigned b_lo = has_b ? s_tile[(tb + ga) * 32 + lane] : 0u;
+              const unsigned b_hi = has_b ? s_tile[(tb + gb) * 32 + lane] : 0u;
+              unsigned supp_lo = __ballot_sync(0xFFFFFFFFu, sa);
+              unsigned supp_hi = __ballot_sync(0xFFFFFFFFu, sbb);
+              unsigned kept_lo = 0u, kept_hi = 0u;
+              // fix-point: the lowest undecided candidate is decided in every round
+              while ((kept_lo | supp_lo) != 0xFFFFFFFFu || (kept_hi | supp_hi) != 0xFFFFFFFFu) {
+                const bool und_a = !((kept_lo | supp_lo) & me), und_b = !((kept_hi | supp_hi) & me);
+                const bool a_hit = (a_lo & kept_lo) != 0u;
+                const bool b_hit = ((b_lo & kept_lo) | (b_hi & kept_hi)) != 0u;
+                const bool a_free = (a_lo & ~supp_lo) == 0u;
+                const bool b_free = ((b_lo & ~supp_lo) | (b_hi & ~supp_hi)) == 0u;
+                const unsigned nk_lo = __ballot_sync(0xFFFFFFFFu, und_a && !a_hit && a_free);
+                const unsigned ns_lo = __ballot_sync(0xFFFFFFFFu, und_a && a_hit);
+                const unsigned nk_hi = __ballot_sync(0xFFFFFFFFu, und_b && !b_hit && b_free);
+                const unsigned ns_hi = __ballot_sync(0xFFFFFFFFu, und_b && b_hit);
+                kept_lo |= nk_lo;
+                supp_lo |= ns_lo;
+                kept_hi |= nk_hi;
+                supp_hi |= ns_hi;
+              }
+              keptw[ga] = kept_lo;
+              keptw[gb] = kept_hi;
+              const int room = K - ns;
+              const int n_lo = __popc(kept_lo);
+              if (kept_lo & me) {
+                const int r = __popc(kept_lo & lt);
+                if (r < room) {
+                  s_sbox[ns + r] = s_cbox[ia];
+                  s_sarea[ns + r] = s_carea[ia];
+                  s_scls[ns + r] = s_ccls[ia];
+                  s_shbox[ns + r] = s_chbox[ia];
+                  s_pick[ns + r] = s_list[g0 + ia];
+                }
+              }
+              if (kept_hi & me) {
+                const int r = n_lo + __popc(kept_hi & lt);
+                if (r < room) {
+                  s_sbox[ns + r] = s_cbox[ib];
+                  s_sarea[ns + r] = s_carea[ib];
+                  s_scls[ns + r] = s_ccls[ib];
+                  s_shbox[ns + r] = s_chbox[ib];
+                  s_pick[ns + r] = s_list[g0 + ib];
+                }
+              }
+              ns += min(room, n_lo + __popc(kept_hi));
             }
           }
-          if (kept_hi & me) {
-            const int r = n_lo + __popc(kept_hi & lt);
-            if (r < room) {
-              s_sbox[n_sel + r] = s_cbox[base + lane + 32];
-              s_sarea[n_sel + r] = s_carea[base + lane + 32];
-              s_scls[n_sel + r] = s_ccls[base + lane + 32];
-              s_shbox[n_sel + r] = s_chbox[base + lane + 32];
-              s_pick[n_sel + r] = s_list[g0 + base + lane + 32];
-            }
-          }
-          if (lane == 0) s_nsel = n_sel + min(room, n_lo + __popc(kept_hi));
+          if (lane == 0) s_nsel = ns;
         }
         __syncthreads();
         PHASE_ADD(14);  // block resolve
         n_sel = s_nsel;
+        seen += m;
+        g0 += m;
+      }
+    } else {
+      for (int g0 = 0; g0 < n && n_sel < K; g0 += kFastThreads) {
+        const int gn = min(kFastThreads, n - g0);
+        __syncthreads();  // s_tmp (sort buffer / previous candidate arrays) is free
+        if (tid < gn) {   // gather the boxes of the next 256 sorted candidates
+          const u64 cp = s_list[g0 + tid];
+          const float4 nb = normalise_box(ssdx_load_box(boxes, box_row0, comp_all_idx(cp)));
+          s_cbox[tid] = nb;
+          s_carea[tid] = box_area(nb);
+          s_ccls[tid] = (unsigned char)comp_all_cls(cp);
+          s_chbox[tid] = make_hbox(nb);
+        }
+        __syncthreads();
+        PHASE_ADD(12);  // box gather
+        for (int base = 0; base < gn && n_sel < K; base += kBlk) {
+          const int m = min(kBlk, gn - base);
+          const int ci = tid >> 2, part = tid & 3;
+          {
+            bool hit = false;
+            float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+            float ai = 0.f;
+            unsigned cls = 0u;
+            HBox hi_box = make_hbox(bi);
+            if (ci < m) {
+              bi = s_cbox[base + ci];
+              ai = s_carea[base + ci];
+              cls = s_ccls[base + ci];
+              hi_box = s_chbox[base + ci];
+            }
+            if (ai > 0.0f) {  // a box without area is never suppressed
+              // kept boxes of every class, newest first; the class test and the exact IoU only for overlapping pairs
+              int s = n_sel - 1 - part;
+              for (; s >= 12 && !hit; s -= 16) {
+                const HBox h0 = s_shbox[s], h1 = s_shbox[s - 4], h2 = s_shbox[s - 8], h3 = s_shbox[s - 12];
+                const bool o0 = hboxes_may_overlap(hi_box, h0), o1 = hboxes_may_overlap(hi_box, h1),
+                           o2 = hboxes_may_overlap(hi_box, h2), o3 = hboxes_may_overlap(hi_box, h3);
+                if (o0 | o1 | o2 | o3) {
+                  hit = (o0 && s_scls[s] == cls && iou_exceeds(bi, ai, s_sbox[s], s_sarea[s], iou_thr)) ||
+                        (o1 && s_scls[s - 4] == cls && iou_exceeds(bi, ai, s_sbox[s - 4], s_sarea[s - 4], iou_thr)) ||
+                        (o2 && s_scls[s - 8] == cls && iou_exceeds(bi, ai, s_sbox[s - 8], s_sarea[s - 8], iou_thr)) ||
+                        (o3 && s_scls[s - 12] == cls && iou_exceeds(bi, ai, s_sbox[s - 12], s_sarea[s - 12], iou_thr));
+                }
+              }
+              for (; s >= 0 && !hit; s -= 4) {
+                if (hboxes_may_overlap(hi_box, s_shbox[s]) && s_scls[s] == cls)
+                  hit = iou_exceeds(bi, ai, s_sbox[s], s_sarea[s], iou_thr);
+              }
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+            if (part == 0) s_sup[ci] = (ci >= m) || (((bal >> (lane & 28)) & 0xFu) != 0u);
+            // earlier candidates j < ci of the same class that suppress ci; this thread tests j = 4*jj + part
+            unsigned lo = 0u, hi = 0u;
+            if (ai > 0.0f && part < ci) {
+              unsigned ov = 0u;
+              const int nj = (ci - part + 3) >> 2;  // number of jj with 4*jj + part < ci
+              const int nj4 = (nj + 3) & ~3;        // stale slots beyond m / ci are masked below
+              for (int j0 = 0; j0 < nj4; j0 += 4) {
+  #pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                  ov |= (unsigned)hboxes_may_overlap(hi_box, s_chbox[base + 4 * (j0 + jj) + part]) << (j0 + jj);
+              }
+              if (nj < 16) ov &= (1u << nj) - 1u;
+              while (ov) {  // class + exact test for the few overlapping pairs
+                const int jj = __ffs(ov) - 1;
+                ov &= ov - 1u;
+                const int j = 4 * jj + part;
+                if (s_ccls[base + j] == cls && iou_exceeds(bi, ai, s_cbox[base + j], s_carea[base + j], iou_thr)) {
+                  if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
+                }
+              }
+            }
+            lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 1);
+            hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 1);
+            lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 2);
+            hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 2);
+            if (part == 0) s_row[ci] = ((u64)hi << 32) | (u64)lo;
+          }
+          __syncthreads();
+          PHASE_ADD(13);  // pair tests
+          if (warp == kFastThreads / 32 - 1) {  // the arbiter favours the highest warp id: keep the serial part there
+            const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
+            const u64 ra = s_row[lane], rb = s_row[lane + 32];
+            const unsigned a_lo = (unsigned)ra & lt;
+            const unsigned b_lo = (unsigned)rb, b_hi = (unsigned)(rb >> 32) & lt;
+            unsigned supp_lo = __ballot_sync(0xFFFFFFFFu, s_sup[lane] != 0);
+            unsigned supp_hi = __ballot_sync(0xFFFFFFFFu, s_sup[lane + 32] != 0);
+            unsigned kept_lo = 0u, kept_hi = 0u;
+            // fix-point: the lowest undecided candidate is decided in every round
+            while ((kept_lo | supp_lo) != 0xFFFFFFFFu || (kept_hi | supp_hi) != 0xFFFFFFFFu) {
+              const bool und_a = !((kept_lo | supp_lo) & me), und_b = !((kept_hi | supp_hi) & me);
+              const bool a_hit = (a_lo & kept_lo) != 0u;
+              const bool b_hit = ((b_lo & kept_lo) | (b_hi & kept_hi)) != 0u;
+              const bool a_free = (a_lo & ~supp_lo) == 0u;
+              const bool b_free = ((b_lo & ~supp_lo) | (b_hi & ~supp_hi)) == 0u;
+              const unsigned nk_lo = __ballot_sync(0xFFFFFFFFu, und_a && !a_hit && a_free);
+              const unsigned ns_lo = __ballot_sync(0xFFFFFFFFu, und_a && a_hit);
+              const unsigned nk_hi = __ballot_sync(0xFFFFFFFFu, und_b && !b_hit && b_free);
+              const unsigned ns_hi = __ballot_sync(0xFFFFFFFFu, und_b && b_hit);
+              kept_lo |= nk_lo;
+              supp_lo |= ns_lo;
+              kept_hi |= nk_hi;
+              supp_hi |= ns_hi;
+            }
+            const int room = K - n_sel;
+            const int n_lo = __popc(kept_lo);
+            if (kept_lo & me) {
+              const int r = __popc(kept_lo & lt);
+              if (r < room) {
+                s_sbox[n_sel + r] = s_cbox[base + lane];
+                s_sarea[n_sel + r] = s_carea[base + lane];
+                s_scls[n_sel + r] = s_ccls[base + lane];
+                s_shbox[n_sel + r] = s_chbox[base + lane];
+                s_pick[n_sel + r] = s_list[g0 + base + lane];
+              }
+            }
+            if (kept_hi & me) {
+              const int r = n_lo + __popc(kept_hi & lt);
+              if (r < room) {
+                s_sbox[n_sel + r] = s_cbox[base + lane + 32];
+                s_sarea[n_sel + r] = s_carea[base + lane + 32];
+                s_scls[n_sel + r] = s_ccls[base + lane + 32];
+                s_shbox[n_sel + r] = s_chbox[base + lane + 32];
+                s_pick[n_sel + r] = s_list[g0 + base + lane + 32];
+              }
+            }
+            if (lane == 0) s_nsel = n_sel + min(room, n_lo + __popc(kept_hi));
+          }
+          __syncthreads();
+          PHASE_ADD(14);  // block resolve
+          n_sel = s_nsel;
+        }
       }
     }
     if (n_sel >= K || comp_hi <= (1ull << 32)) break;  // done, or every candidate has been visited
@@ -1326,16 +1543,16 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
       };
       if (logits) {  // (C == 4) rows of logits: probabilities recomputed as in the select kernel
         const float4 cf4 = class_factor4(cscale);
-        for (int a0 = tid; a0 < A; a0 += kFastThreads * 4) {
+        for (int a0 = tid; a0 < A; a0 += NT * 4) {
           float4 r[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int a = a0 + u * kFastThreads;
+            const int a = a0 + u * NT;
             r[u] = (a < A) ? __ldg(reinterpret_cast<const float4*>(img_scores) + a) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int a = a0 + u * kFastThreads;
+            const int a = a0 + u * NT;
             if (a < A) {
               const float4 p = mul4(ssdx_softmax4(r[u]), cf4);
               consider(p.x, a, 0);
@@ -1347,18 +1564,18 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
         }
       } else {
         const int total = A * C;
-        for (int e0 = tid; e0 < total; e0 += kFastThreads * 8) {  // 8 independent loads in flight per thread
+        for (int e0 = tid; e0 < total; e0 += NT * 8) {  // 8 independent loads in flight per thread
           float sv[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * kFastThreads;
+            const int e = e0 + u * NT;
             sv[u] = (e < total)
                         ? (cscale ? __fmul_rn(__ldg(img_scores + e), __ldg(cscale + e % C)) : __ldg(img_scores + e))
                         : -INFINITY;
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * kFastThreads;
+            const int e = e0 + u * NT;
             const int a = e / C;
             consider(sv[u], a, e - a * C);
           }
@@ -1383,7 +1600,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
   __syncthreads();
   // ---- rows, already in merge order: [label, prob, xmin, ymin, xmax, ymax] (layers.py:155-162), zero padding ----
   float* o = out + (size_t)b * K * 6;
-  for (int r = tid; r < n_sel; r += kFastThreads) {
+  for (int r = tid; r < n_sel; r += NT) {
     const u64 cp = s_pick[r];
     const int idx = comp_all_idx(cp);
     const float4 bx = ssdx_load_box(boxes, box_row0, idx);  // raw (ymin, xmin, ymax, xmax)
@@ -1396,9 +1613,9 @@ __global__ void __launch_bounds__(kFastThreads, MINB)
     row[5] = bx.z;
     if (out_idx) out_idx[(size_t)b * K + r] = idx;
   }
-  for (int e = n_sel * 6 + tid; e < K * 6; e += kFastThreads) o[e] = 0.0f;
+  for (int e = n_sel * 6 + tid; e < K * 6; e += NT) o[e] = 0.0f;
   if (out_idx)
-    for (int e = n_sel + tid; e < K; e += kFastThreads) out_idx[(size_t)b * K + e] = -1;
+    for (int e = n_sel + tid; e < K; e += NT) out_idx[(size_t)b * K + e] = -1;
   if (out_valid && tid == 0) out_valid[b] = n_sel;
   PHASE_ADD(16);  // rows
 #ifdef SSDX_PHASE_TIMERS
@@ -1776,28 +1993,49 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
       // first list sized to max_total (rank (3 K + 63) / 16 of the thread maxima, at most kAllRank = the K = 200 tuning)
       int all_rank = (3 * max_total + 63) / 16;
       all_rank = all_rank < 4 ? 4 : (all_rank > kAllRank ? kAllRank : all_rank);
-      if (logits)
-        ssdx_nms_select_all_kernel<true, true><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
-                                                                             all_rank, lists, info);
-      else if (vec4)
-        ssdx_nms_select_all_kernel<true, false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
-                                                                              all_rank, lists, info);
-      else
-        ssdx_nms_select_all_kernel<false, false><<<batch, kSelThreads, 0, s>>>(scores, cscale, A, C, score_threshold,
-                                                                               all_rank, lists, info);
+#define SSDX_SELECT_ALL(NT)                                                                                          \
+  do {                                                                                                               \
+    if (logits)                                                                                                      \
+      ssdx_nms_select_all_kernel<true, true, NT><<<batch, NT, 0, s>>>(scores, cscale, A, C, score_threshold, all_rank, \
+                                                                      lists, info);                                  \
+    else if (vec4)                                                                                                   \
+      ssdx_nms_select_all_kernel<true, false, NT><<<batch, NT, 0, s>>>(scores, cscale, A, C, score_threshold,         \
+                                                                       all_rank, lists, info);                       \
+    else                                                                                                             \
+      ssdx_nms_select_all_kernel<false, false, NT><<<batch, NT, 0, s>>>(scores, cscale, A, C, score_threshold,        \
+                                                                        all_rank, lists, info);                      \
+  } while (0)
+      const int sel_sms = ssdx_sm_count(device);  // few images: wider CTAs keep more loads in flight per image
+      if (batch <= sel_sms) SSDX_SELECT_ALL(1024);
+      else if (batch <= 3 * sel_sms) SSDX_SELECT_ALL(512);
+      else SSDX_SELECT_ALL(kSelThreads);
+#undef SSDX_SELECT_ALL
       SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
     }
     if (!ph2) return SSDX_OK;
-#define SSDX_FAST_ALL(MAXSEL, MINB, LOG)                                                                            \
-  ssdx_nms_fast_all_kernel<MAXSEL, MINB, LOG><<<batch, kFastThreads, 0, s>>>(                                       \
+#define SSDX_FAST_ALL(MAXSEL, MINB, LOG, ALGO, NT)                                                                  \
+  ssdx_nms_fast_all_kernel<MAXSEL, MINB, LOG, ALGO, NT><<<batch, NT, 0, s>>>(                                       \
       bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx)
+#define SSDX_FAST_ALL_LOG(MAXSEL, MINB, ALGO, NT)           \
+  do {                                                      \
+    if (logits) SSDX_FAST_ALL(MAXSEL, MINB, true, ALGO, NT); \
+    else SSDX_FAST_ALL(MAXSEL, MINB, false, ALGO, NT);       \
+  } while (0)
+    const bool blocked = force != nullptr && force[0] == 'b';  // test hook: the 64-candidate blocked form
+    // few images: one wide CTA per image (the 32 x 32 tiles of a chunk, the kept-box tests, refill scans and rows
+    // spread over 32 or 16 warps; sort and gather stay on the first 8); many images: 7 narrow CTAs per SM
+    const int sms = ssdx_sm_count(device);
     if (max_total <= 256) {
-      if (logits) SSDX_FAST_ALL(256, SSDX_FAST_MINB, true);
-      else SSDX_FAST_ALL(256, SSDX_FAST_MINB, false);
+      if (blocked) SSDX_FAST_ALL_LOG(256, SSDX_FAST_MINB, 0, kFastThreads);
+      else if (batch <= sms) SSDX_FAST_ALL_LOG(256, 1, 1, 1024);
+      else if (batch <= 3 * sms) SSDX_FAST_ALL_LOG(256, 3, 1, 512);
+      else SSDX_FAST_ALL_LOG(256, SSDX_FAST_MINB, 1, kFastThreads);
     } else {
-      if (logits) SSDX_FAST_ALL(kFastMaxSel, 6, true);
-      else SSDX_FAST_ALL(kFastMaxSel, 6, false);
+      if (blocked) SSDX_FAST_ALL_LOG(kFastMaxSel, 6, 0, kFastThreads);
+      else if (batch <= sms) SSDX_FAST_ALL_LOG(kFastMaxSel, 1, 1, 1024);
+      else SSDX_FAST_ALL_LOG(kFastMaxSel, 5, 1, kFastThreads);
     }
+#undef SSDX_FAST_ALL_LOG
 #undef SSDX_FAST_ALL
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_all_kernel");
     return SSDX_OK;  // (no fallback: the band refills of fast_all split even massive score ties)

@@ -34,11 +34,12 @@ def encode_path(request, lib):
     lib._ssdx.set_option("encode_path", "auto")
 
 
-@pytest.fixture(autouse=True, params=["fast", "perclass", "pcta", "generic"])
+@pytest.fixture(autouse=True, params=["fast", "blocked", "perclass", "pcta", "generic"])
 def nms_path(request, lib):
     """NMS tests run on the default dispatch (merged one-pass-per-image pipeline when max_per_class >= max_total,
     else the per-class pipeline: one warp per segment for caps up to 32, one CTA per segment above; generic only for
-    handed-over work), with the per-class pipeline forced ("perclass"), with the per-class CTA kernel forced for every
+    handed-over work), with the merged pipeline's 64-candidate blocked greedy pass instead of the chunked bit matrix
+    ("blocked"), with the per-class pipeline forced ("perclass"), with the per-class CTA kernel forced for every
     cap ("pcta"), and with the exact generic kernel alone."""
     if request.param != "fast":
         if "nms" not in request.node.name:
@@ -449,8 +450,8 @@ def test_nms_randomized_differential(lib, nms_path):
         "fuzz_nms", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_nms.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    seed = {"fast": 11, "perclass": 12, "pcta": 13, "generic": 14}[nms_path]
-    assert mod.run(250 if nms_path == "fast" else 120, seed, verbose=False) == 0
+    seed = {"fast": 11, "perclass": 12, "pcta": 13, "generic": 14, "blocked": 15}[nms_path]
+    assert mod.run(250 if nms_path in ("fast", "blocked") else 120, seed, verbose=False) == 0
 
 
 @pytest.mark.parametrize("C,mpc,mtot", [(4, 200, 200), (4, 4, 10), (6, 50, 50)])

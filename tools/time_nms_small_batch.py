@@ -15,7 +15,7 @@ out = torch.empty((B, K, 6), device="cuda"); val = torch.empty(B, dtype=torch.in
 ws = torch.empty(int(sx.lib.ssdx_nms_workspace_bytes(B, A, C, K, K)), dtype=torch.uint8, device="cuda")
 sp = torch.cuda.current_stream().cuda_stream
 fn = lambda: sx.check(sx.lib.ssdx_nms(yx.data_ptr(), scd.data_ptr(), B, A, C, K, K, 0.45, 0.01, out.data_ptr(), val.data_ptr(), None, ws.data_ptr(), ws.numel(), 0, sp))
-for path in ("auto", "perclass", "pcta"):
+for path in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("auto", "blocked", "perclass", "pcta")):
     sx.set_option("nms_path", path)
     for _ in range(5): fn()
     torch.cuda.synchronize(); ts = []
