@@ -135,16 +135,24 @@ __device__ __forceinline__ HBox make_hbox(const float4 n) {
 __device__ __forceinline__ bool hboxes_may_overlap(const HBox a, const HBox b) {
   return __hbgt2(a.mx, b.mn) && __hbgt2(b.mx, a.mn);
 }
-// Prefilter copy with the class folded in: boxes of class c are shifted by (2 * (c & 15), 2 * (c >> 4)) before the
-// directed roundings (fp32 add and fp16 conversion both round minima down and maxima up), so that boxes of the same
-// class keep "exact overlap implies prefilter overlap" while boxes of different classes inside the usual [-0.5, 1.5]
-// range never pass it.  Pairs that pass are still decided by the class test and the exact fp32 IoU.
-__device__ __forceinline__ HBox make_hbox_cls(const float4 n, const int cls) {
-  const float oy = (float)(2 * (cls & 15)), ox = (float)(2 * (cls >> 4));
+// Prefilter copy with the class folded in: boxes of class c are shifted by unit * (c & 15, c >> 4) before the directed
+// roundings (fp32 add and fp16 conversion both round minima down and maxima up; unit is a power of two, so the
+// shifts are exact), so that boxes of the same class keep "exact overlap implies prefilter overlap" while boxes of
+// different classes whose coordinates stay inside (-unit / 2, unit / 2) never pass it.  Pairs that pass are still
+// decided by the class test and the exact fp32 IoU, so a unit that is too small (or a shift that saturates the
+// fp16 range) only costs exact tests.
+__device__ __forceinline__ HBox make_hbox_cls(const float4 n, const int cls, const float unit) {
+  const float oy = __fmul_rn(unit, (float)(cls & 15)), ox = __fmul_rn(unit, (float)(cls >> 4));
   HBox h;
   h.mn = __halves2half2(__float2half_rd(__fadd_rd(n.x, oy)), __float2half_rd(__fadd_rd(n.y, ox)));
   h.mx = __halves2half2(__float2half_ru(__fadd_ru(n.z, oy)), __float2half_ru(__fadd_ru(n.w, ox)));
   return h;
+}
+// power of two above twice the largest coordinate magnitude `ext` (>= 0, finite or not), within [2^-8, 2^14]
+__device__ __forceinline__ float class_unit(const float ext) {
+  int e = (int)((__float_as_uint(ext) >> 23) & 0xFFu) - 127 + 2;  // ext < 2^(e - 1)
+  e = e < -8 ? -8 : (e > 14 ? 14 : e);
+  return __uint_as_float((unsigned)(e + 127) << 23);
 }
 // exact TF IoU test for a pair that overlaps
 __device__ __forceinline__ bool iou_exceeds_overlapping(const float4 a, const float aa, const float4 b, const float ab,
@@ -155,6 +163,16 @@ __device__ __forceinline__ bool iou_exceeds_overlapping(const float4 a, const fl
   const float inter = __fmul_rn(fmaxf(ih, 0.0f), fmaxf(iw, 0.0f));
   const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
   return iou > thr;
+}
+// the same decision without branches (two of these in flight per thread in the tile loop): a pair that does not
+// overlap has inter = 0 (or NaN from 0 * inf), whose quotient never exceeds thr >= 0
+__device__ __forceinline__ bool iou_exceeds_flat(const float4 a, const float aa, const float4 b, const float ab,
+                                                 const float thr) {
+  const float ih = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  const float iw = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  const float inter = __fmul_rn(fmaxf(ih, 0.0f), fmaxf(iw, 0.0f));
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+  return (aa > 0.0f) & (ab > 0.0f) & (iou > thr);
 }
 __device__ __forceinline__ bool iou_exceeds(const float4 a, const float aa, const float4 b, const float ab,
                                             const float thr) {
@@ -210,23 +228,23 @@ __device__ __forceinline__ int bitonic_sort_desc(u64* v, const int n, const int 
 // Bitonic sort (descending) of 256*EPT u64 held EPT per thread by a 256-thread CTA: element e = r*256 + tid.
 // Partner distance j < 32 -> warp shuffle, j >= 256 -> register exchange inside the thread, 32 <= j <= 128 ->
 // shared-memory exchange (double-buffered: one barrier per such stage).  9 barriers instead of 45 for 512 keys.
-template <int EPT>
+template <int EPT, int TPB = 256>  // TPB threads hold EPT keys each: key e = r * TPB + tid
 __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64* buf1,
                                                   const int tid, const bool active = true) {
-  constexpr int N = 256 * EPT;
+  constexpr int N = TPB * EPT;
   int flip = 0;
 #pragma unroll
   for (int k = 2; k <= N; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 256) {
+      if (j >= TPB) {
         constexpr int dummy = 0;
         (void)dummy;
 #pragma unroll
         for (int r = 0; r < EPT; ++r) {
-          const int rp = r ^ (j >> 8);
+          const int rp = r ^ (j / TPB);
           if (rp > r) {  // the pair (r, rp) lives in this thread; r is the lower index
-            const int e = r * 256 + tid;
+            const int e = r * TPB + tid;
             const bool desc = ((e & k) == 0);
             const u64 a = v[r], b = v[rp];
             const bool swap = desc ? (a < b) : (a > b);
@@ -238,7 +256,7 @@ __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64*
         if (active) {  // (whole warps are active or not)
 #pragma unroll
           for (int r = 0; r < EPT; ++r) {
-            const int e = r * 256 + tid;
+            const int e = r * TPB + tid;
             const u64 p = __shfl_xor_sync(0xFFFFFFFFu, v[r], j);
             const bool take_max = (((e & j) == 0) == ((e & k) == 0));
             v[r] = ((v[r] > p) == take_max) ? v[r] : p;  // keys are distinct or equal: one compare, one select
@@ -249,13 +267,13 @@ __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64*
         flip ^= 1;
         if (active) {
 #pragma unroll
-          for (int r = 0; r < EPT; ++r) buf[r * 256 + tid] = v[r];
+          for (int r = 0; r < EPT; ++r) buf[r * TPB + tid] = v[r];
         }
         __syncthreads();
         if (active) {
 #pragma unroll
           for (int r = 0; r < EPT; ++r) {
-            const int e = r * 256 + tid;
+            const int e = r * TPB + tid;
             const u64 p = buf[e ^ j];
             const bool take_max = (((e & j) == 0) == ((e & k) == 0));
             v[r] = ((v[r] > p) == take_max) ? v[r] : p;
@@ -266,11 +284,13 @@ __device__ __forceinline__ void bitonic_sort_regs(u64 (&v)[EPT], u64* buf0, u64*
   }
 }
 
-// sort s_list[0..n) descending for the fast kernels (threads 0..255 hold the keys; the threads of a wider CTA pass
-// active = false and only take part in the barriers); uniform control flow
-__device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n,
-                                          const int tid, const bool active = true) {
+// sort s_list[0..n) descending for the fast kernels; uniform control flow.  TPB = 256: threads 0..255 hold the keys.
+// TPB = 512 (CTAs of at least 512 threads): lists above 256 keys are spread over 512 threads.  Threads that hold no
+// keys only take part in the barriers.
+template <int TPB = 256>
+__device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n, const int tid) {
   if (n <= 256) {
+    const bool active = tid < 256;
     u64 v[1];
     v[0] = (active && tid < n) ? s_list[tid] : 0ull;
     __syncthreads();
@@ -278,26 +298,30 @@ __device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n,
     __syncthreads();
     if (active) s_list[tid] = v[0];
   } else if (n <= 512) {
-    u64 v[2];
+    constexpr int EPT = 512 / TPB;
+    const bool active = tid < TPB;
+    u64 v[EPT];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) v[r] = (active && r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
+    for (int r = 0; r < EPT; ++r) v[r] = (active && r * TPB + tid < n) ? s_list[r * TPB + tid] : 0ull;
     __syncthreads();
-    bitonic_sort_regs<2>(v, s_list, s_tmp, tid, active);
+    bitonic_sort_regs<EPT, TPB>(v, s_list, s_tmp, tid, active);
     __syncthreads();
     if (active) {
 #pragma unroll
-      for (int r = 0; r < 2; ++r) s_list[r * 256 + tid] = v[r];
+      for (int r = 0; r < EPT; ++r) s_list[r * TPB + tid] = v[r];
     }
   } else {
-    u64 v[4];
+    constexpr int EPT = 1024 / TPB;
+    const bool active = tid < TPB;
+    u64 v[EPT];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) v[r] = (active && r * 256 + tid < n) ? s_list[r * 256 + tid] : 0ull;
+    for (int r = 0; r < EPT; ++r) v[r] = (active && r * TPB + tid < n) ? s_list[r * TPB + tid] : 0ull;
     __syncthreads();
-    bitonic_sort_regs<4>(v, s_list, s_tmp, tid, active);
+    bitonic_sort_regs<EPT, TPB>(v, s_list, s_tmp, tid, active);
     __syncthreads();
     if (active) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) s_list[r * 256 + tid] = v[r];
+      for (int r = 0; r < EPT; ++r) s_list[r * TPB + tid] = v[r];
     }
   }
   __syncthreads();
@@ -1132,6 +1156,68 @@ __global__ void __launch_bounds__(NT)
 }
 
 // ------------------------------------------------------------------------------------------ 2m. merged fast path
+// One refill scan of fast_all: every score of the image whose composite lies in [comp_lo, comp_hi) is appended to
+// s_list (*s_n counts them, also beyond kCap).  Out of line: it runs for the few images whose first list runs dry, and
+// kept inline it would sit (twice unrolled) between the greedy pass and the output rows of every image.
+template <bool LOGITS, int NT>
+__device__ __noinline__ void fast_all_refill_scan(const float* __restrict__ img_scores, const float* __restrict__ cscale,
+                                                  const int A, const int C, const float score_thr, const u64 comp_lo,
+                                                  const u64 comp_hi, u64* s_list, int* s_n, const int tid) {
+  const unsigned key_lo = (unsigned)(comp_lo >> 32), key_hi32 = (unsigned)((comp_hi - 1ull) >> 32);
+  auto consider = [&](const float sc, const int a, const int c) {
+    if (sc > score_thr) {  // false for the -inf padding
+      const unsigned key = score_to_key(sc);
+      if (key >= key_lo && key <= key_hi32) {  // cheap 32-bit pre-test, then the exact composite band
+        const u64 cp = make_comp_all(key, c, a);
+        if (cp >= comp_lo && cp < comp_hi) {
+          const int pos = atomicAdd(s_n, 1);
+          if (pos < kCap) s_list[pos] = cp;
+        }
+      }
+    }
+  };
+  if (LOGITS) {  // (C == 4) rows of logits: probabilities recomputed as in the select kernel
+    const float4 cf4 = class_factor4(cscale);
+    for (int a0 = tid; a0 < A; a0 += NT * 4) {
+      float4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int a = a0 + u * NT;
+        r[u] = (a < A) ? __ldg(reinterpret_cast<const float4*>(img_scores) + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int a = a0 + u * NT;
+        if (a < A) {
+          const float4 p = mul4(ssdx_softmax4(r[u]), cf4);
+          consider(p.x, a, 0);
+          consider(p.y, a, 1);
+          consider(p.z, a, 2);
+          consider(p.w, a, 3);
+        }
+      }
+    }
+  } else {
+    const int total = A * C;
+    for (int e0 = tid; e0 < total; e0 += NT * 8) {  // 8 independent loads in flight per thread
+      float sv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * NT;
+        sv[u] = (e < total)
+                    ? (cscale ? __fmul_rn(__ldg(img_scores + e), __ldg(cscale + e % C)) : __ldg(img_scores + e))
+                    : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * NT;
+        const int a = e / C;
+        consider(sv[u], a, e - a * C);
+      }
+    }
+  }
+}
+
 // MAXSEL >= K; MINB resident CTAs per SM (7 * 148 >= 1024: one wave at batch 1024); LOGITS: `scores` holds raw logits
 // of 4 classes.  ALGO 1 (default): the sorted candidates are taken in chunks of up to 256; a chunk is tested against
 // the boxes kept by earlier chunks and against itself as 32 x 32 tiles of a lower-triangular bit matrix (all warps,
@@ -1143,10 +1229,9 @@ __global__ void __launch_bounds__(NT, MINB)
                              const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
                              const int K, const float iou_thr, const float score_thr, float* __restrict__ out,
                              int* __restrict__ out_valid, int* __restrict__ out_idx) {
-  constexpr bool logits = LOGITS;
   static_assert(ALGO == 1 || NT == kFastThreads, "the blocked form runs 256 threads");
-  __shared__ u64 s_list[kCap];
-  __shared__ u64 s_tmp[kCap];  // second exchange buffer of the sort; the candidate arrays below alias it
+  __shared__ __align__(16) u64 s_list[kCap];
+  __shared__ __align__(16) u64 s_tmp[kCap];  // second exchange buffer of the sort; the candidate arrays (float4 first) alias it
   __shared__ float4 s_sbox[MAXSEL];
   __shared__ float s_sarea[MAXSEL];
   __shared__ u64 s_pick[MAXSEL];
@@ -1158,11 +1243,18 @@ __global__ void __launch_bounds__(NT, MINB)
   // chunk suppresses candidate 32 g + lane (same class, IoU > threshold, earlier in the order)
   __shared__ unsigned s_tile[ALGO == 1 ? kChunkTiles * 32 : 1];
   __shared__ unsigned char s_supb[ALGO == 1 ? kFastThreads : 1];  // suppressed by a box kept in an earlier chunk / beyond m
+  __shared__ unsigned s_keptw[8];  // ALGO 1: kept candidates of the chunk, one word per row group ...
+  __shared__ int s_kbase[8];       // ... and the slot of the first kept box of each group
   __shared__ int s_nsel, s_n;
   float4* s_cbox = reinterpret_cast<float4*>(s_tmp);                              // [kFastThreads]
   float* s_carea = reinterpret_cast<float*>(s_cbox + kFastThreads);               // [kFastThreads]
   unsigned char* s_ccls = reinterpret_cast<unsigned char*>(s_carea + kFastThreads);  // [kFastThreads]
   HBox* s_chbox = reinterpret_cast<HBox*>(s_ccls + kFastThreads);                    // [kFastThreads]
+  // ALGO 1: how the raw box differs from the normalised one (bit 0: y corners swapped, bit 1: x corners swapped,
+  // bit 2: NaN or equal corners - reload the raw box for the output row)
+  unsigned char* s_cflag = reinterpret_cast<unsigned char*>(s_chbox + kFastThreads);  // [kFastThreads]
+  __shared__ unsigned char s_sflag[ALGO == 1 ? MAXSEL : 1];
+  static_assert((sizeof(float4) + sizeof(float) + 1 + sizeof(HBox) + 1) * kFastThreads <= sizeof(u64) * kCap, "s_tmp");
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1188,10 +1280,11 @@ __global__ void __launch_bounds__(NT, MINB)
   PHASE_ADD(10);  // list load
 
   int n_sel = 0;
-  int seen = 0;  // candidates consumed so far (ALGO 1: sizes the chunks after the first from the keep rate)
+  int seen = 0;       // candidates consumed so far (ALGO 1: sizes the chunks after the first from the keep rate)
+  float unit = 0.0f;  // ALGO 1: class shift of the prefilter boxes, from the coordinate range of the first chunk
   while (true) {
     // ---- sort the current tier (merged order) ----
-    fast_sort(s_list, s_tmp, n, tid, tid < kFastThreads);
+    fast_sort<(NT >= 512 ? 512 : 256)>(s_list, s_tmp, n, tid);
     PHASE_ADD(11);  // sort
     if (span == 0ull) {  // band that held the lower half of this tier -> width expected to hold the refill target
       const u64 c_mid = (n >= 2) ? s_list[n >> 1] : 0ull;
@@ -1222,14 +1315,28 @@ __global__ void __launch_bounds__(NT, MINB)
         hb.mx = __float2half2_rn(-INFINITY);
         if (tid < m) {  // gather the boxes of the next m sorted candidates
           const u64 cp = s_list[g0 + tid];
-          bi = normalise_box(ssdx_load_box(boxes, box_row0, comp_all_idx(cp)));
+          const float4 raw = ssdx_load_box(boxes, box_row0, comp_all_idx(cp));
+          const bool fy = raw.x > raw.z, fx = raw.y > raw.w;
+          const bool odd = !((raw.x < raw.z) | fy) | !((raw.y < raw.w) | fx);
+          s_cflag[tid] = (unsigned char)((fy ? 1 : 0) | (fx ? 2 : 0) | (odd ? 4 : 0));
+          bi = normalise_box(raw);
           ai = box_area(bi);
           cls = comp_all_cls(cp);
-          hb = make_hbox_cls(bi, cls);
           s_cbox[tid] = bi;
           s_carea[tid] = ai;
           s_ccls[tid] = (unsigned char)cls;
         }
+        if (unit == 0.0f) {  // (uniform) first chunk of the image: coordinate range -> class shift
+          const float ext = fmaxf(fmaxf(fabsf(bi.x), fabsf(bi.y)), fmaxf(fabsf(bi.z), fabsf(bi.w)));  // (NaN dropped)
+          const unsigned wmax = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(ext));
+          if (lane == 0 && tid < kFastThreads) s_tile[warp] = wmax;
+          __syncthreads();
+          unsigned mx = 0u;
+#pragma unroll
+          for (int w = 0; w < kFastThreads / 32; ++w) mx = max(mx, s_tile[w]);
+          unit = class_unit(__uint_as_float(mx));
+        }
+        if (tid < m) hb = make_hbox_cls(bi, cls, unit);
         if (tid < kFastThreads) {
           s_chbox[tid] = hb;
           s_supb[tid] = (unsigned char)(tid >= m);
@@ -1272,6 +1379,7 @@ __global__ void __launch_bounds__(NT, MINB)
             if (hit) s_supb[ci] = 1;  // (several parts may store the same value)
           }
         }
+        PHASE_ADD(21);  // kept-box tests
         // ---- (b) the chunk against itself: tiles t = g (g + 1) / 2 + jb of the lower triangle, dealt to the warps ----
         {
           const int ntiles = R * (R + 1) / 2;
@@ -1295,19 +1403,24 @@ __global__ void __launch_bounds__(NT, MINB)
               const float a = s_carea[i];
               const unsigned c = s_ccls[i];
               if (a > 0.0f) {
-                while (ov) {
-                  const int jj = __ffs(ov) - 1;
+                while (ov) {  // two pairs per round (the second repeats the first when only one is left)
+                  const int j0 = __ffs(ov) - 1;
                   ov &= ov - 1u;
-                  const int j = 32 * jb + jj;
-                  if (s_ccls[j] == c && iou_exceeds(b, a, s_cbox[j], s_carea[j], iou_thr)) keep |= 1u << jj;
+                  const int j1 = ov ? __ffs(ov) - 1 : j0;
+                  ov &= ov - 1u;
+                  const int c0 = 32 * jb + j0, c1 = 32 * jb + j1;
+                  const bool h0 = (s_ccls[c0] == c) & iou_exceeds_flat(b, a, s_cbox[c0], s_carea[c0], iou_thr);
+                  const bool h1 = (s_ccls[c1] == c) & iou_exceeds_flat(b, a, s_cbox[c1], s_carea[c1], iou_thr);
+                  keep |= ((unsigned)h0 << j0) | ((unsigned)h1 << j1);
                 }
               }
             }
             s_tile[t * 32 + lane] = keep;
           }
         }
+        PHASE_ADD(22);  // tiles (thread 0's share)
         __syncthreads();
-        PHASE_ADD(13);  // pair tests
+        PHASE_ADD(13);  // pair tests: barrier
         // ---- (c) one warp decides the chunk, 64 candidates at a time (the arbiter favours the highest warp id) ----
         if (warp == NT / 32 - 1) {
           const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
@@ -1352,36 +1465,38 @@ __global__ void __launch_bounds__(NT, MINB)
               }
               keptw[ga] = kept_lo;
               keptw[gb] = kept_hi;
-              const int room = K - ns;
-              const int n_lo = __popc(kept_lo);
-              if (kept_lo & me) {
-                const int r = __popc(kept_lo & lt);
-                if (r < room) {
-                  s_sbox[ns + r] = s_cbox[ia];
-                  s_sarea[ns + r] = s_carea[ia];
-                  s_scls[ns + r] = s_ccls[ia];
-                  s_shbox[ns + r] = s_chbox[ia];
-                  s_pick[ns + r] = s_list[g0 + ia];
-                }
+              if (lane == 0) {  // kept masks and the slots their first boxes take: the copies are made by all warps below
+                s_keptw[ga] = kept_lo;
+                s_keptw[gb] = kept_hi;
+                s_kbase[ga] = ns;
+                s_kbase[gb] = ns + __popc(kept_lo);
               }
-              if (kept_hi & me) {
-                const int r = n_lo + __popc(kept_hi & lt);
-                if (r < room) {
-                  s_sbox[ns + r] = s_cbox[ib];
-                  s_sarea[ns + r] = s_carea[ib];
-                  s_scls[ns + r] = s_ccls[ib];
-                  s_shbox[ns + r] = s_chbox[ib];
-                  s_pick[ns + r] = s_list[g0 + ib];
-                }
-              }
-              ns += min(room, n_lo + __popc(kept_hi));
+              ns += min(K - ns, __popc(kept_lo) + __popc(kept_hi));
+            } else if (lane == 0) {
+              s_keptw[2 * sb] = 0u;
+              s_keptw[2 * sb + 1] = 0u;
             }
           }
           if (lane == 0) s_nsel = ns;
         }
         __syncthreads();
         PHASE_ADD(14);  // block resolve
+        if (tid < m) {  // every kept candidate moves itself to its slot (slots beyond K: dropped)
+          const unsigned kw = s_keptw[tid >> 5];
+          if ((kw >> lane) & 1u) {
+            const int r = s_kbase[tid >> 5] + __popc(kw & ((1u << lane) - 1u));
+            if (r < K) {
+              s_sbox[r] = s_cbox[tid];
+              s_sarea[r] = s_carea[tid];
+              s_scls[r] = s_ccls[tid];
+              s_shbox[r] = s_chbox[tid];
+              s_sflag[r] = s_cflag[tid];
+              s_pick[r] = s_list[g0 + tid];
+            }
+          }
+        }
         n_sel = s_nsel;
+        PHASE_ADD(24);  // kept boxes copied
         seen += m;
         g0 += m;
       }
@@ -1528,59 +1643,7 @@ __global__ void __launch_bounds__(NT, MINB)
       __syncthreads();
       if (tid == 0) s_n = 0;
       __syncthreads();
-      const unsigned key_lo = (unsigned)(comp_lo >> 32), key_hi32 = (unsigned)((comp_hi - 1ull) >> 32);
-      auto consider = [&](const float sc, const int a, const int c) {
-        if (sc > score_thr) {  // false for the -inf padding
-          const unsigned key = score_to_key(sc);
-          if (key >= key_lo && key <= key_hi32) {  // cheap 32-bit pre-test, then the exact composite band
-            const u64 cp = make_comp_all(key, c, a);
-            if (cp >= comp_lo && cp < comp_hi) {
-              const int pos = atomicAdd(&s_n, 1);
-              if (pos < kCap) s_list[pos] = cp;
-            }
-          }
-        }
-      };
-      if (logits) {  // (C == 4) rows of logits: probabilities recomputed as in the select kernel
-        const float4 cf4 = class_factor4(cscale);
-        for (int a0 = tid; a0 < A; a0 += NT * 4) {
-          float4 r[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int a = a0 + u * NT;
-            r[u] = (a < A) ? __ldg(reinterpret_cast<const float4*>(img_scores) + a) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int a = a0 + u * NT;
-            if (a < A) {
-              const float4 p = mul4(ssdx_softmax4(r[u]), cf4);
-              consider(p.x, a, 0);
-              consider(p.y, a, 1);
-              consider(p.z, a, 2);
-              consider(p.w, a, 3);
-            }
-          }
-        }
-      } else {
-        const int total = A * C;
-        for (int e0 = tid; e0 < total; e0 += NT * 8) {  // 8 independent loads in flight per thread
-          float sv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * NT;
-            sv[u] = (e < total)
-                        ? (cscale ? __fmul_rn(__ldg(img_scores + e), __ldg(cscale + e % C)) : __ldg(img_scores + e))
-                        : -INFINITY;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * NT;
-            const int a = e / C;
-            consider(sv[u], a, e - a * C);
-          }
-        }
-      }
+      fast_all_refill_scan<LOGITS, NT>(img_scores, cscale, A, C, score_thr, comp_lo, comp_hi, s_list, &s_n, tid);
       __syncthreads();
       const int n_new = s_n;
       if (n_new > kCap) {
@@ -1597,9 +1660,50 @@ __global__ void __launch_bounds__(NT, MINB)
     __syncthreads();
     PHASE_ADD(15);  // refill scans
   }
+  PHASE_ADD(23);  // (loop exit: up to the barrier)
   __syncthreads();
+  PHASE_ADD(19);  // (loop exit: barrier)
   // ---- rows, already in merge order: [label, prob, xmin, ymin, xmax, ymax] (layers.py:155-162), zero padding ----
   float* o = out + (size_t)b * K * 6;
+  if constexpr (ALGO == 1) {
+    if ((size_t)K * 6 * sizeof(float) <= sizeof(s_tmp)) {  // (uniform) rows staged in shared memory, stored coalesced
+      float* s_rows = reinterpret_cast<float*>(s_tmp);
+      for (int r = tid; r < n_sel; r += NT) {
+        const u64 cp = s_pick[r];
+        const int idx = comp_all_idx(cp);
+        const unsigned fl = s_sflag[r];
+        const float4 nb = s_sbox[r];
+        float4 bx = make_float4((fl & 1u) ? nb.z : nb.x, (fl & 2u) ? nb.w : nb.y, (fl & 1u) ? nb.x : nb.z,
+                                (fl & 2u) ? nb.y : nb.w);  // the raw (ymin, xmin, ymax, xmax) back from the normalised box
+        if (fl & 4u) bx = ssdx_load_box(boxes, box_row0, idx);
+        float* row = s_rows + r * 6;
+        row[0] = (float)comp_all_cls(cp);
+        row[1] = key_to_score((unsigned)(cp >> 32));
+        row[2] = bx.y;  // gather [1,0,3,2], layers.py:155
+        row[3] = bx.x;
+        row[4] = bx.w;
+        row[5] = bx.z;
+        if (out_idx) out_idx[(size_t)b * K + r] = idx;
+      }
+      for (int e = n_sel * 6 + tid; e < K * 6; e += NT) s_rows[e] = 0.0f;
+      __syncthreads();
+      PHASE_ADD(20);  // rows staged
+      if ((reinterpret_cast<uintptr_t>(o) & 7) == 0) {  // (K * 6 floats per image: always a whole number of pairs)
+        for (int e = tid; e < K * 3; e += NT)
+          reinterpret_cast<float2*>(o)[e] = reinterpret_cast<const float2*>(s_rows)[e];
+      } else {
+        for (int e = tid; e < K * 6; e += NT) o[e] = s_rows[e];
+      }
+      if (out_idx)
+        for (int e = n_sel + tid; e < K; e += NT) out_idx[(size_t)b * K + e] = -1;
+      if (out_valid && tid == 0) out_valid[b] = n_sel;
+      PHASE_ADD(16);  // rows
+#ifdef SSDX_PHASE_TIMERS
+      if (tid == 0) atomicAdd(&g_phase_cycles[18], 1ull);
+#endif
+      return;
+    }
+  }
   for (int r = tid; r < n_sel; r += NT) {
     const u64 cp = s_pick[r];
     const int idx = comp_all_idx(cp);

@@ -23,8 +23,9 @@ for it in range(2):
     nms(yx, scd); torch.cuda.synchronize()
 sx.lib.ssdx_debug_phase_cycles(out)
 v = list(out)
-names = ["list load", "sort", "box gather", "pair tests", "block resolve", "refill scans", "rows"]
-n = max(v[18], 1); tot = sum(v[10:17])
+names = {10: "list load", 11: "sort", 12: "box gather", 21: "kept-box tests", 22: "tiles (warp 0)", 13: "pair tests: barrier",
+         14: "block resolve", 15: "refill scans", 24: "kept boxes copied", 23: "loop exit: code", 19: "loop exit: barrier", 20: "rows staged", 16: "rows stored"}
+n = max(v[18], 1); tot = sum(v[k] for k in names)
 print(f"nms fast_all, B={B}: images {v[18]}  cycles/image {tot/n:.0f} ({tot/n/1965:.1f} us)")
-for nm, c in zip(names, v[10:17]):
-    print(f"  {nm:14s} {c/n:9.0f} cycles/image  {100*c/max(tot,1):5.1f}%")
+for k, nm in names.items():
+    print(f"  {nm:20s} {v[k]/n:9.0f} cycles/image  {100*v[k]/max(tot,1):5.1f}%")
