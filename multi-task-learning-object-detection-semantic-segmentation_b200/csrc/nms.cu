@@ -154,6 +154,31 @@ __device__ __forceinline__ float class_unit(const float ext) {
   e = e < -8 ? -8 : (e > 14 ? 14 : e);
   return __uint_as_float((unsigned)(e + 127) << 23);
 }
+// The prefilter boxes of a chunk are stored for the tile loop as column pairs: entry 16 * G + p holds candidates
+// 32 * G + p (low halves) and 32 * G + 16 + p (high halves), one half2 per corner, so that one packed compare tests
+// one corner of two columns against a row and the two half results ARE the two columns (no "both halves" reduction):
+// 3.5 instructions per pair instead of 6.5.
+struct __align__(16) HPair {
+  __half2 ymn, ymx, xmn, xmx;
+};
+__device__ __forceinline__ void store_hpair(HPair* pairs, const int i, const HBox h) {
+  __half* f = reinterpret_cast<__half*>(pairs + ((i >> 5) * 16 + (i & 15))) + ((i >> 4) & 1);
+  f[0] = __low2half(h.mn);   // ymn
+  f[2] = __low2half(h.mx);   // ymx
+  f[4] = __high2half(h.mn);  // xmn
+  f[6] = __high2half(h.mx);  // xmx
+}
+__device__ __forceinline__ HBox load_hbox(const HPair* pairs, const int i) {
+  const __half* f = reinterpret_cast<const __half*>(pairs + ((i >> 5) * 16 + (i & 15))) + ((i >> 4) & 1);
+  HBox h;
+  h.mn = __halves2half2(f[0], f[4]);
+  h.mx = __halves2half2(f[2], f[6]);
+  return h;
+}
+// tile t of the lower triangle (t = g (g + 1) / 2 + jb, jb <= g) -> row group g
+__constant__ unsigned char kTileRowGroup[36] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5,
+                                                5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7};
+
 // exact TF IoU test for a pair that overlaps
 __device__ __forceinline__ bool iou_exceeds_overlapping(const float4 a, const float aa, const float4 b, const float ab,
                                                         const float thr) {
@@ -1026,6 +1051,9 @@ __global__ void __launch_bounds__(NT)
   const int tid = threadIdx.x, lane = tid & 31;
   const int NS = (A + kSampleStride - 1) / kSampleStride;
   const float* img = scores + (size_t)b * A * C;
+  // programmatic dependent launch: the CTAs of fast_all may take the SM slots this grid leaves free right away
+  // (they wait in griddepcontrol.wait until this grid has completed and its lists are visible)
+  asm volatile("griddepcontrol.launch_dependents;");
   if (tid == 0) s_cnt = 0;
 
   // ---- sample: every 16th anchor (jittered), all classes; each thread keeps the largest key it sees ----
@@ -1250,6 +1278,8 @@ __global__ void __launch_bounds__(NT, MINB)
   float* s_carea = reinterpret_cast<float*>(s_cbox + kFastThreads);               // [kFastThreads]
   unsigned char* s_ccls = reinterpret_cast<unsigned char*>(s_carea + kFastThreads);  // [kFastThreads]
   HBox* s_chbox = reinterpret_cast<HBox*>(s_ccls + kFastThreads);                    // [kFastThreads]
+  HPair* s_cpair = reinterpret_cast<HPair*>(s_chbox);  // ALGO 1: the same bytes as column pairs [kFastThreads / 2]
+  static_assert(((sizeof(float4) + sizeof(float) + 1) * kFastThreads) % 16 == 0, "s_cpair alignment");
   // ALGO 1: how the raw box differs from the normalised one (bit 0: y corners swapped, bit 1: x corners swapped,
   // bit 2: NaN or equal corners - reload the raw box for the output row)
   unsigned char* s_cflag = reinterpret_cast<unsigned char*>(s_chbox + kFastThreads);  // [kFastThreads]
@@ -1258,6 +1288,9 @@ __global__ void __launch_bounds__(NT, MINB)
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // launched as a programmatic dependent of select_all (same ssdx_nms call): nothing that kernel wrote is read
+  // before this point (a no-op for a plain launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   int n = info[(size_t)b * kInfo + 0];
   // Everything at or above comp_hi (composite order: score key, class, anchor) has been listed.  Candidates are
   // fetched in composite bands [comp_lo, comp_hi), so even thousands of equal scores are split (by class and anchor)
@@ -1283,6 +1316,67 @@ __global__ void __launch_bounds__(NT, MINB)
   int seen = 0;       // candidates consumed so far (ALGO 1: sizes the chunks after the first from the keep rate)
   float unit = 0.0f;  // ALGO 1: class shift of the prefilter boxes, from the coordinate range of the first chunk
   while (true) {
+    if constexpr (ALGO == 1) {
+      // ---- a tier above 512 candidates would take the 1024-key sort (more than twice the time of the 512-key one,
+      //      and the slowest images set the duration of the kernel): raise the lower end of the tier instead - a
+      //      bisection over the score keys for a threshold that keeps 320..512 candidates; what is dropped stays
+      //      below comp_hi and is fetched again by a refill in the rare case it is needed ----
+      if (n > 512) {  // (uniform)
+        unsigned key[kCap / NT];
+        unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+        for (int r = 0; r < kCap / NT; ++r) {
+          const int i = r * NT + tid;
+          key[r] = (i < n) ? (unsigned)(s_list[i] >> 32) : 0u;  // (listed keys are >= 1)
+          if (i < n) kmin = min(kmin, key[r]), kmax = max(kmax, key[r]);
+        }
+        kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
+        kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+        if (tid == 0) s_n = 0, s_nsel = -1;  // (as unsigned: the largest key; s_nsel is rewritten before it is read again)
+        __syncthreads();
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(&s_n), kmax), atomicMin(reinterpret_cast<unsigned*>(&s_nsel), kmin);
+        __syncthreads();
+        unsigned lo = (unsigned)s_nsel;      // count(key >= lo) = n > 512
+        unsigned hi = (unsigned)s_n + 1u;    // count(key >= hi) = 0  (kmax < 2^32 - 1: NaN scores are not listed)
+        unsigned cut = 0u;
+        int n_cut = 0;
+        while (hi - lo > 1u) {
+          const unsigned mid = lo + ((hi - lo) >> 1);
+          __syncthreads();
+          if (tid == 0) s_n = 0;
+          __syncthreads();
+          int c = 0;
+#pragma unroll
+          for (int r = 0; r < kCap / NT; ++r) c += key[r] >= mid;
+          c = __reduce_add_sync(0xFFFFFFFFu, c);
+          if (lane == 0 && c != 0) atomicAdd(&s_n, c);
+          __syncthreads();
+          const int cnt = s_n;
+          if (cnt > 512) {
+            lo = mid;
+          } else {
+            hi = mid;
+            cut = mid;
+            n_cut = cnt;
+            if (cnt >= 320) break;
+          }
+        }
+        if (n_cut > 0) {  // (uniform) keep the n_cut candidates at or above `cut`
+          __syncthreads();
+          if (tid == 0) s_n = 0;
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < kCap / NT; ++r) {
+            if (key[r] >= cut) s_tmp[atomicAdd(&s_n, 1)] = s_list[r * NT + tid];
+          }
+          __syncthreads();
+          for (int i = tid; i < n_cut; i += NT) s_list[i] = s_tmp[i];
+          n = n_cut;
+          comp_hi = (u64)cut << 32;
+          __syncthreads();
+        }
+      }
+    }
     // ---- sort the current tier (merged order) ----
     fast_sort<(NT >= 512 ? 512 : 256)>(s_list, s_tmp, n, tid);
     PHASE_ADD(11);  // sort
@@ -1338,7 +1432,7 @@ __global__ void __launch_bounds__(NT, MINB)
         }
         if (tid < m) hb = make_hbox_cls(bi, cls, unit);
         if (tid < kFastThreads) {
-          s_chbox[tid] = hb;
+          store_hpair(s_cpair, tid, hb);
           s_supb[tid] = (unsigned char)(tid >= m);
         }
         __syncthreads();
@@ -1352,7 +1446,7 @@ __global__ void __launch_bounds__(NT, MINB)
             const float4 b = s_cbox[ci];
             const float a = s_carea[ci];
             const unsigned c = s_ccls[ci];
-            const HBox h = s_chbox[ci];
+            const HBox h = load_hbox(s_cpair, ci);
             bool hit = false;
             if (a > 0.0f) {  // a box without area is never suppressed
               int sidx = n_sel0 - 1 - part;
@@ -1384,17 +1478,24 @@ __global__ void __launch_bounds__(NT, MINB)
         {
           const int ntiles = R * (R + 1) / 2;
           for (int t = warp; t < ntiles; t += NT / 32) {
-            int g = 0;
-            while ((g + 1) * (g + 2) / 2 <= t) ++g;
+            const int g = kTileRowGroup[t];
             const int jb = t - g * (g + 1) / 2;
             const int i = 32 * g + lane;
-            const HBox me = s_chbox[i];  // (rows beyond m overlap nothing)
-            const HBox* col = s_chbox + 32 * jb;  // (columns beyond m overlap nothing either)
+            // the row's own corners, each in both halves (rows and columns beyond m overlap nothing)
+            const HPair mine = s_cpair[g * 16 + (lane & 15)];
+            const bool up = lane >= 16;
+            const __half2 r_ymn = up ? __high2half2(mine.ymn) : __low2half2(mine.ymn);
+            const __half2 r_ymx = up ? __high2half2(mine.ymx) : __low2half2(mine.ymx);
+            const __half2 r_xmn = up ? __high2half2(mine.xmn) : __low2half2(mine.xmn);
+            const __half2 r_xmx = up ? __high2half2(mine.xmx) : __low2half2(mine.xmx);
+            const HPair* col = s_cpair + jb * 16;
             unsigned ov = 0u;
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {  // both packed compares unconditionally, one predicated OR per pair
-              const HBox o = col[jj];
-              if ((__hgt2_mask(me.mx, o.mn) & __hgt2_mask(o.mx, me.mn)) == 0xFFFFFFFFu) ov |= 1u << jj;
+            for (int p = 0; p < 16; ++p) {  // columns 32 jb + p (bit p) and 32 jb + 16 + p (bit 16 + p)
+              const HPair c = col[p];
+              const unsigned all = __hgt2_mask(r_ymx, c.ymn) & __hgt2_mask(c.ymx, r_ymn) & __hgt2_mask(r_xmx, c.xmn) &
+                                   __hgt2_mask(c.xmx, r_xmn);
+              ov |= all & (0x00010001u << p);
             }
             if (jb == g) ov &= (1u << lane) - 1u;  // earlier candidates only
             unsigned keep = 0u;
@@ -1423,7 +1524,7 @@ __global__ void __launch_bounds__(NT, MINB)
         PHASE_ADD(13);  // pair tests: barrier
         // ---- (c) one warp decides the chunk, 64 candidates at a time (the arbiter favours the highest warp id) ----
         if (warp == NT / 32 - 1) {
-          const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
+          const unsigned me = 1u << lane;
           unsigned keptw[8];
 #pragma unroll
           for (int w = 0; w < 8; ++w) keptw[w] = 0u;
@@ -1489,7 +1590,7 @@ __global__ void __launch_bounds__(NT, MINB)
               s_sbox[r] = s_cbox[tid];
               s_sarea[r] = s_carea[tid];
               s_scls[r] = s_ccls[tid];
-              s_shbox[r] = s_chbox[tid];
+              s_shbox[r] = load_hbox(s_cpair, tid);
               s_sflag[r] = s_cflag[tid];
               s_pick[r] = s_list[g0 + tid];
             }
@@ -2117,9 +2218,39 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
       SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
     }
     if (!ph2) return SSDX_OK;
+    // select_all of this very call is the stream predecessor: launch as its programmatic dependent
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t fa_cfg = {};
+    fa_cfg.gridDim = dim3(batch);
+    fa_cfg.dynamicSmemBytes = 0;
+    fa_cfg.stream = s;
+    fa_cfg.attrs = pdl_attr;
+#ifdef SSDX_NO_PDL
+    fa_cfg.numAttrs = 0;
+#else
+    fa_cfg.numAttrs = ph1 ? 1 : 0;
+#endif
+    const u64* lists_c = lists;
+    const int* info_c = info;
+    // 7 CTAs of 31 KB per SM only fit with the largest shared-memory carve-out: ask for it (a hint the driver may
+    // otherwise not choose on its own)
+#ifdef SSDX_NO_CARVEOUT
+#define SSDX_FAST_ALL_CARVEOUT(MAXSEL, MINB, LOG, ALGO, NT) do {} while (0)
+#else
+#define SSDX_FAST_ALL_CARVEOUT(MAXSEL, MINB, LOG, ALGO, NT)                                          \
+  SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_fast_all_kernel<MAXSEL, MINB, LOG, ALGO, NT>,              \
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+#endif
 #define SSDX_FAST_ALL(MAXSEL, MINB, LOG, ALGO, NT)                                                                  \
-  ssdx_nms_fast_all_kernel<MAXSEL, MINB, LOG, ALGO, NT><<<batch, NT, 0, s>>>(                                       \
-      bx, scores, cscale, lists, info, A, C, max_total, iou_threshold, score_threshold, out, out_valid, out_anchor_idx)
+  do {                                                                                                              \
+    fa_cfg.blockDim = dim3(NT);                                                                                     \
+    SSDX_FAST_ALL_CARVEOUT(MAXSEL, MINB, LOG, ALGO, NT);                                                            \
+    SSDX_CUDA(cudaLaunchKernelEx(&fa_cfg, ssdx_nms_fast_all_kernel<MAXSEL, MINB, LOG, ALGO, NT>, bx, scores, cscale, \
+                                 lists_c, info_c, A, C, max_total, iou_threshold, score_threshold, out, out_valid,  \
+                                 out_anchor_idx));                                                                  \
+  } while (0)
 #define SSDX_FAST_ALL_LOG(MAXSEL, MINB, ALGO, NT)           \
   do {                                                      \
     if (logits) SSDX_FAST_ALL(MAXSEL, MINB, true, ALGO, NT); \
@@ -2140,6 +2271,7 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
       else SSDX_FAST_ALL_LOG(kFastMaxSel, 5, 1, kFastThreads);
     }
 #undef SSDX_FAST_ALL_LOG
+#undef SSDX_FAST_ALL_CARVEOUT
 #undef SSDX_FAST_ALL
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_all_kernel");
     return SSDX_OK;  // (no fallback: the band refills of fast_all split even massive score ties)

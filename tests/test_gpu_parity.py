@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI, via the ssdseglib mirror) against the CPU oracle and
 the committed golden fixtures.  Bar: matched indices / labels / NMS keep-sets / TP flags / counts bit-exact;
 offsets and decoded coordinates within 1e-5 relative in fp32 (absolute floors stated at each check)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -411,6 +413,33 @@ def test_nms_merged_runs_dry_and_refills(lib):
     scores = orc.dedup_scores(rng.uniform(0.02, 1, size=(B, A, C)).astype(np.float32))
     out = nms_check(lib, yxyx, scores, 200, 200, 0.45, 0.01)
     assert (out[..., 1] > 0).sum(axis=1).max() <= 4 * 40 + 40  # ~ one survivor per (cluster, class)
+
+
+@pytest.mark.parametrize("batch", [40, 200, 460])
+def test_nms_merged_pipeline_cta_widths(lib, batch):
+    """The merged pipeline picks 1024-, 512- or 256-thread CTAs from the batch size (up to one, up to three, more than
+    three images per SM).  Half of the images hold clustered boxes (several chunks per image: kept-box tests, chunk
+    sizing from the keep rate), a few hold boxes with swapped / equal corners (output rows rebuilt from the
+    normalised box); pixel and unit-square coordinates (class shift of the prefilter).  C oracle on every image."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(batch)
+    A, C = 1500, 5
+    c = rng.uniform(60, 580, size=(batch, A, 2))
+    centers = rng.uniform(80, 560, size=(batch, 12, 2))
+    which = rng.integers(0, 12, size=(batch, A))
+    clustered = np.take_along_axis(centers, which[..., None].repeat(2, -1), axis=1) + rng.normal(0, 5, size=(batch, A, 2))
+    c[::2] = clustered[::2]
+    wh = rng.uniform(30, 120, size=(batch, A, 2))
+    yxyx = np.concatenate([c - wh / 2, c + wh / 2], -1).astype(np.float32)
+    yxyx[1::7, ::3] = yxyx[1::7, ::3][..., [2, 1, 0, 3]]      # y corners swapped
+    yxyx[3::7, ::5] = yxyx[3::7, ::5][..., [0, 3, 2, 1]]      # x corners swapped
+    yxyx[5::7, ::4, 2] = yxyx[5::7, ::4, 0]                   # no height
+    yxyx[1::4] /= 640.0                                       # unit-square coordinates
+    scores = orc.dedup_scores(rng.uniform(0.0, 1, size=(batch, A, C)).astype(np.float32))
+    layer = lib.layers.NonMaximumSuppression(120, 120, 0.45, 0.05, False)
+    out, valid, aidx = layer.call(yxyx, scores, return_aux=True)
+    ref, vref, aref = c_oracle.combined_nms(yxyx, scores, 120, 120, 0.45, 0.05, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(valid, vref) and np.array_equal(aidx, aref) and np.array_equal(out, ref)
 
 
 @pytest.mark.parametrize("C,mpc,mtot", [(4, 200, 200), (4, 400, 300), (4, 20, 50), (7, 100, 100)])

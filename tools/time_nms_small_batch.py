@@ -25,3 +25,16 @@ for path in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("auto", "blocked"
         for _ in range(10): fn()
         e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) * 100)
     ts.sort(); print(f"B={B} nms_path={path}: {ts[len(ts)//2]:.1f} us")
+if len(sys.argv) > 3:  # the two phases on their own (ssdx_nms_select / ssdx_nms_finish)
+    sx.set_option("nms_path", "auto")
+    f1 = lambda: sx.check(sx.lib.ssdx_nms_select(scd.data_ptr(), None, B, A, C, K, K, 0.01, ws.data_ptr(), ws.numel(), 0, sp))
+    f2 = lambda: sx.check(sx.lib.ssdx_nms_finish(yx.data_ptr(), scd.data_ptr(), None, B, A, C, K, K, 0.45, 0.01, out.data_ptr(), val.data_ptr(), None, ws.data_ptr(), ws.numel(), 0, sp))
+    for name, f in (("select", f1), ("finish", f2)):
+        for _ in range(5): f()
+        torch.cuda.synchronize(); ts = []
+        for _ in range(20):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10): f()
+            e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) * 100)
+        ts.sort(); print(f"B={B} {name} alone: {ts[len(ts)//2]:.1f} us")
