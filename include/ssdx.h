@@ -59,8 +59,9 @@ SSDX_API int ssdx_device_count(int* count);
 /* Process-level dispatch override; every path of an entry point gives identical results, the options exist for tests
  * and tuning runs.  key "encode_path": "auto" | "grid_fused" | "grid_split" (closed-form windows, anchor tables that
  * are unions of regular grids) | "tile_fused" | "tile_tiled" (tile match, any anchor table);
- * key "nms_path": "auto" | "perclass" | "pcta" | "generic" | "blocked".  A forced path that cannot serve a call (table is not a
- * grid, shapes too large for one CTA per image) falls back to the automatic choice for that call. */
+ * key "nms_path": "auto" | "perclass" | "pcta" | "generic" | "blocked"; key "nms_cta": "auto" | "256" | "512" | "1024"
+ * (threads per image in the merged NMS pipeline; auto = from the batch size).  A forced path that cannot serve a call
+ * (table is not a grid, shapes too large for one CTA per image) falls back to the automatic choice for that call. */
 SSDX_API int ssdx_set_option(const char* key, const char* value);
 
 /* ---- anchors: datacoder.py:6-117 (ctor), boxes.py:391-445 (conversions) ----

@@ -33,6 +33,8 @@ bool ssdx_debug_sync() {
 
 static std::atomic<int> g_encode_path(SSDX_ENC_AUTO);
 static std::atomic<int> g_nms_path(0);
+static std::atomic<int> g_nms_cta(0);
+int ssdx_option_nms_cta() { return g_nms_cta.load(std::memory_order_relaxed); }
 int ssdx_option_encode_path() { return g_encode_path.load(std::memory_order_relaxed); }
 const char* ssdx_option_nms_path() {
   static const char* const names[5] = {nullptr, "perclass", "pcta", "generic", "blocked"};
@@ -230,6 +232,14 @@ int ssdx_set_option(const char* key, const char* value) {
     for (int i = 0; i < 5; ++i)
       if (strcmp(value, v[i]) == 0) {
         g_nms_path.store(i);
+        return SSDX_OK;
+      }
+  } else if (strcmp(key, "nms_cta") == 0) {
+    static const char* const v[4] = {"auto", "256", "512", "1024"};
+    static const int w[4] = {0, 256, 512, 1024};
+    for (int i = 0; i < 4; ++i)
+      if (strcmp(value, v[i]) == 0) {
+        g_nms_cta.store(w[i]);
         return SSDX_OK;
       }
   } else {

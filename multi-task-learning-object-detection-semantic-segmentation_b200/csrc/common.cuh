@@ -132,6 +132,7 @@ static inline size_t ssdx_align_up(size_t v, size_t a) { return (v + a - 1) / a 
 // results - the options exist so that tests and tuning runs can pin one.
 enum { SSDX_ENC_AUTO = 0, SSDX_ENC_TILE_FUSED, SSDX_ENC_TILE_TILED, SSDX_ENC_GRID_FUSED, SSDX_ENC_GRID_SPLIT };
 int ssdx_option_encode_path();
+int ssdx_option_nms_cta();  // 0 (auto: from the batch size) | 256 | 512 | 1024 threads per image in the merged NMS pipeline
 const char* ssdx_option_nms_path();  // NULL (auto) | "perclass" | "pcta" | "generic" | "blocked"
 
 // number of SMs of a device (cached per device)

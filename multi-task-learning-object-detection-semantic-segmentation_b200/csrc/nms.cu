@@ -2211,8 +2211,10 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
                                                                         all_rank, lists, info);                      \
   } while (0)
       const int sel_sms = ssdx_sm_count(device);  // few images: wider CTAs keep more loads in flight per image
-      if (batch <= sel_sms) SSDX_SELECT_ALL(1024);
-      else if (batch <= 3 * sel_sms) SSDX_SELECT_ALL(512);
+      const int sel_cta = ssdx_option_nms_cta() ? ssdx_option_nms_cta()
+                                                : (batch <= sel_sms ? 1024 : (batch <= 3 * sel_sms ? 512 : kSelThreads));
+      if (sel_cta == 1024) SSDX_SELECT_ALL(1024);
+      else if (sel_cta == 512) SSDX_SELECT_ALL(512);
       else SSDX_SELECT_ALL(kSelThreads);
 #undef SSDX_SELECT_ALL
       SSDX_LAUNCH_CHECK("ssdx_nms_select_all_kernel");
@@ -2260,14 +2262,16 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
     // few images: one wide CTA per image (the 32 x 32 tiles of a chunk, the kept-box tests, refill scans and rows
     // spread over 32 or 16 warps; sort and gather stay on the first 8); many images: 7 narrow CTAs per SM
     const int sms = ssdx_sm_count(device);
+    // (ssdx_set_option("nms_cta", ...) pins the width: the tests run every width at small batch sizes)
+    const int cta = ssdx_option_nms_cta() ? ssdx_option_nms_cta() : (batch <= sms ? 1024 : (batch <= 3 * sms ? 512 : 256));
     if (max_total <= 256) {
       if (blocked) SSDX_FAST_ALL_LOG(256, SSDX_FAST_MINB, 0, kFastThreads);
-      else if (batch <= sms) SSDX_FAST_ALL_LOG(256, 1, 1, 1024);
-      else if (batch <= 3 * sms) SSDX_FAST_ALL_LOG(256, 3, 1, 512);
+      else if (cta == 1024) SSDX_FAST_ALL_LOG(256, 1, 1, 1024);
+      else if (cta == 512) SSDX_FAST_ALL_LOG(256, 3, 1, 512);
       else SSDX_FAST_ALL_LOG(256, SSDX_FAST_MINB, 1, kFastThreads);
     } else {
       if (blocked) SSDX_FAST_ALL_LOG(kFastMaxSel, 6, 0, kFastThreads);
-      else if (batch <= sms) SSDX_FAST_ALL_LOG(kFastMaxSel, 1, 1, 1024);
+      else if (cta == 1024) SSDX_FAST_ALL_LOG(kFastMaxSel, 1, 1, 1024);
       else SSDX_FAST_ALL_LOG(kFastMaxSel, 5, 1, kFastThreads);
     }
 #undef SSDX_FAST_ALL_LOG

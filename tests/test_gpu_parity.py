@@ -36,19 +36,24 @@ def encode_path(request, lib):
     lib._ssdx.set_option("encode_path", "auto")
 
 
-@pytest.fixture(autouse=True, params=["fast", "blocked", "perclass", "pcta", "generic"])
+@pytest.fixture(autouse=True, params=["fast", "fast_256t", "fast_512t", "blocked", "perclass", "pcta", "generic"])
 def nms_path(request, lib):
     """NMS tests run on the default dispatch (merged one-pass-per-image pipeline when max_per_class >= max_total,
     else the per-class pipeline: one warp per segment for caps up to 32, one CTA per segment above; generic only for
-    handed-over work), with the merged pipeline's 64-candidate blocked greedy pass instead of the chunked bit matrix
+    handed-over work), at the pinned CTA widths of the merged pipeline ("fast_256t": the kernel of the bench's batch
+    size; "fast_512t"), with the merged pipeline's 64-candidate blocked greedy pass instead of the chunked bit matrix
     ("blocked"), with the per-class pipeline forced ("perclass"), with the per-class CTA kernel forced for every
     cap ("pcta"), and with the exact generic kernel alone."""
     if request.param != "fast":
         if "nms" not in request.node.name:
             pytest.skip("NMS driver does not matter for this test")
-        lib._ssdx.set_option("nms_path", request.param)
+        if request.param.startswith("fast_"):  # the default pipeline at a pinned CTA width (auto: 1024 threads per
+            lib._ssdx.set_option("nms_cta", request.param[5:-1])  # image at these batch sizes)
+        else:
+            lib._ssdx.set_option("nms_path", request.param)
     yield request.param
     lib._ssdx.set_option("nms_path", "auto")
+    lib._ssdx.set_option("nms_cta", "auto")
 
 
 @pytest.fixture(scope="module")
@@ -479,8 +484,8 @@ def test_nms_randomized_differential(lib, nms_path):
         "fuzz_nms", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_nms.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    seed = {"fast": 11, "perclass": 12, "pcta": 13, "generic": 14, "blocked": 15}[nms_path]
-    assert mod.run(250 if nms_path in ("fast", "blocked") else 120, seed, verbose=False) == 0
+    seed = {"fast": 11, "perclass": 12, "pcta": 13, "generic": 14, "blocked": 15, "fast_256t": 16, "fast_512t": 17}[nms_path]
+    assert mod.run(250 if nms_path.startswith("fast") or nms_path == "blocked" else 120, seed, verbose=False) == 0
 
 
 @pytest.mark.parametrize("C,mpc,mtot", [(4, 200, 200), (4, 4, 10), (6, 50, 50)])

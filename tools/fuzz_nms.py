@@ -1,6 +1,6 @@
 """GPU box: randomized differential test of the NMS dispatch (merged / warp-per-segment / CTA-per-segment / generic)
 against the C oracle: random shapes, class counts, caps, thresholds, score distributions (distinct, quantised to force
-ties, saturated), box layouts (spread, clustered, degenerate).  usage: python tools/fuzz_nms.py [cases] [seed]"""
+ties, saturated), box layouts (spread, clustered, degenerate).  usage: python tools/fuzz_nms.py [cases] [seed] [nms_cta]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multi-task-learning-object-detection-semantic-segmentation_b200"))
@@ -52,4 +52,7 @@ def run(cases: int, seed: int, verbose: bool = True) -> int:
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 3:  # pinned CTA width of the merged pipeline: 256 | 512 | 1024
+        from ssdseglib import _ssdx
+        _ssdx.set_option("nms_cta", sys.argv[3])
     sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 200, int(sys.argv[2]) if len(sys.argv) > 2 else 0) else 0)
