@@ -655,6 +655,23 @@ def gpu_arm(args, rank, world, local_rank):
         as the two input branches of the reference's NMS layer allow (models.py:402-414)."""
         nonlocal sp
         cur = torch.cuda.current_stream(dev)
+        if events is None and args.nms_beside_decode:
+            # encode; then, side by side, the decode kernel (materialises the (B, A, 4) box tensor: memory-bound) and
+            # the NMS call that reads the offsets itself (ssdx_decode_nms: the few hundred boxes an image's candidates
+            # touch are decoded on the fly with the decode kernel's own arithmetic - detections bit-identical to NMS of
+            # the decoded tensor; its second kernel is instruction-bound)
+            if "encode" in stages:
+                sx.check(sx.lib.ssdx_encode(handle, d_boxes.data_ptr(), d_labels.data_ptr(), d_counts.data_ptr(), B,
+                                            G_STD, C_STD, 0.5, std, o_labels.data_ptr(), o_offsets.data_ptr(), None,
+                                            ws_enc.data_ptr(), ws_enc.numel(), sp))
+            src = o_offsets if "encode" in stages else d_pred_off
+            side.wait_stream(cur)
+            sx.check(sx.lib.ssdx_decode(dec_layer._anchors.handle, src.data_ptr(), B, std, 0, o_boxes.data_ptr(), sp))
+            sx.check(sx.lib.ssdx_decode_nms(dec_layer._anchors.handle, src.data_ptr(), std, d_scores.data_ptr(), None, B,
+                                            C_STD, K_STD, K_STD, 0.45, 0.01, o_det.data_ptr(), o_valid.data_ptr(), None,
+                                            ws_nms.data_ptr(), ws_nms.numel(), side.cuda_stream))
+            cur.wait_stream(side)
+            return
         if events is not None or not overlap:
             run_range(0, B, sp, ws_enc, ws_nms, events, stream if events is not None else cur)
             return
@@ -954,6 +971,9 @@ def main():
     ap.add_argument("--nms-split", type=int, default=1,
                     help="sub-batches of the NMS stage alone, pipelined on two streams: the candidate selection "
                          "(memory-bound) of one overlaps the sort + suppression (instruction-bound) of the other")
+    ap.add_argument("--nms-beside-decode", action="store_true",
+                    help="after encode, run the decode kernel and the NMS call that reads the offsets (ssdx_decode_nms) "
+                         "side by side on two streams")
     ap.add_argument("--pipeline-streams", type=int, default=2)
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to the CPU cores next to its GPU")
     ap.add_argument("--pipeline-split", default="", help="comma-separated sub-batch sizes instead of an even split")
