@@ -30,14 +30,22 @@
 //   boxes already selected for its own class: within a class that is exactly the per-class greedy order, and the
 //   visiting order is the merge order, so everything after the K-th selection can never reach the output.  One
 //   list, one sort and one greedy pass per image instead of one per (image, class), and no merge kernel.
-//   1m. select_all : one CTA per image: threshold from a 1/16 sample of all classes (CTA-wide bisection), then one
-//                    streaming pass with a single compare per score; ~400 composites
+//   1m. select_all : one CTA per image (256 threads; 512 / 1024 when the batch leaves SMs idle): threshold from a
+//                    1/16 sample of all classes (bisection over the per-thread sample maxima), then one streaming
+//                    pass with a single compare per score; ~400 composites
 //                    (score key << 32 | ~class << 24 | ~anchor) per image.
-//   2m. fast_all   : one CTA per image: register bitonic sort, blocked greedy suppression with a class-equality
-//                    test on the rare overlapping pairs, rows written in place.  A list that runs dry - or that
-//                    overflowed, or that holds thousands of equal scores - is refilled in bands of the full 64-bit
-//                    composite order (score key, class, anchor), narrowed down to a single composite if need be:
-//                    the kernel never hands an image over to the generic kernel.
+//   2m. fast_all   : one CTA per image, launched as a programmatic dependent of select_all: a tier above 512
+//                    candidates is trimmed by a bisection over the score keys; register bitonic sort; the sorted
+//                    candidates are taken in chunks of up to 256: box gather, test against the boxes kept by
+//                    earlier chunks, the chunk against itself as 32 x 32 tiles of a lower-triangular bit matrix
+//                    (all warps, no barrier inside; fp16 prefilter boxes stored as column pairs, class folded in as
+//                    a coordinate shift; class test and exact fp32 IoU on the pairs that pass), one warp resolves
+//                    the chunk from the bit rows with a parallel fix-point, all warps copy the kept boxes; rows
+//                    staged in shared memory.  A list that runs dry - or that overflowed, or that holds thousands of
+//                    equal scores - is refilled in bands of the full 64-bit composite order (score key, class,
+//                    anchor), narrowed down to a single composite if need be: the kernel never hands an image over
+//                    to the generic kernel.  (ssdx_set_option("nms_path", "blocked"): the round-1 form of the greedy
+//                    pass, 64 candidates at a time against the kept boxes.)
 //
 // IoU follows TF's IOU(): min/max-normalised corners, area = (y1-y0)*(x1-x0), 0 if either area <= 0,
 // inter / ((area_i + area_j) - inter) with IEEE division, suppressed iff IoU > iou_thr (strict).
