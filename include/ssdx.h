@@ -228,9 +228,10 @@ SSDX_API int ssdx_iou_pred_vs_true(const int32_t* pred_label, const float* pred_
  * The reference's class head ends in tf.keras.layers.Softmax (models.py:259, :694) whose (B,A,C) output feeds
  * SegmentationSuppression and the NMS layer.  ssdx_softmax_scores writes probabilities = softmax(logits) [* class_scale]
  * (rows = B*A; shifted by the row maximum, hardware exponential, fp32 sum in class order, one hardware reciprocal: within
- * ~4e-6 relative of the exact soft-max, inside the path's 1e-5 fp32 tolerance).  ssdx_nms_logits == ssdx_softmax_scores followed by ssdx_nms_scaled, bit for bit, but when the merged
- * NMS pipeline applies (max_per_class >= max_total, 4 classes) the probabilities are computed inside the score filter
- * as the logits are read and never written to memory; otherwise they are materialised in the workspace first. */
+ * ~4e-6 relative of the exact soft-max, inside the path's 1e-5 fp32 tolerance).  ssdx_nms_logits == ssdx_softmax_scores
+ * followed by ssdx_nms_scaled, bit for bit, but with 4 classes (rows of 16 aligned bytes) the probabilities are
+ * computed inside the kernels that read the scores and never written to memory; otherwise they are materialised in the
+ * workspace first. */
 SSDX_API int ssdx_softmax_scores(const float* logits, int64_t rows, int32_t num_classes, const float* class_scale,
                                  float* out, int device, ssdx_stream stream);
 SSDX_API size_t ssdx_nms_logits_workspace_bytes(int32_t batch, int32_t num_anchors, int32_t num_classes,

@@ -117,6 +117,18 @@ __device__ __forceinline__ float4 mul4(const float4 a, const float4 b) {
   return make_float4(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), __fmul_rn(a.w, b.w));
 }
 
+// score of anchor a for class c of one image (cls_scores = image base + c): the stored probability, or - LOGITS, four
+// aligned classes - the soft-max of the anchor's row of logits, recomputed as everywhere else (ssdx_softmax4)
+template <bool LOGITS>
+__device__ __forceinline__ float class_score(const float* __restrict__ cls_scores, const int a, const int C, const int c,
+                                             const float cf) {
+  if (LOGITS) {
+    const float4 p = ssdx_softmax4(__ldg(reinterpret_cast<const float4*>(cls_scores - c) + a));
+    return __fmul_rn(c == 0 ? p.x : (c == 1 ? p.y : (c == 2 ? p.z : p.w)), cf);
+  }
+  return __fmul_rn(__ldg(cls_scores + (size_t)a * C), cf);
+}
+
 // box normalised as TF does: (y0, x0, y1, x1) with y0<=y1, x0<=x1
 __device__ __forceinline__ float4 normalise_box(const float4 b) {
   return make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
@@ -515,6 +527,7 @@ __global__ void __launch_bounds__(kSelThreads)
 }
 
 // ------------------------------------------------------------------------------------------ 2. fast path
+template <bool LOGITS>  // LOGITS: `scores` holds raw logits of 4 classes (the refill scans recompute the soft-max rows)
 __global__ void __launch_bounds__(kFastThreads, 6)
     ssdx_nms_fast_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                          const float* __restrict__ cscale, const u64* __restrict__ lists, const int* __restrict__ info, const int A, const int C,
@@ -706,7 +719,7 @@ __global__ void __launch_bounds__(kFastThreads, 6)
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int a = a0 + u * kFastThreads;
-          sv[u] = (a < A) ? __fmul_rn(__ldg(img_scores + (size_t)a * C), cf) : -INFINITY;
+          sv[u] = (a < A) ? class_score<LOGITS>(img_scores, a, C, c, cf) : -INFINITY;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -1868,6 +1881,7 @@ __host__ __device__ inline size_t gen_smem_bytes(int A, int limit) {
   return s;
 }
 
+template <bool LOGITS>  // LOGITS: `scores` holds raw logits of 4 classes
 __global__ void __launch_bounds__(kGenThreads)
     ssdx_nms_generic_kernel(const ssdx_box_src boxes, const float* __restrict__ scores,
                             const float* __restrict__ cscale, const int A, const int C, const int limit, const float iou_thr, const float score_thr,
@@ -1909,7 +1923,7 @@ __global__ void __launch_bounds__(kGenThreads)
     int n = 0;
     unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
     for (int i = tid; i < A; i += kGenThreads) {
-      const float s = __fmul_rn(__ldg(img_scores + (size_t)i * C), cf);
+      const float s = class_score<LOGITS>(img_scores, i, C, c, cf);
       unsigned k = 0u;
       if (s > score_thr) {
         k = score_to_key(s);
@@ -2137,15 +2151,14 @@ static bool nms_merged_applies(const int A, const int C, const int max_per_class
          max_total <= kFastMaxSel;
 }
 
-// raw logits can be consumed directly (soft-max inside the kernels that read the scores): 4 aligned classes on the
-// merged pipeline, or on the per-class pipeline with caps small enough for the one-warp-per-segment kernel
+// raw logits can be consumed directly (soft-max inside every kernel that reads the scores) when they are rows of 4
+// aligned classes; otherwise ssdx_nms_logits materialises the probabilities first
 static bool nms_logits_fusable(const int A, const int C, const int max_per_class, const int max_total,
                                const float* logits) {
-  if (C != 4 || (((uintptr_t)logits & 15) != 0)) return false;
-  if (nms_merged_applies(A, C, max_per_class, max_total)) return true;
-  const char* force = ssdx_option_nms_path();
-  if (force != nullptr && (force[0] == 'g' || (force[0] == 'p' && force[1] == 'c'))) return false;
-  return (max_per_class < A ? max_per_class : A) <= 32;
+  (void)A;
+  (void)max_per_class;
+  (void)max_total;
+  return C == 4 && (((uintptr_t)logits & 15) == 0);
 }
 
 // phases: 1 = candidate selection (reads only the scores), 2 = everything that needs the boxes.  ssdx_nms runs both;
@@ -2300,8 +2313,8 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   SSDX_CHECK_ARG(gen_smem <= 227 * 1024,
                  "ssdx_nms: num_anchors=%d with max_per_class=%d needs %zu B of shared memory (limit 232448)", A,
                  max_per_class, gen_smem);
-  SSDX_CUDA(cudaFuncSetAttribute(ssdx_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)gen_smem));
+  SSDX_CUDA(cudaFuncSetAttribute(logits ? ssdx_nms_generic_kernel<true> : ssdx_nms_generic_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));
   // 1. select
   const bool use_fast = !force_generic;
   // first tier of a dense class: ~16 * rank candidates, sized to the per-class cap (a tier that runs dry is refilled
@@ -2351,15 +2364,24 @@ static int nms_run(const int phases, const int logits, const ssdx_box_src* fused
   if (use_fast) {
     // 2. fast path
     dim3 gseg(C, batch);
-    ssdx_nms_fast_kernel<<<gseg, kFastThreads, 0, s>>>(bx, scores, cscale, lists, info, A, C, limit, iou_threshold,
-                                                       score_threshold, picks, pick_cnt, flags);
+    if (logits)
+      ssdx_nms_fast_kernel<true><<<gseg, kFastThreads, 0, s>>>(bx, scores, cscale, lists, info, A, C, limit,
+                                                               iou_threshold, score_threshold, picks, pick_cnt, flags);
+    else
+      ssdx_nms_fast_kernel<false><<<gseg, kFastThreads, 0, s>>>(bx, scores, cscale, lists, info, A, C, limit,
+                                                                iou_threshold, score_threshold, picks, pick_cnt, flags);
     SSDX_LAUNCH_CHECK("ssdx_nms_fast_kernel");
   }
   // 3. generic path (flag-gated; handles every segment when the fast path is not applicable)
   const int gen_grid = use_fast ? min(num_segments, 2 * ssdx_sm_count(device)) : num_segments;
-  ssdx_nms_generic_kernel<<<gen_grid, kGenThreads, gen_smem, s>>>(bx, scores, cscale, A, C, limit, iou_threshold,
-                                                                  score_threshold, picks, pick_cnt,
-                                                                  use_fast ? flags : nullptr, num_segments);
+  if (logits)
+    ssdx_nms_generic_kernel<true><<<gen_grid, kGenThreads, gen_smem, s>>>(bx, scores, cscale, A, C, limit, iou_threshold,
+                                                                          score_threshold, picks, pick_cnt,
+                                                                          use_fast ? flags : nullptr, num_segments);
+  else
+    ssdx_nms_generic_kernel<false><<<gen_grid, kGenThreads, gen_smem, s>>>(bx, scores, cscale, A, C, limit, iou_threshold,
+                                                                           score_threshold, picks, pick_cnt,
+                                                                           use_fast ? flags : nullptr, num_segments);
   SSDX_LAUNCH_CHECK("ssdx_nms_generic_kernel");
   // 4. merge
   ssdx_nms_merge_kernel<<<batch, kMergeThreads, stage ? merge_smem : 0, s>>>(bx, picks, pick_cnt, A, C, limit,
@@ -2416,7 +2438,7 @@ extern "C" size_t ssdx_nms_logits_workspace_bytes(int32_t batch, int32_t num_anc
                                                   int32_t max_per_class, int32_t max_total) {
   const size_t base = ssdx_nms_workspace_bytes(batch, num_anchors, num_classes, max_per_class, max_total);
   if (base == 0) return 0;
-  // room to materialise the probabilities when the fused path does not apply (class count != 4, binding per-class cap)
+  // room to materialise the probabilities when the fused path does not apply (class count != 4, unaligned rows)
   return ssdx_align_up(base, 256) + ssdx_align_up((size_t)batch * num_anchors * num_classes * sizeof(float), 256);
 }
 
