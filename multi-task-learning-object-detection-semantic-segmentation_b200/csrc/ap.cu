@@ -11,7 +11,8 @@
 // hundred thousand predictions of an evaluation: 470 us for 819,200 of them):
 //   every prediction has the 64-bit composite  class << 56 | ~confidence key << 24 | index  (all distinct: ties in
 //   confidence fall in input order - NumPy's quicksort leaves them unspecified - and any sample splits evenly);
-//   A  one CTA sorts a strided sample of 4096 composites; every (4096 / S)-th one is a splitter;
+//   A  one CTA sorts a strided sample of 4096 composites (4 keys per thread: registers, shuffles, 25 shared-memory
+//      exchanges); every (4096 / S)-th one is a splitter;
 //   B  bucket of a prediction = (number of splitters <= composite) + class: monotone in the composite and one class
 //      per bucket; per (CTA, bucket) counts and per-bucket TP counts - every CTA owns a contiguous chunk;
 //   C  column scans over the CTAs (one warp per bucket), then one CTA: bucket offsets and per bucket the rank / TP
@@ -65,37 +66,70 @@ __device__ __forceinline__ int splitters_below(const u64* splitters, const int n
   return lo;
 }
 
-// A: splitters[k] = sorted sample[(k + 1) * ns / S], k < S - 1
+// A: splitters[k] = sorted sample[(k + 1) * ns / S], k < S - 1.  The 4096 sampled composites are sorted (ascending)
+// as 4 keys per thread of one 1024-thread CTA: exchange distances of 1024 and 2048 stay inside a thread, distances
+// below 32 are warp shuffles, only the 25 stages at distances 32..512 go through shared memory (a smem-only network
+// takes a barrier in each of its 78 stages: 41 us, the longest kernel of the AP tail).
 __global__ void __launch_bounds__(1024)
     ssdx_ap_sample_kernel(const float* __restrict__ conf, const int* __restrict__ label, const long long n, const int C,
                           const int bg, const int S, u64* __restrict__ splitters) {
+  static_assert(kSample == 4 * 1024, "4 keys per thread");
   __shared__ u64 s[kSample];
   const int tid = threadIdx.x;
   const int ns = (int)(n < kSample ? n : kSample);
-  for (int j = tid; j < kSample; j += 1024) {
-    u64 v = kPad;
+  u64 v[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {  // key e = r * 1024 + tid
+    const int j = r * 1024 + tid;
+    v[r] = kPad;
     if (j < ns) {
       const long long i = (long long)j * n / ns;
-      v = composite(scored_class(label[i], C, bg), conf[i], i);
+      v[r] = composite(scored_class(label[i], C, bg), conf[i], i);
     }
-    s[j] = v;
   }
-  __syncthreads();
-  // ascending bitonic sort, every thread a compare-exchange per step (kSample / 2 pairs over 1024 threads)
-  for (int k = 2; k <= kSample; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll
-      for (int t = tid; t < kSample / 2; t += 1024) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int p = i | j;
-        const u64 a = s[i], b = s[p];
-        if ((a > b) == ((i & k) == 0)) {
-          s[i] = b;
-          s[p] = a;
+  for (int k = 2; k <= kSample; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 1024) {  // both keys of a pair live in this thread
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int rp = r ^ (j >> 10);
+          if (rp > r) {
+            const bool up = (((r * 1024 + tid) & k) == 0);  // ascending block: the smaller key at the lower index
+            const u64 a = v[r], b = v[rp];
+            const bool swap = up ? (a > b) : (a < b);
+            v[r] = swap ? b : a;
+            v[rp] = swap ? a : b;
+          }
+        }
+      } else if (j < 32) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int e = r * 1024 + tid;
+          const u64 p = __shfl_xor_sync(0xFFFFFFFFu, v[r], j);
+          const bool take_min = (((e & j) == 0) == ((e & k) == 0));
+          v[r] = ((v[r] < p) == take_min) ? v[r] : p;  // (equal keys: either copy)
+        }
+      } else {
+        __syncthreads();  // the previous exchange has been read
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s[r * 1024 + tid] = v[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int e = r * 1024 + tid;
+          const u64 p = s[e ^ j];
+          const bool take_min = (((e & j) == 0) == ((e & k) == 0));
+          v[r] = ((v[r] < p) == take_min) ? v[r] : p;
         }
       }
-      __syncthreads();
     }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) s[r * 1024 + tid] = v[r];
+  __syncthreads();
   for (int k = tid; k < S - 1; k += 1024) splitters[k] = s[(int)(((long long)(k + 1) * ns) / S)];
 }
 
