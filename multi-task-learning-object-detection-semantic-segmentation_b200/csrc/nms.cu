@@ -372,6 +372,93 @@ __device__ __forceinline__ void fast_sort(u64* s_list, u64* s_tmp, const int n, 
   __syncthreads();
 }
 
+// Sort s_list[0..n), n <= 512, descending, by counting instead of a network (fast_all, ALGO 1): the keys are binned
+// by score key (256 bins over [min, max], a monotone map), a scan over the bins from the top gives every bin its base,
+// the keys are scattered bin by bin into s_tmp, and every key then counts the larger keys of its own bin: base + count
+// is its exact rank (the composites are distinct).  ~60 instructions per key and 6 barriers where the 512-key bitonic
+// network spends ~380 per key and 11; thousands of equal score keys (one bin) only cost the quadratic count.
+// s_bins: 512 words of scratch (counts, then bases), s_mm: 2 words (min / max key).
+template <int NT>
+__device__ __forceinline__ void rank_sort_512(u64* s_list, u64* s_tmp, unsigned* s_bins, unsigned* s_mm, const int n,
+                                              const int tid) {
+  constexpr int EPT = (512 + NT - 1) / NT;
+  const int lane = tid & 31;
+  u64 v[EPT];
+  unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+  for (int r = 0; r < EPT; ++r) {
+    const int e = r * NT + tid;
+    v[r] = (e < n) ? s_list[e] : 0ull;
+    if (e < n) {
+      kmin = min(kmin, (unsigned)(v[r] >> 32));
+      kmax = max(kmax, (unsigned)(v[r] >> 32));
+    }
+  }
+  if (tid < 256) s_bins[tid] = 0u;
+  if (tid == 0) {
+    s_mm[0] = 0xFFFFFFFFu;
+    s_mm[1] = 0u;
+  }
+  __syncthreads();
+  kmin = __reduce_min_sync(0xFFFFFFFFu, kmin);
+  kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+  if (lane == 0) {
+    atomicMin(&s_mm[0], kmin);
+    atomicMax(&s_mm[1], kmax);
+  }
+  __syncthreads();
+  kmin = s_mm[0];
+  kmax = s_mm[1];
+  // bin = floor((key - min) * 256 / (max - min + 1)) in fp32: conversion, product and truncation are all monotone
+  const float inv = __fdividef(256.0f, (float)(kmax - kmin) + 1.0f);
+  int bin[EPT], pos[EPT];
+#pragma unroll
+  for (int r = 0; r < EPT; ++r) {
+    bin[r] = 0;
+    pos[r] = 0;
+    if (r * NT + tid < n) {
+      bin[r] = min(255, (int)((float)((unsigned)(v[r] >> 32) - kmin) * inv));
+      pos[r] = (int)atomicAdd(&s_bins[bin[r]], 1u);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {  // bases: exclusive scan of the counts from the highest bin down; lane l owns bins 255 - 8 l - u
+    unsigned c[8], sum = 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      c[u] = s_bins[255 - 8 * lane - u];
+      sum += c[u];
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    unsigned base = incl - sum;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s_bins[256 + 255 - 8 * lane - u] = base;
+      base += c[u];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < EPT; ++r)
+    if (r * NT + tid < n) s_tmp[s_bins[256 + bin[r]] + pos[r]] = v[r];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < EPT; ++r) {
+    if (r * NT + tid < n) {
+      const int base = (int)s_bins[256 + bin[r]], cnt = (int)s_bins[bin[r]];
+      int larger = 0;
+      for (int i = 0; i < cnt; ++i) larger += s_tmp[base + i] > v[r];
+      s_list[base + larger] = v[r];
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------ 1. select
 // info per (image, class): [0] listed candidates (may exceed kCap), [2] threshold key (every candidate with key >= it
 // is listed).  Same scheme as the merged select below, per class: threshold = the kTierRank-th largest of the
@@ -1295,6 +1382,7 @@ __global__ void __launch_bounds__(NT, MINB)
   __shared__ unsigned s_keptw[8];  // ALGO 1: kept candidates of the chunk, one word per row group ...
   __shared__ int s_kbase[8];       // ... and the slot of the first kept box of each group
   __shared__ int s_nsel, s_n;
+  __shared__ unsigned s_mm[2];  // rank_sort_512: smallest / largest score key of the tier
   float4* s_cbox = reinterpret_cast<float4*>(s_tmp);                              // [kFastThreads]
   float* s_carea = reinterpret_cast<float*>(s_cbox + kFastThreads);               // [kFastThreads]
   unsigned char* s_ccls = reinterpret_cast<unsigned char*>(s_carea + kFastThreads);  // [kFastThreads]
@@ -1399,7 +1487,8 @@ __global__ void __launch_bounds__(NT, MINB)
       }
     }
     // ---- sort the current tier (merged order) ----
-    fast_sort<(NT >= 512 ? 512 : 256)>(s_list, s_tmp, n, tid);
+    if (ALGO == 1 && n <= 512) rank_sort_512<NT>(s_list, s_tmp, s_tile, s_mm, n, tid);  // (uniform)
+    else fast_sort<(NT >= 512 ? 512 : 256)>(s_list, s_tmp, n, tid);
     PHASE_ADD(11);  // sort
     if (span == 0ull) {  // band that held the lower half of this tier -> width expected to hold the refill target
       const u64 c_mid = (n >= 2) ? s_list[n >> 1] : 0ull;
