@@ -35,7 +35,8 @@
 //                    pass with a single compare per score; ~400 composites
 //                    (score key << 32 | ~class << 24 | ~anchor) per image.
 //   2m. fast_all   : one CTA per image, launched as a programmatic dependent of select_all: a tier above 512
-//                    candidates is trimmed by a bisection over the score keys; register bitonic sort; the sorted
+//                    candidates is trimmed by a bisection over the score keys; sort by counting (256 bins over the
+//                    score keys + exact rank inside the bin; bitonic network above 512 keys); the sorted
 //                    candidates are taken in chunks of up to 256: box gather, test against the boxes kept by
 //                    earlier chunks, the chunk against itself as 32 x 32 tiles of a lower-triangular bit matrix
 //                    (all warps, no barrier inside; fp16 prefilter boxes stored as column pairs, class folded in as
