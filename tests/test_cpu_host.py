@@ -457,3 +457,12 @@ def test_nccl_binding_is_optional_and_fails_cleanly(ssdseglib):
     with pytest.raises(ValueError):
         sx.set_option("encode_path", "no-such-path")
     sx.set_option("encode_path", "auto")
+    # dispatch pins of the NMS entry points: every documented value is accepted, anything else is refused
+    for key, values in (("nms_path", ("perclass", "pcta", "generic", "blocked", "auto")),
+                        ("nms_cta", ("256", "512", "1024", "auto"))):
+        for v in values:
+            sx.set_option(key, v)
+        with pytest.raises(ValueError):
+            sx.set_option(key, "300")
+    with pytest.raises(ValueError):
+        sx.set_option("no-such-key", "auto")
