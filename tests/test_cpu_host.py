@@ -466,3 +466,83 @@ def test_nccl_binding_is_optional_and_fails_cleanly(ssdseglib):
             sx.set_option(key, "300")
     with pytest.raises(ValueError):
         sx.set_option("no-such-key", "auto")
+
+
+# ---- design invariants of the merged NMS kernel, restated in NumPy (csrc/nms.cu: make_hbox_cls, class_unit, rank_sort_512)
+def _f16_down(x64):
+    """float64 -> float16 rounded towards -inf (what __float2half_rd(__fadd_rd(.)) yields for these exact sums)."""
+    with np.errstate(over="ignore"):  # (beyond the fp16 range: +-inf, stepped back to the largest finite value)
+        h = x64.astype(np.float16)
+    bad = h.astype(np.float64) > x64
+    h[bad] = np.nextafter(h[bad], np.float16(-np.inf))
+    return h
+
+
+def _f16_up(x64):
+    with np.errstate(over="ignore"):
+        h = x64.astype(np.float16)
+    bad = h.astype(np.float64) < x64
+    h[bad] = np.nextafter(h[bad], np.float16(np.inf))
+    return h
+
+
+def _class_unit(ext):
+    e = int((np.float32(ext).view(np.uint32) >> 23) & 0xFF) - 127 + 2
+    return np.float64(2.0 ** min(max(e, -8), 14))
+
+
+@pytest.mark.parametrize("scale", [1.0, 640.0, 3000.0])
+def test_class_shifted_fp16_prefilter_is_conservative_and_separates_classes(scale):
+    """Prefilter of ssdx_nms_fast_all_kernel: boxes of class c are shifted by unit * (c & 15, c >> 4) and rounded
+    outwards to fp16.  (1) Same class: exact fp32 overlap implies prefilter overlap (never a false negative).
+    (2) Different classes: no pair passes while the shifted coordinates stay inside the fp16 range."""
+    rng = np.random.default_rng(int(scale))
+    n, C = 400, 40
+    c0 = rng.uniform(-0.2, 1.2, size=(n, 2)) * scale
+    wh = rng.uniform(0.0, 0.5, size=(n, 2)) * scale
+    box = np.concatenate([c0 - wh / 2, c0 + wh / 2], 1).astype(np.float32)  # normalised (y0, x0, y1, x1)
+    box[::7, 2] = box[::7, 0]  # degenerate
+    cls = rng.integers(0, C, size=n)
+    unit = _class_unit(np.abs(box).max())
+    oy, ox = unit * (cls & 15), unit * (cls >> 4)
+    b64 = box.astype(np.float64)
+    mn = np.stack([_f16_down(b64[:, 0] + oy), _f16_down(b64[:, 1] + ox)], 1).astype(np.float64)
+    mx = np.stack([_f16_up(b64[:, 2] + oy), _f16_up(b64[:, 3] + ox)], 1).astype(np.float64)
+    pre = ((mx[:, None, 0] > mn[None, :, 0]) & (mx[None, :, 0] > mn[:, None, 0]) &
+           (mx[:, None, 1] > mn[None, :, 1]) & (mx[None, :, 1] > mn[:, None, 1]))
+    exact = ((box[:, None, 2] > box[None, :, 0]) & (box[None, :, 2] > box[:, None, 0]) &
+             (box[:, None, 3] > box[None, :, 1]) & (box[None, :, 3] > box[:, None, 1]))
+    same = cls[:, None] == cls[None, :]
+    assert not np.any(exact & same & ~pre)
+    in_range = 15 * unit + np.abs(box).max() < 65504  # (beyond it the shifts saturate: only more exact tests)
+    if in_range:
+        assert not np.any(pre & ~same)
+    else:
+        assert scale == 3000.0
+
+
+def test_rank_sort_bins_are_monotone_and_ranks_exact():
+    """rank_sort_512 (csrc/nms.cu): bin = min(255, int(float32(key - kmin) * inv)) must be non-decreasing in the key, so
+    that (keys in higher bins) + (larger keys in the own bin) is the exact descending rank."""
+    rng = np.random.default_rng(5)
+    for trial in range(50):
+        n = int(rng.integers(2, 513))
+        kind = trial % 4
+        if kind == 0:
+            hi = rng.integers(0x80000000, 0xBF800000, size=n, dtype=np.uint64)          # any positive score
+        elif kind == 1:
+            hi = np.uint64(0xBF000000) + rng.integers(0, 4096, size=n, dtype=np.uint64)  # crowded
+        elif kind == 2:
+            hi = np.full(n, 0xBF7FFFFF, np.uint64)                                       # all equal
+        else:
+            hi = rng.choice(np.array([1, 0x80000000, 0xFF7FFFFF, 0xFF800000], np.uint64), size=n)  # extremes
+        lo = rng.permutation(1 << 20)[:n].astype(np.uint64)                               # distinct composites
+        keys = (hi << np.uint64(32)) | lo
+        kmin, kmax = hi.min(), hi.max()
+        inv = np.float32(256.0) / (np.float32(np.float32(kmax - kmin)) + np.float32(1.0))
+        bins = np.minimum(255, (np.float32((hi - kmin).astype(np.float32)) * inv).astype(np.int64))
+        order = np.argsort(hi, kind="stable")
+        assert np.all(np.diff(bins[order]) >= 0)
+        rank = np.array([(bins > bins[i]).sum() + ((bins == bins[i]) & (keys > keys[i])).sum() for i in range(n)])
+        assert np.array_equal(np.sort(rank), np.arange(n))
+        assert np.array_equal(keys[np.argsort(rank)], np.sort(keys)[::-1])
