@@ -546,3 +546,55 @@ def test_rank_sort_bins_are_monotone_and_ranks_exact():
         rank = np.array([(bins > bins[i]).sum() + ((bins == bins[i]) & (keys > keys[i])).sum() for i in range(n)])
         assert np.array_equal(np.sort(rank), np.arange(n))
         assert np.array_equal(keys[np.argsort(rank)], np.sort(keys)[::-1])
+
+
+def test_chunk_fix_point_equals_sequential_greedy():
+    """Resolve step of ssdx_nms_fast_all_kernel (csrc/nms.cu, step (c)): 64 candidates at a time, candidates suppressed
+    by boxes kept in earlier 64-blocks are marked first, then rounds of: undecided + a kept suppressor -> suppressed;
+    undecided + every suppressor decided as suppressed -> kept.  Must equal the sequential greedy pass."""
+    rng = np.random.default_rng(17)
+    for trial in range(40):
+        m = int(rng.integers(1, 257))
+        dens = float(rng.choice([0.0, 0.01, 0.05, 0.3, 0.9]))
+        M = np.tril(rng.random((m, m)) < dens, -1)            # M[i, j]: earlier candidate j suppresses i when kept
+        pre = rng.random(m) < float(rng.choice([0.0, 0.2]))   # suppressed by boxes of earlier chunks
+        kept_seq = np.zeros(m, bool)
+        for i in range(m):
+            kept_seq[i] = not pre[i] and not np.any(M[i, :i] & kept_seq[:i])
+        kept = np.zeros(m, bool)
+        for s0 in range(0, m, 64):
+            blk = slice(s0, min(s0 + 64, m))
+            sup = pre[blk] | np.any(M[blk, :s0] & kept[None, :s0], axis=1)
+            k = np.zeros(sup.size, bool)
+            Mb = M[blk, blk]
+            rounds = 0
+            while not np.all(k | sup):
+                und = ~(k | sup)
+                hit = np.any(Mb & k[None, :], axis=1)
+                free = ~np.any(Mb & ~sup[None, :], axis=1)
+                new_k, new_s = und & ~hit & free, und & hit
+                assert new_k.any() or new_s.any()               # the lowest undecided candidate is always decided
+                k |= new_k
+                sup |= new_s
+                rounds += 1
+            kept[blk] = k
+        assert np.array_equal(kept, kept_seq)
+
+
+def test_sample_sort_network_sorts():
+    """Exchange pattern of ssdx_ap_sample_kernel (csrc/ap.cu): 4096 keys, key e = r * 1024 + tid, stage (k, j) pairs e
+    with e ^ j and keeps the minimum where ((e & j) == 0) == ((e & k) == 0): ascending order at the end."""
+    rng = np.random.default_rng(23)
+    v = rng.integers(0, 1 << 62, size=4096, dtype=np.int64)
+    v[0:4000:5] = v[1:4001:5]  # duplicates
+    e = np.arange(4096)
+    k = 2
+    while k <= 4096:
+        j = k >> 1
+        while j > 0:
+            p = v[e ^ j]
+            take_min = ((e & j) == 0) == ((e & k) == 0)
+            v = np.where(take_min, np.minimum(v, p), np.maximum(v, p))
+            j >>= 1
+        k <<= 1
+    assert np.all(np.diff(v) >= 0)
